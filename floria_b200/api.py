@@ -1,0 +1,317 @@
+"""ctypes host binding of libfloria_b200.so (the C-ABI of include/floria_b200.h).
+
+Method names mirror the reference's pub fns (src/lib.rs:1-23) for the hot path so parity tests read like calls
+into floria itself.  The library is the only compute path: loading fails loudly when the CUDA build is missing
+and fb_init fails when there is no device (no CPU fallback).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from ._cdefs import (
+    BlockResults,
+    FbBlockResults,
+    FbFrags,
+    FbParams,
+    FbParts,
+    FbTimings,
+    Parts,
+    default_params,
+    f64p,
+    i64p,
+    ptr,
+    u8p,
+    u32p,
+    u64p,
+)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfloria_b200.so")
+
+EXPORTS = [
+    "fb_init", "fb_destroy", "fb_last_error", "fb_params_default", "fb_last_timings", "fb_stream",
+    "fb_frags_upload", "fb_frags_free", "fb_dfrags_bytes", "fb_get_range_with_lengths",
+    "fb_find_reads_in_interval", "fb_phase_blocks", "fb_phase_blocks_resident", "fb_free_block_results",
+    "fb_score_reads", "fb_hap_block_from_partition", "fb_get_mec_stats_epsilon", "fb_beam_search_phasing",
+    "fb_optimize_clustering", "fb_process_reads_for_final_parts", "fb_free_parts", "fb_get_hapq",
+    "fb_update_hap_graph",
+]
+
+_lib = None
+
+
+class FloriaB200Error(RuntimeError):
+    pass
+
+
+def load_library():
+    """dlopen the CUDA library; raises if it has not been built (python -m floria_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FloriaB200Error(
+            f"{LIB_PATH} is missing: build it with `python -m floria_b200.build` (nvcc, sm_100a). "
+            "There is no CPU fallback."
+        )
+    L = C.CDLL(LIB_PATH)
+    L.fb_last_error.restype = C.c_char_p
+    L.fb_last_error.argtypes = [C.c_void_p]
+    L.fb_init.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.fb_destroy.argtypes = [C.c_void_p]
+    L.fb_stream.restype = C.c_void_p
+    L.fb_stream.argtypes = [C.c_void_p]
+    L.fb_last_timings.argtypes = [C.c_void_p, C.POINTER(FbTimings)]
+    L.fb_frags_upload.argtypes = [C.c_void_p, C.POINTER(FbFrags), C.POINTER(C.c_void_p)]
+    L.fb_frags_free.argtypes = [C.c_void_p, C.c_void_p]
+    L.fb_dfrags_bytes.restype = C.c_uint64
+    L.fb_dfrags_bytes.argtypes = [C.c_void_p]
+    L.fb_get_range_with_lengths.restype = C.c_int64
+    L.fb_get_range_with_lengths.argtypes = [u64p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, u32p, u32p,
+                                            C.c_uint64]
+    L.fb_find_reads_in_interval.restype = C.c_int64
+    L.fb_find_reads_in_interval.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, u32p, u32p, u32p, C.c_uint64]
+    L.fb_phase_blocks.argtypes = [C.c_void_p, C.POINTER(FbFrags), C.c_uint64, u32p, u32p, C.POINTER(FbParams),
+                                  C.POINTER(C.POINTER(FbBlockResults))]
+    L.fb_phase_blocks_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, u32p, u32p, C.POINTER(FbParams),
+                                           C.POINTER(C.POINTER(FbBlockResults))]
+    L.fb_free_block_results.argtypes = [C.POINTER(FbBlockResults)]
+    L.fb_score_reads.argtypes = [C.c_void_p, C.POINTER(FbFrags), C.c_uint64, u32p, u8p, C.c_uint32,
+                                 C.POINTER(FbParams), f64p, f64p, i64p, i64p, u32p]
+    L.fb_hap_block_from_partition.argtypes = [C.c_void_p, C.POINTER(FbFrags), C.c_uint64, u32p, u8p, C.c_uint32,
+                                              C.c_int, C.POINTER(FbParams), C.c_uint32, C.c_uint32, f64p, u8p]
+    L.fb_get_mec_stats_epsilon.argtypes = [C.c_void_p, C.POINTER(FbFrags), C.c_uint64, u32p, u8p, C.c_uint32,
+                                           C.c_int, C.POINTER(FbParams), f64p, f64p]
+    L.fb_beam_search_phasing.argtypes = [C.c_void_p, C.POINTER(FbFrags), C.c_uint64, u32p, C.c_uint32,
+                                         C.POINTER(FbParams), u8p, f64p, f64p, f64p, f64p, C.c_uint64, u64p]
+    L.fb_optimize_clustering.argtypes = [C.c_void_p, C.POINTER(FbFrags), C.c_uint64, u32p, u8p, C.c_uint32,
+                                         C.POINTER(FbParams), u8p, f64p, u32p]
+    L.fb_process_reads_for_final_parts.argtypes = [C.c_void_p, C.POINTER(FbFrags), C.c_uint64, u64p, u32p, u32p,
+                                                   u32p, C.POINTER(FbParams), C.POINTER(C.POINTER(FbParts))]
+    L.fb_free_parts.argtypes = [C.POINTER(FbParts)]
+    L.fb_get_hapq.argtypes = [C.c_void_p, C.POINTER(FbFrags), C.c_uint64, u64p, u32p, u32p, u32p, u64p, C.c_uint64,
+                              C.POINTER(FbParams), u8p, f64p, f64p]
+    L.fb_update_hap_graph.argtypes = [C.c_void_p, C.POINTER(FbFrags), C.c_uint64, u64p, u64p, u32p, u32p, u32p,
+                                      C.POINTER(FbParams), f64p]
+    _lib = L
+    return L
+
+
+def get_range_with_lengths(snp_to_genome_pos, block_length, overlap_len, minimal_density):
+    """utils_frags.rs:405-463 (host-side; defines the work units)."""
+    L = load_library()
+    g = np.ascontiguousarray(snp_to_genome_pos, dtype=np.uint64)
+    cap = len(g) + 1
+    lo = np.zeros(cap, np.uint32)
+    hi = np.zeros(cap, np.uint32)
+    n = L.fb_get_range_with_lengths(ptr(g, u64p), len(g), block_length, overlap_len, minimal_density, ptr(lo, u32p),
+                                    ptr(hi, u32p), cap)
+    if n < 0:
+        raise FloriaB200Error("VCF malformed. Positions are not increasing")
+    return lo[:n].copy(), hi[:n].copy()
+
+
+def find_reads_in_interval(start, end, frags):
+    """local_clustering.rs:12-59."""
+    L = load_library()
+    out = np.zeros(max(frags.n_reads, 1), np.uint32)
+    n = L.fb_find_reads_in_interval(start, end, frags.n_reads, ptr(frags.first, u32p), ptr(frags.last, u32p),
+                                    ptr(out, u32p), len(out))
+    return out[:n].copy()
+
+
+class DeviceFrags:
+    def __init__(self, ctx, handle, frags):
+        self.ctx = ctx
+        self.handle = handle
+        self.frags = frags
+
+    @property
+    def nbytes(self):
+        return int(self.ctx.L.fb_dfrags_bytes(self.handle))
+
+    def free(self):
+        if self.handle:
+            self.ctx.L.fb_frags_free(self.ctx.h, self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    def __init__(self, device=0):
+        self.L = load_library()
+        h = C.c_void_p()
+        rc = self.L.fb_init(device, C.byref(h))
+        if rc != 0:
+            raise FloriaB200Error(f"fb_init failed ({rc}): " + self.L.fb_last_error(None).decode())
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.fb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise FloriaB200Error(f"floria_b200 error {rc}: " + self.L.fb_last_error(self.h).decode())
+
+    @property
+    def stream(self):
+        return self.L.fb_stream(self.h)
+
+    def timings(self):
+        t = FbTimings()
+        self._chk(self.L.fb_last_timings(self.h, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in FbTimings._fields_}
+
+    # ---- data movement ----
+    def upload(self, frags):
+        fs = frags.as_struct()
+        out = C.c_void_p()
+        self._chk(self.L.fb_frags_upload(self.h, C.byref(fs), C.byref(out)))
+        return DeviceFrags(self, out, frags)
+
+    # ---- batched hot path ----
+    def phase_blocks(self, frags, blk_lo, blk_hi, params):
+        lo = np.ascontiguousarray(blk_lo, dtype=np.uint32)
+        hi = np.ascontiguousarray(blk_hi, dtype=np.uint32)
+        out = C.POINTER(FbBlockResults)()
+        fs = frags.as_struct()
+        self._chk(self.L.fb_phase_blocks(self.h, C.byref(fs), len(lo), ptr(lo, u32p), ptr(hi, u32p), C.byref(params),
+                                         C.byref(out)))
+        res = BlockResults(out.contents)
+        self.L.fb_free_block_results(out)
+        return res
+
+    def phase_blocks_resident(self, dfrags, blk_lo, blk_hi, params):
+        lo = np.ascontiguousarray(blk_lo, dtype=np.uint32)
+        hi = np.ascontiguousarray(blk_hi, dtype=np.uint32)
+        out = C.POINTER(FbBlockResults)()
+        self._chk(self.L.fb_phase_blocks_resident(self.h, dfrags.handle, len(lo), ptr(lo, u32p), ptr(hi, u32p),
+                                                  C.byref(params), C.byref(out)))
+        res = BlockResults(out.contents)
+        self.L.fb_free_block_results(out)
+        return res
+
+    # ---- fine-grained entry points ----
+    def score_reads(self, frags, sel, hap, ploidy, params):
+        sel = np.ascontiguousarray(sel, dtype=np.uint32)
+        hap = np.ascontiguousarray(hap, dtype=np.uint8)
+        n = len(sel)
+        same = np.zeros((n, ploidy))
+        diff = np.zeros((n, ploidy))
+        sq = np.zeros((n, ploidy), np.int64)
+        dq = np.zeros((n, ploidy), np.int64)
+        ne = np.zeros((n, ploidy), np.uint32)
+        fs = frags.as_struct()
+        self._chk(self.L.fb_score_reads(self.h, C.byref(fs), n, ptr(sel, u32p), ptr(hap, u8p), ploidy,
+                                        C.byref(params), ptr(same, f64p), ptr(diff, f64p), ptr(sq, i64p),
+                                        ptr(dq, i64p), ptr(ne, u32p)))
+        return same, diff, sq, dq, ne
+
+    def hap_block_from_partition(self, frags, sel, hap, ploidy, use_qual, params, pos_lo, n_pos):
+        sel = np.ascontiguousarray(sel, dtype=np.uint32)
+        hap = np.ascontiguousarray(hap, dtype=np.uint8)
+        counts = np.zeros((ploidy, n_pos, 4))
+        mask = np.zeros((ploidy, n_pos), np.uint8)
+        fs = frags.as_struct()
+        self._chk(self.L.fb_hap_block_from_partition(self.h, C.byref(fs), len(sel), ptr(sel, u32p), ptr(hap, u8p),
+                                                     ploidy, int(use_qual), C.byref(params), pos_lo, n_pos,
+                                                     ptr(counts, f64p), ptr(mask, u8p)))
+        return counts, mask
+
+    def get_mec_stats_epsilon(self, frags, sel, hap, ploidy, use_phred, params):
+        sel = np.ascontiguousarray(sel, dtype=np.uint32)
+        hap = np.ascontiguousarray(hap, dtype=np.uint8)
+        bases = np.zeros(ploidy)
+        errors = np.zeros(ploidy)
+        fs = frags.as_struct()
+        self._chk(self.L.fb_get_mec_stats_epsilon(self.h, C.byref(fs), len(sel), ptr(sel, u32p), ptr(hap, u8p),
+                                                  ploidy, int(use_phred), C.byref(params), ptr(bases, f64p),
+                                                  ptr(errors, f64p)))
+        return bases, errors
+
+    def beam_search_phasing(self, frags, sel, ploidy, params, tap_cap=0):
+        sel = np.ascontiguousarray(sel, dtype=np.uint32)
+        hap = np.zeros(max(len(sel), 1), np.uint8)
+        score = C.c_double(0)
+        tn = C.c_uint64(0)
+        ts = np.zeros(max(tap_cap, 1))
+        td = np.zeros(max(tap_cap, 1))
+        tp = np.zeros(max(tap_cap, 1))
+        fs = frags.as_struct()
+        self._chk(self.L.fb_beam_search_phasing(self.h, C.byref(fs), len(sel), ptr(sel, u32p), ploidy,
+                                                C.byref(params), ptr(hap, u8p), C.byref(score), ptr(ts, f64p),
+                                                ptr(td, f64p), ptr(tp, f64p), tap_cap, C.byref(tn)))
+        n = min(int(tn.value), tap_cap)
+        return hap[: len(sel)], score.value, (ts[:n], td[:n], tp[:n], int(tn.value))
+
+    def optimize_clustering(self, frags, sel, hap_in, ploidy, params):
+        sel = np.ascontiguousarray(sel, dtype=np.uint32)
+        hap_in = np.ascontiguousarray(hap_in, dtype=np.uint8)
+        hap = np.zeros(max(len(sel), 1), np.uint8)
+        score = C.c_double(0)
+        nr = C.c_uint32(0)
+        fs = frags.as_struct()
+        self._chk(self.L.fb_optimize_clustering(self.h, C.byref(fs), len(sel), ptr(sel, u32p), ptr(hap_in, u8p),
+                                                ploidy, C.byref(params), ptr(hap, u8p), C.byref(score),
+                                                C.byref(nr)))
+        return hap[: len(sel)], score.value, int(nr.value)
+
+    def process_reads_for_final_parts(self, frags, part_ptr, part_reads, range_lo, range_hi, params):
+        pp = np.ascontiguousarray(part_ptr, np.uint64)
+        pr = np.ascontiguousarray(part_reads, np.uint32)
+        rl = np.ascontiguousarray(range_lo, np.uint32)
+        rh = np.ascontiguousarray(range_hi, np.uint32)
+        out = C.POINTER(FbParts)()
+        fs = frags.as_struct()
+        self._chk(self.L.fb_process_reads_for_final_parts(self.h, C.byref(fs), len(pp) - 1, ptr(pp, u64p),
+                                                          ptr(pr, u32p), ptr(rl, u32p), ptr(rh, u32p),
+                                                          C.byref(params), C.byref(out)))
+        res = Parts(out.contents)
+        self.L.fb_free_parts(out)
+        return res
+
+    def get_hapq(self, frags, part_ptr, part_reads, range_lo, range_hi, snp_to_genome_pos, params):
+        pp = np.ascontiguousarray(part_ptr, np.uint64)
+        pr = np.ascontiguousarray(part_reads, np.uint32)
+        rl = np.ascontiguousarray(range_lo, np.uint32)
+        rh = np.ascontiguousarray(range_hi, np.uint32)
+        g = np.ascontiguousarray(snp_to_genome_pos, np.uint64)
+        n = len(pp) - 1
+        hapq = np.zeros(max(n, 1), np.uint8)
+        rel = np.zeros(max(n, 1))
+        avg = C.c_double(0)
+        fs = frags.as_struct()
+        self._chk(self.L.fb_get_hapq(self.h, C.byref(fs), n, ptr(pp, u64p), ptr(pr, u32p), ptr(rl, u32p),
+                                     ptr(rh, u32p), ptr(g, u64p), len(g), C.byref(params), ptr(hapq, u8p),
+                                     ptr(rel, f64p), C.byref(avg)))
+        return hapq[:n], rel[:n], avg.value
+
+    def update_hap_graph(self, frags, col_ptr, node_ptr, node_reads, node_lo, node_hi, params):
+        cp = np.ascontiguousarray(col_ptr, np.uint64)
+        npt = np.ascontiguousarray(node_ptr, np.uint64)
+        nr = np.ascontiguousarray(node_reads, np.uint32)
+        nl = np.ascontiguousarray(node_lo, np.uint32)
+        nh = np.ascontiguousarray(node_hi, np.uint32)
+        n_cols = len(cp) - 1
+        tot = sum(int(cp[i + 1] - cp[i]) * int(cp[i + 2] - cp[i + 1]) for i in range(n_cols - 1))
+        out = np.zeros(max(tot, 1))
+        fs = frags.as_struct()
+        self._chk(self.L.fb_update_hap_graph(self.h, C.byref(fs), n_cols, ptr(cp, u64p), ptr(npt, u64p),
+                                             ptr(nr, u32p), ptr(nl, u32p), ptr(nh, u32p), C.byref(params),
+                                             ptr(out, f64p)))
+        return out[:tot]

@@ -1,0 +1,55 @@
+"""Builds floria_b200/libfloria_b200.so (CUDA, sm_100a) in-tree with nvcc.  `python -m floria_b200.build`."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libfloria_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
+    "-Xcompiler", "-fPIC,-O3,-Wall", "--fmad=false", "-Xptxas", "-v",
+]
+
+
+def sources():
+    return [os.path.join(CSRC, "fb_lib.cu")]
+
+
+def stale():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "floria_b200.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not stale():
+        return OUT
+    cmd = [NVCC] + FLAGS + ["-o", OUT] + sources()
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed")
+    with open(os.path.join(HERE, "build_ptxas.log"), "w") as fh:
+        fh.write(res.stdout + res.stderr)
+    return OUT
+
+
+def build_hosttest(force=False):
+    """CPU build of fb_seq.h's host-compilable logic (unit tests only)."""
+    out = os.path.join(HERE, "libfb_hosttest.so")
+    src = os.path.join(CSRC, "fb_hosttest.cpp")
+    if force or not os.path.exists(out) or os.path.getmtime(out) < max(
+            os.path.getmtime(src), os.path.getmtime(os.path.join(CSRC, "fb_seq.h"))):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", out, src])
+    return out
+
+
+if __name__ == "__main__":
+    build_hosttest(force="--force" in sys.argv)
+    build(force="--force" in sys.argv, verbose=True)
+    print(OUT)

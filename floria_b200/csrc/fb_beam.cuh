@@ -1,0 +1,751 @@
+// fb_beam.cuh — K5/K6: beam_search_phasing (global_clustering.rs:10-179) as a persistent kernel.
+//
+// One CTA runs one (block, ploidy) instance from first read to backtrack; CTAs pull instances from a work queue
+// (largest first).  The reference keeps, per search node, a deep copy of `ploidy` nested hash maps
+// (types_structs.rs:326-376 build_truncated_hap_block).  Here a node is `ploidy` references into a pool of dense
+// HAPLOTYPE STATES (counts [pos][4] + is-max planes), shared copy-on-write between nodes:
+//   * a child (node n, read -> hap j) differs from its parent in ONE state: ref[n][j] + read;
+//   * children are scored, de-duplicated and pushed through an exact emulation of Rust's BinaryHeap BEFORE any state is
+//     materialised; only the states of the surviving generation are built (in place when nothing else still needs the
+//     parent state);
+//   * HapBlock equality (global_clustering.rs:123-127) is decided exactly: a linear hash of the in-window counts
+//     (H = sum G(pos,allele) * count mod 2^64, so H(state + read) = H(state) + delta(read)) filters candidates, and
+//     every hash match is verified word by word on the virtual states;
+//   * the sliding window (positions < current read's first SNP are dropped, types_structs.rs:346-360) never needs
+//     a physical truncation: reads arrive sorted by first position, so dropped positions are never scored again;
+//     they are removed from the hashes and excluded from the equality test.
+// Heap order, `<=` tie behaviour, the width rule (ploidy*B for the first 25 reads), pruning by p - lse > ln(0.01) and
+// the final into_sorted_vec()[0] + parent walk follow the reference line by line (see fb_seq.h for the heap).
+#pragma once
+#include <limits.h>
+
+#include <vector>
+
+#include "fb_common.cuh"
+#include "fb_kernels.cuh"
+
+#define FB_BEAM_THREADS 256
+#define FB_BEAM_WARPS (FB_BEAM_THREADS / 32)
+
+struct BeamTapDev {
+    double *same, *diff, *logp;
+    unsigned long long cap;
+};
+
+struct BeamParams {
+    DFragsDev fr;
+    const InstDev *inst;
+    const RInfo *rinfo;
+    const uint32_t *lut;
+    const int *order;  // instance indices to run, largest first
+    int n_work;
+    int *work_counter;
+    uint8_t *assign_out;  // engine assign buffer 0
+    double eps, div_factor, cutoff;
+    int eps_safe;
+    uint32_t B;           // max_number_solns
+    uint32_t maxP, maxW, maxNS;
+    uint8_t *scratch;     // per-CTA slots
+    uint64_t slot_bytes;  // pool + history
+    uint64_t hist_off;    // offset of the history array inside a slot
+    unsigned long long *cells_out;  // [n_inst]
+    double *best_out;               // [n_inst]
+    unsigned long long *tapn_out;   // [n_inst]
+    BeamTapDev tap;                 // only meaningful for single-instance calls
+};
+
+// shared-memory carve-up (same arithmetic on host and device)
+struct BeamSmem {
+    uint32_t off_nd_score, off_nd_err, off_nd_ref, off_st_hash, off_sc_same, off_sc_diff, off_st_hi, off_st_mark,
+        off_free, off_live, off_ch_score, off_ch_parent, off_ch_part, off_ch_class, off_ch_diff, off_hp_score,
+        off_hp_item, off_lut, off_wscr, off_misc, off_job, off_addnew, off_plain, total;
+    __host__ __device__ void layout(uint32_t P, uint32_t W, uint32_t NS) {
+        uint32_t o = 0;
+        auto take = [&](uint32_t bytes) {
+            uint32_t r = o;
+            o += (bytes + 15u) & ~15u;
+            return r;
+        };
+        off_nd_score = take(2 * W * 8);
+        off_nd_err = take(2 * W * P * 8);
+        off_nd_ref = take(2 * W * P * 2);
+        off_st_hash = take(NS * 8);
+        off_sc_same = take(NS * 8);
+        off_sc_diff = take(NS * 8);
+        off_st_hi = take(NS * 4);
+        off_st_mark = take(NS * 4);
+        off_free = take(NS * 4);
+        off_live = take(NS * 4);
+        off_ch_score = take(W * P * 8);
+        off_ch_diff = take(W * P * 8);
+        off_ch_parent = take(W * P * 2);
+        off_ch_part = take(W * P * 2);
+        off_ch_class = take(W * P * 2);
+        off_hp_score = take((W + 2) * 8);
+        off_hp_item = take((W + 2) * 4);
+        off_lut = take(256 * 4);
+        off_wscr = take(FB_BEAM_WARPS * 16 * 4);
+        off_misc = take(256);
+        off_job = take((W + 1) * 16);
+        off_addnew = take(NS * 4);
+        off_plain = take(NS * 4);
+        total = o;
+    }
+};
+
+// exact left-to-right f64 sum of the diff/epsilon items of one read vs one state (canonical order); state planes
+// beyond `hi` are empty.  Warp-cooperative; returns the same value on every lane.
+__device__ double fb_replay_diff_state(const DFragsDev &fr, uint32_t g0, uint32_t g1, const uint2 *__restrict__ mh,
+                                       uint32_t lg0, int hi, const uint32_t *lut, double eps, uint32_t *wscratch) {
+    const uint32_t lane = fb_lane();
+    SeqSum ss;
+    ss.init();
+    for (uint32_t base = g0; base < g1; base += 32) {
+        uint32_t g = base + lane;
+        bool valid = g < g1;
+        uint32_t w[16];
+        uint32_t diffbits = 0, emptybits = 0;
+        if (valid) {
+            uint4 q = fr.qual[g];
+            uint32_t al = fr.allele[g];
+            uint32_t pr = fr.present[g];
+            fb_group_weights(q, pr, lut, w);
+            uint32_t lg = lg0 + (g - g0);
+            uint2 m = ((int)lg <= hi) ? mh[lg] : make_uint2(0u, 0u);
+            uint32_t same, ne;
+            fb_group_masks(al, m, same, ne);
+            diffbits = pr & ne & ~same;
+            emptybits = pr & ~ne & 0xFFFFu;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) w[k] = 0;
+        }
+        long long Wl = (long long)fb_masked_sum(w, diffbits);
+        unsigned anyE = __ballot_sync(0xFFFFFFFFu, emptybits != 0);
+        if (!anyE) {
+            long long tot = (long long)fb_warp_sum_u64((unsigned long long)Wl);
+            if (ss.add_dyadic_run(tot)) continue;
+        }
+        for (int l = 0; l < 32; ++l) {
+            long long Wl_l = __shfl_sync(0xFFFFFFFFu, Wl, l);
+            uint32_t eb = __shfl_sync(0xFFFFFFFFu, emptybits, l);
+            uint32_t db = __shfl_sync(0xFFFFFFFFu, diffbits, l);
+            if (eb == 0) {
+                if (ss.add_dyadic_run(Wl_l)) continue;
+            }
+            __syncwarp();
+            if (lane == l) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) wscratch[k] = w[k];
+            }
+            __syncwarp();
+            uint32_t bits = eb | db;
+            while (bits) {
+                int k = __ffs(bits) - 1;
+                bits &= bits - 1;
+                if ((eb >> k) & 1u)
+                    ss.add_eps(eps, 0);
+                else
+                    ss.add_dyadic((long long)wscratch[k]);
+            }
+        }
+    }
+    return ss.S;
+}
+
+struct BeamJob {
+    uint32_t src, dst, inplace, _pad;
+};
+
+__global__ void __launch_bounds__(FB_BEAM_THREADS) k_beam(BeamParams bp) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ int s_work;
+    const int tid = threadIdx.x;
+    const uint32_t lane = tid & 31, warp = tid >> 5;
+
+    BeamSmem L;
+    L.layout(bp.maxP, bp.maxW, bp.maxNS);
+    double *nd_score = reinterpret_cast<double *>(smem + L.off_nd_score);     // [2][W]
+    double *nd_err = reinterpret_cast<double *>(smem + L.off_nd_err);         // [2][W][P]
+    uint16_t *nd_ref = reinterpret_cast<uint16_t *>(smem + L.off_nd_ref);     // [2][W][P]
+    unsigned long long *st_hash = reinterpret_cast<unsigned long long *>(smem + L.off_st_hash);
+    double *sc_same = reinterpret_cast<double *>(smem + L.off_sc_same);
+    double *sc_diff = reinterpret_cast<double *>(smem + L.off_sc_diff);
+    int *st_hi = reinterpret_cast<int *>(smem + L.off_st_hi);
+    int *st_mark = reinterpret_cast<int *>(smem + L.off_st_mark);
+    int *st_free = reinterpret_cast<int *>(smem + L.off_free);
+    int *live = reinterpret_cast<int *>(smem + L.off_live);
+    double *ch_score = reinterpret_cast<double *>(smem + L.off_ch_score);
+    double *ch_diff = reinterpret_cast<double *>(smem + L.off_ch_diff);
+    uint16_t *ch_parent = reinterpret_cast<uint16_t *>(smem + L.off_ch_parent);
+    uint16_t *ch_part = reinterpret_cast<uint16_t *>(smem + L.off_ch_part);
+    uint16_t *ch_class = reinterpret_cast<uint16_t *>(smem + L.off_ch_class);
+    double *hp_score = reinterpret_cast<double *>(smem + L.off_hp_score);
+    int *hp_item = reinterpret_cast<int *>(smem + L.off_hp_item);
+    uint32_t *lut_s = reinterpret_cast<uint32_t *>(smem + L.off_lut);
+    uint32_t *wscr = reinterpret_cast<uint32_t *>(smem + L.off_wscr) + warp * 16;
+    BeamJob *jobs = reinterpret_cast<BeamJob *>(smem + L.off_job);
+    int *addnew = reinterpret_cast<int *>(smem + L.off_addnew);
+    int *plain = reinterpret_cast<int *>(smem + L.off_plain);
+    // misc scalars
+    struct Misc {
+        unsigned long long delta;
+        int n_nodes[2];
+        int n_live, n_free, n_children, n_jobs_copy, n_jobs_inplace, hp_len;
+        RInfo ri;
+        uint32_t first0;  // block-local position0 of the read's first SNP
+        uint32_t nnz;
+    };
+    Misc *ms = reinterpret_cast<Misc *>(smem + L.off_misc);
+
+    for (int i = tid; i < 256; i += FB_BEAM_THREADS) lut_s[i] = bp.lut[i];
+    uint8_t *slot = bp.scratch + (uint64_t)blockIdx.x * bp.slot_bytes;
+    uint32_t *hist = reinterpret_cast<uint32_t *>(slot + bp.hist_off);
+    const uint32_t *__restrict__ qual32 = reinterpret_cast<const uint32_t *>(bp.fr.qual);
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_work = atomicAdd(bp.work_counter, 1);
+        __syncthreads();
+        const int wk = s_work;
+        if (wk >= bp.n_work) break;
+        const int ii = bp.order[wk];
+        const InstDev in = bp.inst[ii];
+        const uint32_t P = in.ploidy;
+        const uint32_t Wmax = P * bp.B;
+        const uint32_t NS = P * bp.B * (P + 1) + 1;
+        const uint32_t npos = in.ng * 16;
+        // counts + planes (uint2 == one 64-bit word), rounded to an even word count to keep 16-byte alignment
+        const uint64_t state_words = ((uint64_t)npos * 4 + in.ng + 1) & ~1ULL;
+        unsigned long long *pool = reinterpret_cast<unsigned long long *>(slot);
+#define ST_CNT(s) (pool + (uint64_t)(s) * state_words)
+#define ST_MASK(s) (reinterpret_cast<uint2 *>(pool + (uint64_t)(s) * state_words + (uint64_t)npos * 4))
+        const uint32_t Wm = bp.maxW;  // smem strides
+        const uint32_t Pm = bp.maxP;
+#define ND_SCORE(g, n) nd_score[(g) * Wm + (n)]
+#define ND_ERR(g, n, h) nd_err[((g) * Wm + (n)) * Pm + (h)]
+#define ND_REF(g, n, h) nd_ref[((g) * Wm + (n)) * Pm + (h)]
+
+        // ---- init: one root node over the empty state (global_clustering.rs:29-47) ---------------------------------
+        for (uint32_t s = tid; s < NS; s += FB_BEAM_THREADS) {
+            st_hash[s] = 0;
+            st_hi[s] = -1;
+            st_mark[s] = 0;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int nf = 0;
+            for (int s = (int)NS - 1; s >= 1; --s) st_free[nf++] = s;  // pop from the back: 1, 2, 3, ...
+            ms->n_free = nf;
+            ms->n_live = 1;
+            live[0] = 0;
+            ms->n_nodes[0] = 1;
+            ND_SCORE(0, 0) = 0.0;
+            for (uint32_t h = 0; h < P; ++h) {
+                ND_ERR(0, 0, h) = 0.0;
+                ND_REF(0, 0, h) = 0;
+            }
+        }
+        int gen = 0;
+        uint32_t prev_start = 0;  // block-local position0 from which the hashes are valid
+        int gmax = -1;            // last block-local group touched so far
+        unsigned long long cells = 0, tapn = 0;
+        __syncthreads();
+
+        for (uint32_t step = 0; step < in.n_reads; ++step) {
+            const uint32_t width = step < 25 ? Wmax : bp.B;  // global_clustering.rs:50-53
+            if (tid == 0) {
+                RInfo ri = bp.rinfo[in.read_off + step];
+                ms->ri = ri;
+                ms->first0 = (bp.fr.first[ri.rid] - 1u) - in.ag0 * 16u;
+                ms->nnz = bp.fr.nnz[ri.rid];
+                ms->delta = 0ULL;
+            }
+            __syncthreads();
+            const RInfo ri = ms->ri;
+            const uint32_t cur_start = ms->first0;
+            const uint32_t g0 = ri.gbase + ri.lg0, g1 = ri.gbase + ri.lg1;  // global groups of the read
+            const int n_nodes = ms->n_nodes[gen];
+            const int n_live = ms->n_live;
+            const int gmax_new = max(gmax, (int)ri.lg1 - 1);
+            const uint32_t wend = (uint32_t)(gmax_new + 1) * 16u;  // one past the last live window position
+
+            // ---- P1: window advance: drop positions [prev_start, cur_start) from every live state's hash -----------
+            if (cur_start > prev_start) {
+                for (int li = warp; li < n_live; li += FB_BEAM_WARPS) {
+                    const int s = live[li];
+                    const int hi = st_hi[s];
+                    unsigned long long sub = 0;
+                    const uint32_t pend = min(cur_start, (uint32_t)(hi + 1) * 16u);
+                    const unsigned long long *c = ST_CNT(s);
+                    for (uint32_t x = prev_start * 4 + lane; x < pend * 4 && pend > prev_start; x += 32) {
+                        const uint32_t pos = x >> 2, a = x & 3;
+                        sub += fb_G(in.ag0 * 16u + pos, a) * (c[x] & FB_CNT_MASK);
+                    }
+                    sub = fb_warp_sum_u64(sub);
+                    if (lane == 0) st_hash[s] -= sub;
+                }
+            }
+            // ---- delta(read) = sum over its cells of G(pos, allele) * weight ------------------------------------------
+            {
+                unsigned long long d = 0;
+                for (uint32_t x = tid; x < (ri.lg1 - ri.lg0) * 4; x += FB_BEAM_THREADS) {
+                    const uint32_t lg = ri.lg0 + (x >> 2), sub = x & 3;
+                    const uint32_t g = ri.gbase + lg;
+                    const uint32_t q = qual32[(uint64_t)g * 4 + sub];
+                    const uint32_t al = bp.fr.allele[g], pr = bp.fr.present[g];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t c = sub * 4 + k;
+                        if ((pr >> c) & 1u) {
+                            const uint32_t av = ((al >> c) & 1u) | (((al >> (16 + c)) & 1u) << 1);
+                            d += fb_G((in.ag0 + lg) * 16u + c, av) * (unsigned long long)lut_s[(q >> (8 * k)) & 0xFFu];
+                        }
+                    }
+                }
+                d = fb_warp_sum_u64(d);
+                if (lane == 0 && d) atomicAdd(&ms->delta, d);
+            }
+            // ---- P2: score the read against every live state (utils_frags.rs:32-75) --------------------------------------
+            for (int li = warp; li < n_live; li += FB_BEAM_WARPS) {
+                const int s = live[li];
+                const int hi = st_hi[s];
+                const uint2 *mk = ST_MASK(s);
+                unsigned long long total = 0, same = 0, emptyw = 0;
+                uint32_t ne_cnt = 0;
+                for (uint32_t g = g0 + lane; g < g1; g += 32) {
+                    uint4 q = bp.fr.qual[g];
+                    uint32_t al = bp.fr.allele[g];
+                    uint32_t pr = bp.fr.present[g];
+                    uint32_t w[16];
+                    fb_group_weights(q, pr, lut_s, w);
+                    uint32_t t = 0;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) t += w[k];
+                    total += t;
+                    const uint32_t lg = ri.lg0 + (g - g0);
+                    uint2 m = ((int)lg <= hi) ? mk[lg] : make_uint2(0u, 0u);
+                    uint32_t sb, ne;
+                    fb_group_masks(al, m, sb, ne);
+                    same += fb_masked_sum(w, sb);
+                    uint32_t eb = pr & ~ne & 0xFFFFu;
+                    if (eb) {
+                        emptyw += fb_masked_sum(w, eb);
+                        ne_cnt += __popc(eb);
+                    }
+                }
+                total = fb_warp_sum_u64(total);
+                same = fb_warp_sum_u64(same);
+                emptyw = fb_warp_sum_u64(emptyw);
+                ne_cnt = fb_warp_sum_u32(ne_cnt);
+                const long long diff_q = (long long)(total - same - emptyw);
+                double diff_f;
+                if (ne_cnt == 0)
+                    diff_f = fb_q26_to_f64(diff_q);
+                else if (bp.eps_safe)
+                    diff_f = fb_q26_to_f64(diff_q + (long long)ne_cnt * (long long)(bp.eps * FB_Q26));
+                else
+                    diff_f = fb_replay_diff_state(bp.fr, g0, g1, mk, ri.lg0, hi, lut_s, bp.eps, wscr);
+                if (lane == 0) {
+                    sc_same[s] = fb_q26_to_f64((long long)same);
+                    sc_diff[s] = diff_f;
+                }
+            }
+            __syncthreads();
+
+            // ---- P3: per node p-values, pruning, child scores (global_clustering.rs:71-115, 181-208) ----------------------
+            if (tid < n_nodes) {
+                const int n = tid;
+                double pv[FB_MAXP];
+                for (uint32_t j = 0; j < P; ++j) {
+                    const int s = ND_REF(gen, n, j);
+                    const double same = sc_same[s], diff = sc_diff[s];
+                    pv[j] = 1.0 * fb_stable_binom_cdf_p_rev(fb_as_usize(same + diff), fb_as_usize(diff), bp.eps,
+                                                            bp.div_factor);
+                    if (bp.tap.cap) {
+                        const unsigned long long o = tapn + (unsigned long long)n * P + j;
+                        if (o < bp.tap.cap) {
+                            if (bp.tap.same) bp.tap.same[o] = same;
+                            if (bp.tap.diff) bp.tap.diff[o] = diff;
+                            if (bp.tap.logp) bp.tap.logp[o] = pv[j];
+                        }
+                    }
+                }
+                const double lse = fb_log_sum_exp(pv, (int)P);
+                for (uint32_t j = 0; j < P; ++j) {
+                    double sc = -1.0;  // < 0 marks "pruned" (scores are sums of non-negative terms)
+                    if (pv[j] - lse > bp.cutoff) {
+                        double mec = 0.0;  // new_error_vec.iter().map(|x| x.1).sum()
+                        for (uint32_t h = 0; h < P; ++h) {
+                            double e = ND_ERR(gen, n, h);
+                            if (h == j) e = e + sc_diff[ND_REF(gen, n, j)];
+                            mec += e;
+                        }
+                        sc = -(-1.0 * mec);  // new_node_score = -score, score = -1.0 * mec
+                    }
+                    ch_score[n * P + j] = sc;  // staging, compacted below
+                }
+            }
+            __syncthreads();
+
+            // ---- P4 (warp 0): compaction, equality classes, exact BinaryHeap emulation -------------------------------------
+            if (warp == 0) {
+                // compaction in evaluation order (node in heap order, j ascending); staged scores are read before being
+                // overwritten because the compacted index never exceeds the staging index.
+                int nc = 0;
+                for (int x0 = 0; x0 < n_nodes * (int)P; x0 += 32) {
+                    const int x = x0 + (int)lane;
+                    double sc = x < n_nodes * (int)P ? ch_score[x] : -1.0;
+                    const bool keep = sc >= 0.0;
+                    const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
+                    __syncwarp();
+                    if (keep) {
+                        const int o = nc + __popc(bal & ((1u << lane) - 1u));
+                        ch_score[o] = sc;
+                        ch_parent[o] = (uint16_t)(x / (int)P);
+                        ch_part[o] = (uint16_t)(x % (int)P);
+                    }
+                    nc += __popc(bal);
+                    __syncwarp();
+                }
+                const unsigned long long delta = ms->delta;
+                // equality classes of the children's (virtual) blocks
+                int n_classes = 0;  // class representatives are children; ch_class[c] = index of the representative child
+                for (int c = 0; c < nc; ++c) {
+                    const int n1 = ch_parent[c], j1 = ch_part[c];
+                    int found = -1;
+                    for (int r0 = 0; r0 < c && found < 0; r0 += 32) {
+                        const int r = r0 + (int)lane;
+                        bool cand = false;
+                        if (r < c && ch_class[r] == r) {  // r is a representative
+                            const int n2 = ch_parent[r], j2 = ch_part[r];
+                            cand = true;
+                            for (uint32_t i = 0; i < P; ++i) {
+                                const unsigned long long ha =
+                                    st_hash[ND_REF(gen, n1, i)] + ((int)i == j1 ? delta : 0ULL);
+                                const unsigned long long hb =
+                                    st_hash[ND_REF(gen, n2, i)] + ((int)i == j2 ? delta : 0ULL);
+                                if (ha != hb) {
+                                    cand = false;
+                                    break;
+                                }
+                            }
+                        }
+                        unsigned bal = __ballot_sync(0xFFFFFFFFu, cand);
+                        while (bal && found < 0) {
+                            const int rr = r0 + __ffs(bal) - 1;
+                            bal &= bal - 1;
+                            // exact verification on the virtual states
+                            const int n2 = ch_parent[rr], j2 = ch_part[rr];
+                            bool eq = true;
+                            for (uint32_t i = 0; i < P && eq; ++i) {
+                                const int sA = ND_REF(gen, n1, i), sB = ND_REF(gen, n2, i);
+                                const bool addA = (int)i == j1, addB = (int)i == j2;
+                                if (sA == sB && addA == addB) continue;
+                                const unsigned long long *cA = ST_CNT(sA), *cB = ST_CNT(sB);
+                                const int hiA = st_hi[sA], hiB = st_hi[sB];
+                                for (uint32_t p0 = cur_start; p0 < wend; p0 += 32) {
+                                    const uint32_t pos = p0 + lane;
+                                    bool neq = false;
+                                    if (pos < wend) {
+                                        const uint32_t lg = pos >> 4, k = pos & 15;
+                                        unsigned long long A[4], Bw[4];
+#pragma unroll
+                                        for (int a = 0; a < 4; ++a) {
+                                            A[a] = ((int)lg <= hiA) ? cA[(uint64_t)pos * 4 + a] : 0ULL;
+                                            Bw[a] = ((int)lg <= hiB) ? cB[(uint64_t)pos * 4 + a] : 0ULL;
+                                        }
+                                        if ((addA || addB) && lg >= ri.lg0 && lg < ri.lg1) {
+                                            const uint32_t g = ri.gbase + lg;
+                                            const uint32_t pr = bp.fr.present[g];
+                                            if ((pr >> k) & 1u) {
+                                                const uint32_t al = bp.fr.allele[g];
+                                                const uint32_t av = ((al >> k) & 1u) | (((al >> (16 + k)) & 1u) << 1);
+                                                const uint32_t q = qual32[(uint64_t)g * 4 + (k >> 2)];
+                                                const unsigned long long w = lut_s[(q >> (8 * (k & 3))) & 0xFFu];
+#pragma unroll
+                                                for (int a = 0; a < 4; ++a) {
+                                                    if ((uint32_t)a == av) {
+                                                        if (addA) A[a] = (A[a] + w) | FB_PRESENT;
+                                                        if (addB) Bw[a] = (Bw[a] + w) | FB_PRESENT;
+                                                    }
+                                                }
+                                            }
+                                        }
+                                        neq = (A[0] != Bw[0]) | (A[1] != Bw[1]) | (A[2] != Bw[2]) | (A[3] != Bw[3]);
+                                    }
+                                    if (__any_sync(0xFFFFFFFFu, neq)) {
+                                        eq = false;
+                                        break;
+                                    }
+                                }
+                            }
+                            if (eq) found = rr;
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) ch_class[c] = (uint16_t)(found >= 0 ? found : c);
+                    if (found < 0) n_classes++;
+                    __syncwarp();
+                }
+                (void)n_classes;
+                // heap: global_clustering.rs:122-135
+                HeapRef hp;
+                hp.score = hp_score;
+                hp.item = hp_item;
+                hp.len = 0;
+                for (int c = 0; c < nc; ++c) {
+                    const double sc = ch_score[c];
+                    const int cls = ch_class[c];
+                    bool exists = false;
+                    for (int e0 = 0; e0 < hp.len; e0 += 32) {
+                        const int e = e0 + (int)lane;
+                        bool hit = false;
+                        if (e < hp.len) hit = (ch_class[hp_item[e]] == cls) && (hp_score[e] >= sc);
+                        if (__any_sync(0xFFFFFFFFu, hit)) exists = true;
+                    }
+                    if (!exists) {
+                        if (lane == 0) {
+                            hp.push(sc, c);
+                            if ((uint32_t)hp.len > width) hp.pop();
+                        }
+                        hp.len = __shfl_sync(0xFFFFFFFFu, hp.len, 0);
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0) {
+                    ms->hp_len = hp.len;
+                    ms->n_children = nc;
+                }
+                // ---- which states does the next generation need? ---------------------------------------------------------
+                for (uint32_t s = lane; s < NS; s += 32) {
+                    plain[s] = 0;
+                    addnew[s] = -1;
+                    st_mark[s] = 0;
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    const int len = hp.len;
+                    for (int e = 0; e < len; ++e) {
+                        const int c = hp_item[e];
+                        const int n = ch_parent[c], j = ch_part[c];
+                        for (uint32_t i = 0; i < P; ++i)
+                            if ((int)i != j) plain[ND_REF(gen, n, i)] = 1;
+                    }
+                    int nj_copy = 0, nj_inpl = 0;
+                    int nfree = ms->n_free;
+                    // jobs: copies first [0, nj_copy), in-place ones stored from the back of the array
+                    for (int e = 0; e < len; ++e) {
+                        const int c = hp_item[e];
+                        const int n = ch_parent[c], j = ch_part[c];
+                        const int s = ND_REF(gen, n, j);
+                        if (addnew[s] < 0) {
+                            if (!plain[s]) {
+                                addnew[s] = s;
+                                BeamJob jb;
+                                jb.src = s;
+                                jb.dst = s;
+                                jb.inplace = 1;
+                                jb._pad = 0;
+                                jobs[(int)Wm - nj_inpl] = jb;
+                                nj_inpl++;
+                            } else {
+                                const int d = st_free[--nfree];
+                                addnew[s] = d;
+                                BeamJob jb;
+                                jb.src = s;
+                                jb.dst = d;
+                                jb.inplace = 0;
+                                jb._pad = 0;
+                                jobs[nj_copy++] = jb;
+                            }
+                        }
+                    }
+                    ms->n_free = nfree;
+                    ms->n_jobs_copy = nj_copy;
+                    ms->n_jobs_inplace = nj_inpl;
+                    // next generation's node tables + history
+                    const int ng2 = gen ^ 1;
+                    for (int e = 0; e < len; ++e) {
+                        const int c = hp_item[e];
+                        const int n = ch_parent[c], j = ch_part[c];
+                        ND_SCORE(ng2, e) = hp_score[e];
+                        for (uint32_t i = 0; i < P; ++i) {
+                            int s = ND_REF(gen, n, i);
+                            double er = ND_ERR(gen, n, i);
+                            if ((int)i == j) {
+                                er = er + sc_diff[s];
+                                s = addnew[s];
+                            }
+                            ND_REF(ng2, e, i) = (uint16_t)s;
+                            ND_ERR(ng2, e, i) = er;
+                            st_mark[s] = 1;
+                        }
+                        hist[(uint64_t)step * Wm + e] = (uint32_t)n | ((uint32_t)j << 16);
+                    }
+                    ms->n_nodes[ng2] = len;
+                }
+            }
+            __syncthreads();
+
+            // ---- P5: materialise the new states (types_structs.rs:368-373 on the dense layout) ------------------------------
+            {
+                const int nj_copy = ms->n_jobs_copy, nj_inpl = ms->n_jobs_inplace;
+                const unsigned long long delta = ms->delta;
+                const int gs = (int)(cur_start >> 4);
+                // copies: groups [gs, gmax_new]; in place: the read's groups only
+                for (int pass = 0; pass < 2; ++pass) {
+                    const int nj = pass == 0 ? nj_copy : nj_inpl;
+                    const int glo = pass == 0 ? gs : (int)ri.lg0;
+                    const int ghi = pass == 0 ? gmax_new : (int)ri.lg1 - 1;
+                    const int nq = (ghi - glo + 1) * 4;  // quarters per job
+                    const int total = nj * nq;
+                    for (int base = 0; base < total; base += FB_BEAM_THREADS) {
+                        const int idx = base + tid;
+                        const bool act = idx < total;
+                        uint32_t pl[4] = {0, 0, 0, 0};
+                        int lg = 0;
+                        uint32_t sub = 0;
+                        BeamJob jb;
+                        jb.src = jb.dst = jb.inplace = jb._pad = 0;
+                        if (act) {
+                            const int jn = idx / nq, qx = idx % nq;
+                            jb = pass == 0 ? jobs[jn] : jobs[(int)Wm - jn];
+                            lg = glo + (qx >> 2);
+                            sub = (uint32_t)qx & 3u;
+                            const int hi_src = st_hi[jb.src];
+                            unsigned long long wv[16];
+                            const ulonglong2 *src =
+                                reinterpret_cast<const ulonglong2 *>(ST_CNT(jb.src) + ((uint64_t)lg * 16 + sub * 4) * 4);
+                            if (lg <= hi_src) {
+#pragma unroll
+                                for (int x = 0; x < 8; ++x) {
+                                    ulonglong2 v = src[x];
+                                    wv[2 * x] = v.x;
+                                    wv[2 * x + 1] = v.y;
+                                }
+                            } else {
+#pragma unroll
+                                for (int x = 0; x < 16; ++x) wv[x] = 0ULL;
+                            }
+                            if (lg >= (int)ri.lg0 && lg < (int)ri.lg1) {
+                                const uint32_t g = ri.gbase + (uint32_t)lg;
+                                const uint32_t q = qual32[(uint64_t)g * 4 + sub];
+                                const uint32_t al = bp.fr.allele[g], pr = bp.fr.present[g];
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const uint32_t c = sub * 4 + k;
+                                    if ((pr >> c) & 1u) {
+                                        const uint32_t av = ((al >> c) & 1u) | (((al >> (16 + c)) & 1u) << 1);
+                                        const unsigned long long w = lut_s[(q >> (8 * k)) & 0xFFu];
+#pragma unroll
+                                        for (int a = 0; a < 4; ++a)
+                                            if ((uint32_t)a == av) wv[k * 4 + a] = (wv[k * 4 + a] + w) | FB_PRESENT;
+                                    }
+                                }
+                            }
+                            ulonglong2 *dst =
+                                reinterpret_cast<ulonglong2 *>(ST_CNT(jb.dst) + ((uint64_t)lg * 16 + sub * 4) * 4);
+#pragma unroll
+                            for (int x = 0; x < 8; ++x) dst[x] = make_ulonglong2(wv[2 * x], wv[2 * x + 1]);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                unsigned long long mx = 0;
+#pragma unroll
+                                for (int a = 0; a < 4; ++a) {
+                                    unsigned long long v = wv[k * 4 + a] & FB_CNT_MASK;
+                                    mx = v > mx ? v : mx;
+                                }
+                                if (mx > 0) {
+#pragma unroll
+                                    for (int a = 0; a < 4; ++a)
+                                        if ((wv[k * 4 + a] & FB_CNT_MASK) == mx) pl[a] |= 1u << (sub * 4 + k);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int a = 0; a < 4; ++a) {
+                            pl[a] |= __shfl_xor_sync(0xFFFFFFFFu, pl[a], 1);
+                            pl[a] |= __shfl_xor_sync(0xFFFFFFFFu, pl[a], 2);
+                        }
+                        if (act && sub == 0)
+                            ST_MASK(jb.dst)[lg] = make_uint2(pl[0] | (pl[1] << 16), pl[2] | (pl[3] << 16));
+                    }
+                }
+                __syncthreads();
+                // per-state bookkeeping of the new states
+                const int njt = nj_copy + nj_inpl;
+                if (tid < njt) {
+                    const BeamJob jb = tid < nj_copy ? jobs[tid] : jobs[(int)Wm - (tid - nj_copy)];
+                    const unsigned long long h = st_hash[jb.src] + delta;
+                    const int hi = max(st_hi[jb.src], (int)ri.lg1 - 1);
+                    // (src may equal dst; each dst is written by exactly one thread, and src values of other jobs are
+                    //  never a dst of a copy job, so reading before the barrier below is race free for copies; in-place
+                    //  jobs read and write their own entry)
+                    st_hash[jb.dst] = h;
+                    st_hi[jb.dst] = hi;
+                }
+                __syncthreads();
+            }
+            // ---- free list + live list of the next generation (warp 0, deterministic order) --------------------------------
+            if (warp == 0) {
+                int nl = 0, nf = 0;
+                for (uint32_t s0 = 0; s0 < NS; s0 += 32) {
+                    const uint32_t s = s0 + lane;
+                    const bool isl = s < NS && st_mark[s];
+                    const unsigned bal = __ballot_sync(0xFFFFFFFFu, isl);
+                    if (isl) live[nl + __popc(bal & ((1u << lane) - 1u))] = (int)s;
+                    nl += __popc(bal);
+                }
+                // free list: descending ids so that pops hand out ascending ids
+                for (int s0 = (int)((NS + 31) / 32) * 32 - 32; s0 >= 0; s0 -= 32) {
+                    const int s = s0 + 31 - (int)lane;  // lane 0 sees the largest id of the chunk
+                    const bool isf = s >= 1 && s < (int)NS && !st_mark[s];
+                    const unsigned bal = __ballot_sync(0xFFFFFFFFu, isf);
+                    if (isf) st_free[nf + __popc(bal & ((1u << lane) - 1u))] = s;
+                    nf += __popc(bal);
+                }
+                if (lane == 0) {
+                    ms->n_live = nl;
+                    ms->n_free = nf;
+                }
+            }
+            cells += (unsigned long long)n_nodes * ms->nnz;
+            tapn += (unsigned long long)n_nodes * P;
+            gen ^= 1;
+            prev_start = cur_start;
+            gmax = gmax_new;
+            __syncthreads();
+        }
+
+        // ---- global_clustering.rs:149-176: best = into_sorted_vec()[0]; walk the parent pointers ------------------------------
+        if (tid == 0) {
+            const int len = ms->n_nodes[gen];
+            HeapRef hp;
+            hp.score = hp_score;
+            hp.item = hp_item;
+            hp.len = len;
+            for (int e = 0; e < len; ++e) {
+                hp_score[e] = ND_SCORE(gen, e);
+                hp_item[e] = e;
+            }
+            hp.into_sorted();
+            int e = hp_item[0];
+            bp.best_out[ii] = hp_score[0];
+            uint8_t *as = bp.assign_out + in.assign_off;
+            for (int step = (int)in.n_reads - 1; step >= 0; --step) {
+                const uint32_t v = hist[(uint64_t)step * Wm + e];
+                as[step] = (uint8_t)(v >> 16);
+                e = (int)(v & 0xFFFFu);
+            }
+            bp.cells_out[ii] = cells;
+            bp.tapn_out[ii] = tapn;
+        }
+#undef ST_CNT
+#undef ST_MASK
+#undef ND_SCORE
+#undef ND_ERR
+#undef ND_REF
+    }
+}
+

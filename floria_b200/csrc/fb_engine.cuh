@@ -1,0 +1,467 @@
+// fb_engine.cuh — host-side engine: context, HBM-resident fragments, the batched plan over (block, ploidy)
+// instances and the launch sequences that replace optimize_clustering (local_clustering.rs:71-130) and
+// get_mec_stats_epsilon_no_phred (local_clustering.rs:187-215).
+#pragma once
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/floria_b200.h"
+#include "fb_common.cuh"
+#include "fb_kernels.cuh"
+
+struct fb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint32_t *d_lut = nullptr;  // 256 x u32 (units of 2^-26)
+    uint32_t h_lut[256];
+    float h_lut_f[256];
+    bool lut_valid = false;
+    fb_timings tim;
+    int *d_n_active = nullptr;
+    int *h_n_active = nullptr;  // pinned
+    int sm_count = 148;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+};
+
+struct fb_dfrags {
+    fb_ctx *ctx = nullptr;
+    uint64_t n_reads = 0, nnz = 0, n_groups = 0, bytes = 0;
+    uint32_t *d_first = nullptr, *d_last = nullptr, *d_nnz = nullptr, *d_gstart = nullptr, *d_gptr = nullptr;
+    uint4 *d_qual = nullptr;
+    uint32_t *d_allele = nullptr;
+    uint16_t *d_present = nullptr;
+    std::vector<uint32_t> h_first, h_last, h_nnz, h_gstart, h_gptr, h_prefmax_last;
+    DFragsDev dev() const {
+        DFragsDev d;
+        d.n_reads = n_reads;
+        d.first = d_first;
+        d.last = d_last;
+        d.nnz = d_nnz;
+        d.gstart = d_gstart;
+        d.gptr = d_gptr;
+        d.qual = d_qual;
+        d.allele = d_allele;
+        d.present = d_present;
+        return d;
+    }
+};
+
+static thread_local std::string g_init_err;
+
+#define FB_CK(call)                                                                                   \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            char b_[512];                                                                             \
+            snprintf(b_, sizeof(b_), "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            ctx->err = b_;                                                                            \
+            return FB_ERR_CUDA;                                                                       \
+        }                                                                                             \
+    } while (0)
+
+#define FB_FAIL(code, ...)                        \
+    do {                                          \
+        char b_[512];                             \
+        snprintf(b_, sizeof(b_), __VA_ARGS__);    \
+        ctx->err = b_;                            \
+        return code;                              \
+    } while (0)
+
+template <class T>
+static int fb_dalloc(fb_ctx *ctx, T **p, size_t n) {
+    *p = nullptr;
+    if (n == 0) n = 1;
+    FB_CK(cudaMalloc((void **)p, n * sizeof(T)));
+    return FB_OK;
+}
+template <class T>
+static int fb_upload(fb_ctx *ctx, T **p, const T *h, size_t n) {
+    int rc = fb_dalloc(ctx, p, n);
+    if (rc) return rc;
+    if (n) FB_CK(cudaMemcpyAsync(*p, h, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return FB_OK;
+}
+template <class T>
+static int fb_upload(fb_ctx *ctx, T **p, const std::vector<T> &h) {
+    return fb_upload(ctx, p, h.data(), h.size());
+}
+
+static cudaEvent_t fb_event(fb_ctx *ctx) {
+    if (ctx->ev_used == ctx->ev_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        ctx->ev_pool.push_back(e);
+    }
+    cudaEvent_t e = ctx->ev_pool[ctx->ev_used++];
+    cudaEventRecord(e, ctx->stream);
+    return e;
+}
+
+// local_clustering.rs:12-59 find_reads_in_interval on the sorted contig (same result as the reference's linear scan:
+// reads are sorted by first_position, so the scan's `break` is an upper bound found by bisection, and the prefix maximum
+// of last_position bounds where `last >= start` can first hold).
+static void fb_find_reads(const fb_dfrags *df, uint32_t start, uint32_t end, std::vector<uint32_t> &out) {
+    out.clear();
+    const std::vector<uint32_t> &first = df->h_first, &last = df->h_last, &pm = df->h_prefmax_last;
+    size_t n = first.size();
+    size_t hi = std::upper_bound(first.begin(), first.end(), end) - first.begin();
+    size_t lo = std::lower_bound(pm.begin(), pm.begin() + hi, start) - pm.begin();
+    (void)n;
+    for (size_t i = lo; i < hi; ++i) {
+        if (last[i] < start) continue;
+        if (last[i] - first[i] > 10000) continue;
+        out.push_back((uint32_t)i);
+    }
+}
+
+// ---- the batched plan -------------------------------------------------------------------------------------------------
+struct BlockPlan {
+    std::vector<uint32_t> reads;  // counter_ids ascending
+    uint32_t ag0 = 0, ng = 0;
+    uint64_t nnz = 0;
+    uint32_t read_off = 0;
+};
+
+struct Engine {
+    fb_ctx *ctx = nullptr;
+    const fb_dfrags *df = nullptr;
+    std::vector<BlockPlan> blocks;
+    std::vector<InstDev> inst;
+    std::vector<InstState> st;
+    std::vector<uint64_t> assign_prefix, tile_prefix, hap_prefix, moves_off;
+    std::vector<uint32_t> moves_cap;
+    std::vector<RInfo> rinfo;
+    uint64_t tot_assign = 0, tot_gain = 0, tot_cnt = 0, tot_mask = 0, tot_mec = 0, tot_moves = 0;
+    // device
+    InstDev *d_inst = nullptr;
+    InstState *d_st = nullptr;
+    uint64_t *d_assign_prefix = nullptr, *d_tile_prefix = nullptr, *d_hap_prefix = nullptr, *d_moves_off = nullptr;
+    uint32_t *d_moves_cap = nullptr;
+    RInfo *d_rinfo = nullptr;
+    uint8_t *d_assign[2] = {nullptr, nullptr};
+    uint64_t *d_cnt[2] = {nullptr, nullptr};
+    uint2 *d_masks[2] = {nullptr, nullptr};
+    double *d_mec[2] = {nullptr, nullptr};
+    double *d_gain = nullptr;
+    MoveRec *d_moves = nullptr;
+    double eps = 0;
+    int eps_safe = 0;
+
+    ~Engine() { release(); }
+    void release() {
+        cudaFree(d_inst);
+        cudaFree(d_st);
+        cudaFree(d_assign_prefix);
+        cudaFree(d_tile_prefix);
+        cudaFree(d_hap_prefix);
+        cudaFree(d_moves_off);
+        cudaFree(d_moves_cap);
+        cudaFree(d_rinfo);
+        for (int b = 0; b < 2; ++b) {
+            cudaFree(d_assign[b]);
+            cudaFree(d_cnt[b]);
+            cudaFree(d_masks[b]);
+            cudaFree(d_mec[b]);
+        }
+        cudaFree(d_gain);
+        cudaFree(d_moves);
+        d_inst = nullptr;
+        d_st = nullptr;
+        d_assign_prefix = d_tile_prefix = d_hap_prefix = d_moves_off = nullptr;
+        d_moves_cap = nullptr;
+        d_rinfo = nullptr;
+        for (int b = 0; b < 2; ++b) {
+            d_assign[b] = nullptr;
+            d_cnt[b] = nullptr;
+            d_masks[b] = nullptr;
+            d_mec[b] = nullptr;
+        }
+        d_gain = nullptr;
+        d_moves = nullptr;
+    }
+
+    // add a block given its (ascending) read list; returns block index
+    int add_block(const std::vector<uint32_t> &reads) {
+        BlockPlan b;
+        b.reads = reads;
+        uint32_t gmin = 0xFFFFFFFFu, gmax = 0;
+        for (uint32_t r : reads) {
+            uint32_t g0 = df->h_gstart[r];
+            uint32_t g1 = g0 + (df->h_gptr[r + 1] - df->h_gptr[r]);
+            gmin = std::min(gmin, g0);
+            gmax = std::max(gmax, g1);
+            b.nnz += df->h_nnz[r];
+        }
+        if (reads.empty()) {
+            gmin = 0;
+            gmax = 0;
+        }
+        b.ag0 = gmin;
+        b.ng = gmax - gmin;
+        b.read_off = (uint32_t)rinfo.size();
+        for (uint32_t r : reads) {
+            RInfo ri;
+            ri.rid = r;
+            ri.lg0 = df->h_gstart[r] - gmin;
+            ri.lg1 = ri.lg0 + (df->h_gptr[r + 1] - df->h_gptr[r]);
+            ri.gbase = df->h_gptr[r] - ri.lg0;
+            rinfo.push_back(ri);
+        }
+        blocks.push_back(std::move(b));
+        return (int)blocks.size() - 1;
+    }
+    int add_instance(int block, uint32_t ploidy) {
+        const BlockPlan &b = blocks[block];
+        InstDev in;
+        memset(&in, 0, sizeof(in));
+        in.block = (uint32_t)block;
+        in.ploidy = ploidy;
+        in.n_reads = (uint32_t)b.reads.size();
+        in.ng = b.ng;
+        in.ag0 = b.ag0;
+        in.read_off = b.read_off;
+        in.mec_off = (uint32_t)tot_mec;
+        in.assign_off = tot_assign;
+        in.gain_off = tot_gain;
+        in.cnt_off = tot_cnt;
+        in.mask_off = tot_mask;
+        assign_prefix.push_back(tot_assign);
+        hap_prefix.push_back(tot_mec);
+        uint32_t tiles = (b.ng + FB_HIST_TILE_GROUPS - 1) / FB_HIST_TILE_GROUPS;
+        tot_assign += in.n_reads;
+        tot_gain += (uint64_t)in.n_reads * ploidy;
+        tot_cnt += (uint64_t)ploidy * b.ng * 64;
+        tot_mask += (uint64_t)ploidy * b.ng;
+        tot_mec += ploidy;
+        tile_counts.push_back((uint64_t)tiles * ploidy);
+        uint64_t maxm = (uint64_t)in.n_reads * (ploidy > 1 ? ploidy - 1 : 1);
+        uint32_t cap = 1;
+        while (cap < maxm) cap <<= 1;
+        moves_off.push_back(tot_moves);
+        moves_cap.push_back(cap);
+        tot_moves += cap;
+        InstState s;
+        memset(&s, 0, sizeof(s));
+        s.cur = 0;
+        s.active = 1;
+        st.push_back(s);
+        inst.push_back(in);
+        return (int)inst.size() - 1;
+    }
+    std::vector<uint64_t> tile_counts;
+
+    int finalize_and_upload(double eps_) {
+        eps = eps_;
+        eps_safe = fb_eps_is_safe(eps_);
+        int n = (int)inst.size();
+        assign_prefix.push_back(tot_assign);
+        hap_prefix.push_back(tot_mec);
+        tile_prefix.assign(n + 1, 0);
+        for (int i = 0; i < n; ++i) tile_prefix[i + 1] = tile_prefix[i] + tile_counts[i];
+        int rc;
+        if ((rc = fb_upload(ctx, &d_inst, inst))) return rc;
+        if ((rc = fb_upload(ctx, &d_st, st))) return rc;
+        if ((rc = fb_upload(ctx, &d_assign_prefix, assign_prefix))) return rc;
+        if ((rc = fb_upload(ctx, &d_tile_prefix, tile_prefix))) return rc;
+        if ((rc = fb_upload(ctx, &d_hap_prefix, hap_prefix))) return rc;
+        if ((rc = fb_upload(ctx, &d_moves_off, moves_off))) return rc;
+        if ((rc = fb_upload(ctx, &d_moves_cap, moves_cap))) return rc;
+        if ((rc = fb_upload(ctx, &d_rinfo, rinfo))) return rc;
+        for (int b = 0; b < 2; ++b) {
+            if ((rc = fb_dalloc(ctx, &d_assign[b], tot_assign))) return rc;
+            if ((rc = fb_dalloc(ctx, &d_cnt[b], tot_cnt))) return rc;
+            if ((rc = fb_dalloc(ctx, &d_masks[b], tot_mask))) return rc;
+            if ((rc = fb_dalloc(ctx, &d_mec[b], tot_mec * 2))) return rc;
+            FB_CK(cudaMemsetAsync(d_assign[b], 0, std::max<uint64_t>(tot_assign, 1), ctx->stream));
+        }
+        if ((rc = fb_dalloc(ctx, &d_gain, tot_gain))) return rc;
+        if ((rc = fb_dalloc(ctx, &d_moves, tot_moves))) return rc;
+        return FB_OK;
+    }
+
+    int n_inst() const { return (int)inst.size(); }
+
+    int launch_sizes(int which) {
+        int n = n_inst();
+        if (!n) return FB_OK;
+        k_sizes<<<(n + 7) / 8, 256, 0, ctx->stream>>>(d_inst, d_st, n, d_assign[0], d_assign[1], which);
+        ctx->tim.n_launches++;
+        FB_CK(cudaGetLastError());
+        return FB_OK;
+    }
+    int launch_hist(int which, int use_phred, int only_active, int buf = 0, int assign_cur = 0) {
+        int n = n_inst();
+        uint64_t ctas = tile_prefix[n];
+        if (!ctas) return FB_OK;
+        HistArgs a;
+        a.fr = df->dev();
+        a.inst = d_inst;
+        a.st = d_st;
+        a.n_inst = n;
+        a.tile_prefix = d_tile_prefix;
+        a.rinfo = d_rinfo;
+        a.assign[0] = d_assign[0];
+        a.assign[1] = d_assign[1];
+        a.cnt[0] = d_cnt[0];
+        a.cnt[1] = d_cnt[1];
+        a.masks[0] = d_masks[0];
+        a.masks[1] = d_masks[1];
+        a.lut = ctx->d_lut;
+        a.use_phred = use_phred;
+        a.which = which;
+        a.buf = buf;
+        a.only_active = only_active;
+        a.assign_cur = assign_cur;
+        cudaEvent_t e0 = fb_event(ctx);
+        k_hist<<<(unsigned)ctas, FB_HIST_THREADS, 0, ctx->stream>>>(a);
+        cudaEvent_t e1 = fb_event(ctx);
+        hist_ev.push_back(std::make_pair(e0, e1));
+        ctx->tim.n_launches++;
+        ctx->tim.n_hist_launches++;
+        FB_CK(cudaGetLastError());
+        return FB_OK;
+    }
+    int launch_mec(int which, int only_active, int buf = 0) {
+        int n = n_inst();
+        uint64_t warps = hap_prefix[n];
+        if (!warps) return FB_OK;
+        MecArgs a;
+        a.inst = d_inst;
+        a.st = d_st;
+        a.n_inst = n;
+        a.hap_prefix = d_hap_prefix;
+        a.cnt[0] = d_cnt[0];
+        a.cnt[1] = d_cnt[1];
+        a.mec[0] = d_mec[0];
+        a.mec[1] = d_mec[1];
+        a.eps = eps;
+        a.eps_safe = eps_safe;
+        a.which = which;
+        a.buf = buf;
+        a.only_active = only_active;
+        cudaEvent_t e0 = fb_event(ctx);
+        k_mec<<<(unsigned)((warps + 7) / 8), 256, 0, ctx->stream>>>(a);
+        cudaEvent_t e1 = fb_event(ctx);
+        mec_ev.push_back(std::make_pair(e0, e1));
+        ctx->tim.n_launches++;
+        FB_CK(cudaGetLastError());
+        return FB_OK;
+    }
+    SweepArgs sweep_args(int mode) {
+        SweepArgs a;
+        memset(&a, 0, sizeof(a));
+        a.fr = df->dev();
+        a.inst = d_inst;
+        a.st = d_st;
+        a.n_inst = n_inst();
+        a.assign_prefix = d_assign_prefix;
+        a.rinfo = d_rinfo;
+        a.assign[0] = d_assign[0];
+        a.assign[1] = d_assign[1];
+        a.masks[0] = d_masks[0];
+        a.masks[1] = d_masks[1];
+        a.lut = ctx->d_lut;
+        a.eps = eps;
+        a.eps_safe = eps_safe;
+        a.mode = mode;
+        a.gain = d_gain;
+        return a;
+    }
+    int launch_sweep(const SweepArgs &a) {
+        if (!tot_assign) return FB_OK;
+        cudaEvent_t e0 = fb_event(ctx);
+        k_sweep<<<(unsigned)((tot_assign + FB_SWEEP_WARPS - 1) / FB_SWEEP_WARPS), FB_SWEEP_WARPS * 32, 0, ctx->stream>>>(a);
+        cudaEvent_t e1 = fb_event(ctx);
+        sweep_ev.push_back(std::make_pair(e0, e1));
+        ctx->tim.n_launches++;
+        ctx->tim.n_sweep_launches++;
+        FB_CK(cudaGetLastError());
+        return FB_OK;
+    }
+    int launch_select() {
+        int n = n_inst();
+        if (!n) return FB_OK;
+        SelectArgs a;
+        a.inst = d_inst;
+        a.st = d_st;
+        a.n_inst = n;
+        a.gain = d_gain;
+        a.assign[0] = d_assign[0];
+        a.assign[1] = d_assign[1];
+        a.moves = d_moves;
+        a.moves_off = d_moves_off;
+        a.moves_cap = d_moves_cap;
+        cudaEvent_t e0 = fb_event(ctx);
+        k_select<<<n, FB_SELECT_THREADS, 0, ctx->stream>>>(a);
+        cudaEvent_t e1 = fb_event(ctx);
+        select_ev.push_back(std::make_pair(e0, e1));
+        ctx->tim.n_launches++;
+        FB_CK(cudaGetLastError());
+        return FB_OK;
+    }
+    int launch_accept(int init, uint32_t iter, uint32_t max_iters) {
+        int n = n_inst();
+        if (!n) return FB_OK;
+        AcceptArgs a;
+        a.inst = d_inst;
+        a.st = d_st;
+        a.n_inst = n;
+        a.mec[0] = d_mec[0];
+        a.mec[1] = d_mec[1];
+        a.init = init;
+        a.iter = iter;
+        a.max_iters = max_iters;
+        a.n_active = ctx->d_n_active;
+        k_accept<<<(n + 127) / 128, 128, 0, ctx->stream>>>(a);
+        ctx->tim.n_launches++;
+        FB_CK(cudaGetLastError());
+        return FB_OK;
+    }
+
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> hist_ev, mec_ev, sweep_ev, select_ev;
+    uint64_t active_assign = 0;  // for cell accounting of launches (all instances are streamed by every launch)
+
+    // optimize_clustering (local_clustering.rs:71-130) for every instance, starting from assign[0].
+    int run_optimize(uint32_t max_iters) {
+        int rc;
+        if ((rc = launch_sizes(0))) return rc;
+        if ((rc = launch_hist(0, 1, 0))) return rc;
+        if ((rc = launch_mec(0, 0))) return rc;
+        if ((rc = launch_accept(1, 0, max_iters))) return rc;
+        for (uint32_t it = 0; it < max_iters; ++it) {
+            if ((rc = launch_sweep(sweep_args(FB_SWEEP_MOVES)))) return rc;
+            if ((rc = launch_select())) return rc;
+            if ((rc = launch_hist(1, 1, 1))) return rc;
+            if ((rc = launch_mec(1, 1))) return rc;
+            FB_CK(cudaMemsetAsync(ctx->d_n_active, 0, sizeof(int), ctx->stream));
+            if ((rc = launch_accept(0, it, max_iters))) return rc;
+            FB_CK(cudaMemcpyAsync(ctx->h_n_active, ctx->d_n_active, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            FB_CK(cudaStreamSynchronize(ctx->stream));
+            if (*ctx->h_n_active == 0) break;
+        }
+        return FB_OK;
+    }
+
+    void collect_timings() {
+        auto sum = [](std::vector<std::pair<cudaEvent_t, cudaEvent_t>> &v) {
+            float t = 0;
+            for (auto &p : v) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, p.first, p.second);
+                t += ms;
+            }
+            return t;
+        };
+        ctx->tim.sweep_ms += sum(sweep_ev);
+        ctx->tim.hist_ms += sum(hist_ev);
+        ctx->tim.mec_ms += sum(mec_ev);
+        ctx->tim.select_ms += sum(select_ev);
+    }
+};

@@ -1,0 +1,671 @@
+// fb_kernels.cuh — packing, scoring sweep (K1), haplotype histogram (K2), MEC reduction (K3), move selection (K4).
+// Reference functions each kernel reproduces are cited at the kernel.  All paths relative to /root/reference.
+#pragma once
+#include "fb_common.cuh"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// pack: CSR cells -> banded planes.  One thread per stored cell.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void k_pack(uint64_t nnz, uint64_t n_reads, const uint64_t *__restrict__ row_ptr,
+                       const uint32_t *__restrict__ pos, const uint8_t *__restrict__ allele,
+                       const uint8_t *__restrict__ qual, const uint32_t *__restrict__ gstart,
+                       const uint32_t *__restrict__ gptr, uint8_t *__restrict__ qual_out,
+                       uint32_t *__restrict__ allele_out, uint32_t *__restrict__ present_out32) {
+    uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nnz) return;
+    // read of this cell: last r with row_ptr[r] <= c
+    uint64_t lo = 0, hi = n_reads;  // invariant: row_ptr[lo] <= c < row_ptr[hi]
+    while (hi - lo > 1) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (row_ptr[mid] <= c)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    uint32_t p0 = pos[c] - 1u;
+    uint32_t g = gptr[lo] + ((p0 >> 4) - gstart[lo]);
+    uint32_t k = p0 & 15u;
+    uint32_t a = allele[c];
+    atomicOr(&allele_out[g], ((a & 1u) << k) | (((a >> 1) & 1u) << (16 + k)));
+    atomicOr(&present_out32[g >> 1], 1u << (k + 16u * (g & 1u)));
+    qual_out[(uint64_t)g * 16 + k] = qual[c];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K1 score_sweep.  One warp per (instance, read); lanes stride over the read's 16-cell groups.
+// Reproduces utils_frags.rs:32-75 distance_read_haplo_epsilon_empty for the read against EVERY haplotype of the
+// instance's current table, and (mode MOVES) the candidate-move generation of opt_iterate, local_clustering.rs:300-325.
+// Exactness: same/diff weight sums are integer (units of 2^-26) warp reductions; the f64 `diff` is formed exactly as the
+// reference's left-to-right sum in canonical position order (closed form when no epsilon term can round, otherwise the
+// warp-cooperative replay below).
+// ---------------------------------------------------------------------------------------------------------------------
+#define FB_SWEEP_MOVES 0
+#define FB_SWEEP_SCORE 1
+#define FB_SWEEP_WARPS 8
+
+struct SweepArgs {
+    DFragsDev fr;
+    const InstDev *inst;
+    InstState *st;
+    int n_inst;
+    const uint64_t *assign_prefix;  // [n_inst+1] == inst[i].assign_off, last = total
+    const RInfo *rinfo;
+    const uint8_t *assign[2];
+    const uint2 *masks[2];
+    const uint32_t *lut;  // 256 weights in units of 2^-26
+    double eps;
+    int eps_safe;
+    int mode;
+    // MOVES
+    double *gain;
+    // SCORE (any may be null)
+    double *o_same, *o_diff;
+    long long *o_same_q26, *o_diff_q26;
+    uint32_t *o_nempty;
+};
+
+// exact left-to-right f64 sum of the diff/epsilon items of one read vs one haplotype (canonical order)
+__device__ double fb_replay_diff(const DFragsDev &fr, uint32_t g0, uint32_t g1, const uint2 *__restrict__ mh,
+                                 uint32_t lg0, const uint32_t *lut, double eps, uint32_t *wscratch /*16 per warp*/) {
+    const uint32_t lane = fb_lane();
+    SeqSum ss;
+    ss.init();
+    for (uint32_t base = g0; base < g1; base += 32) {
+        uint32_t g = base + lane;
+        bool valid = g < g1;
+        uint32_t w[16];
+        uint32_t diffbits = 0, emptybits = 0;
+        if (valid) {
+            uint4 q = fr.qual[g];
+            uint32_t al = fr.allele[g];
+            uint32_t pr = fr.present[g];
+            fb_group_weights(q, pr, lut, w);
+            uint2 m = mh[lg0 + (g - g0)];
+            uint32_t same, ne;
+            fb_group_masks(al, m, same, ne);
+            diffbits = pr & ne & ~same;
+            emptybits = pr & ~ne & 0xFFFFu;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) w[k] = 0;
+        }
+        long long Wl = (long long)fb_masked_sum(w, diffbits);
+        unsigned anyE = __ballot_sync(0xFFFFFFFFu, emptybits != 0);
+        if (!anyE) {
+            long long tot = (long long)fb_warp_sum_u64((unsigned long long)Wl);
+            if (ss.add_dyadic_run(tot)) continue;
+        }
+        for (int l = 0; l < 32; ++l) {
+            long long Wl_l = __shfl_sync(0xFFFFFFFFu, Wl, l);
+            uint32_t eb = __shfl_sync(0xFFFFFFFFu, emptybits, l);
+            uint32_t db = __shfl_sync(0xFFFFFFFFu, diffbits, l);
+            if (eb == 0) {
+                if (ss.add_dyadic_run(Wl_l)) continue;
+            }
+            __syncwarp();
+            if (lane == l) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) wscratch[k] = w[k];
+            }
+            __syncwarp();
+            uint32_t bits = eb | db;
+            while (bits) {
+                int k = __ffs(bits) - 1;
+                bits &= bits - 1;
+                if ((eb >> k) & 1u)
+                    ss.add_eps(eps, 0);
+                else
+                    ss.add_dyadic((long long)wscratch[k]);
+            }
+        }
+    }
+    return ss.S;
+}
+
+template <int P>
+__device__ void fb_sweep_body(const SweepArgs &a, const InstDev &in, int ii, uint64_t slot, const RInfo ri,
+                              const uint32_t *lut_s, uint32_t *wscratch) {
+    const uint32_t lane = fb_lane();
+    const int cur = a.st[ii].cur;
+    const uint2 *__restrict__ masks = a.masks[cur] + in.mask_off;
+    const uint32_t g0 = a.fr.gptr[ri.rid], g1 = a.fr.gptr[ri.rid + 1];
+    unsigned long long total = 0, same[P], emptyw[P];
+    uint32_t ne_cnt[P];
+#pragma unroll
+    for (int h = 0; h < P; ++h) {
+        same[h] = 0;
+        emptyw[h] = 0;
+        ne_cnt[h] = 0;
+    }
+    for (uint32_t g = g0 + lane; g < g1; g += 32) {
+        uint4 q = a.fr.qual[g];
+        uint32_t al = a.fr.allele[g];
+        uint32_t pr = a.fr.present[g];
+        uint32_t w[16];
+        fb_group_weights(q, pr, lut_s, w);
+        uint32_t t = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) t += w[k];
+        total += t;
+        const uint32_t lg = ri.lg0 + (g - g0);
+#pragma unroll
+        for (int h = 0; h < P; ++h) {
+            uint2 m = masks[(uint32_t)h * in.ng + lg];
+            uint32_t sb, ne;
+            fb_group_masks(al, m, sb, ne);
+            same[h] += fb_masked_sum(w, sb);
+            uint32_t eb = pr & ~ne & 0xFFFFu;
+            if (eb) {
+                emptyw[h] += fb_masked_sum(w, eb);
+                ne_cnt[h] += __popc(eb);
+            }
+        }
+    }
+    total = fb_warp_sum_u64(total);
+    double diff_f[P];
+    long long same_q[P], diff_q[P];
+#pragma unroll
+    for (int h = 0; h < P; ++h) {
+        same[h] = fb_warp_sum_u64(same[h]);
+        emptyw[h] = fb_warp_sum_u64(emptyw[h]);
+        ne_cnt[h] = fb_warp_sum_u32(ne_cnt[h]);
+        same_q[h] = (long long)same[h];
+        diff_q[h] = (long long)(total - same[h] - emptyw[h]);
+    }
+#pragma unroll
+    for (int h = 0; h < P; ++h) {
+        if (ne_cnt[h] == 0) {
+            diff_f[h] = fb_q26_to_f64(diff_q[h]);
+        } else if (a.eps_safe) {
+            // every term is a multiple of 2^-26: the sum is exact in any order
+            diff_f[h] = fb_q26_to_f64(diff_q[h] + (long long)ne_cnt[h] * (long long)(a.eps * FB_Q26));
+        } else {
+            diff_f[h] = fb_replay_diff(a.fr, g0, g1, masks + (uint32_t)h * in.ng, ri.lg0, lut_s, a.eps, wscratch);
+        }
+    }
+    if (lane != 0) return;
+    if (a.mode == FB_SWEEP_SCORE) {
+#pragma unroll
+        for (int h = 0; h < P; ++h) {
+            uint64_t o = slot * P + h;
+            if (a.o_same) a.o_same[o] = fb_q26_to_f64(same_q[h]);
+            if (a.o_diff) a.o_diff[o] = diff_f[h];
+            if (a.o_same_q26) a.o_same_q26[o] = same_q[h];
+            if (a.o_diff_q26) a.o_diff_q26[o] = diff_q[h];
+            if (a.o_nempty) a.o_nempty[o] = ne_cnt[h];
+        }
+    } else {
+        // opt_iterate (local_clustering.rs:300-325): gain of moving the read from its haplotype i to j
+        const uint32_t r_local = (uint32_t)(slot - in.assign_off);
+        const int i = a.assign[cur][slot];
+        double *gout = a.gain + in.gain_off + (uint64_t)r_local * P;
+        const bool skip = (i >= P) || a.st[ii].sizes[cur][i] <= 1;  // `if partition[i].len() <= 1 { continue; }`
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            double g = 0.0;
+            if (!skip && j != i) {
+                double errors_read = 0.0;
+#pragma unroll
+                for (int h = 0; h < P; ++h)
+                    if (h == i) errors_read = diff_f[h];
+                double diff_score = errors_read - diff_f[j];
+                if (diff_score > 0.0) g = diff_score;
+            }
+            gout[j] = g;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(FB_SWEEP_WARPS * 32) k_sweep(SweepArgs a) {
+    __shared__ uint32_t lut_s[256];
+    __shared__ uint32_t wscr[FB_SWEEP_WARPS][16];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut_s[i] = a.lut[i];
+    __syncthreads();
+    const uint64_t total = a.assign_prefix[a.n_inst];
+    const uint64_t slot = (uint64_t)blockIdx.x * FB_SWEEP_WARPS + (threadIdx.x >> 5);
+    if (slot >= total) return;
+    const int ii = fb_upper_seg(a.assign_prefix, a.n_inst, slot);
+    const InstDev in = a.inst[ii];
+    if (a.mode == FB_SWEEP_MOVES && !a.st[ii].active) return;
+    const RInfo ri = a.rinfo[in.read_off + (uint32_t)(slot - in.assign_off)];
+    uint32_t *ws = wscr[threadIdx.x >> 5];
+    switch (in.ploidy) {
+        case 1: fb_sweep_body<1>(a, in, ii, slot, ri, lut_s, ws); break;
+        case 2: fb_sweep_body<2>(a, in, ii, slot, ri, lut_s, ws); break;
+        case 3: fb_sweep_body<3>(a, in, ii, slot, ri, lut_s, ws); break;
+        case 4: fb_sweep_body<4>(a, in, ii, slot, ri, lut_s, ws); break;
+        case 5: fb_sweep_body<5>(a, in, ii, slot, ri, lut_s, ws); break;
+        case 6: fb_sweep_body<6>(a, in, ii, slot, ri, lut_s, ws); break;
+        case 7: fb_sweep_body<7>(a, in, ii, slot, ri, lut_s, ws); break;
+        case 8: fb_sweep_body<8>(a, in, ii, slot, ri, lut_s, ws); break;
+        default: break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K2 hap_histogram.  One CTA per (instance, tile of 1024 positions, haplotype); every thread owns 4 consecutive
+// positions x 4 alleles of exact 64-bit counters (thread-private columns of shared memory: no atomics) and the CTA
+// streams the block's reads assigned to that haplotype.  Reproduces utils_frags.rs:160-184 set_to_seq_dict /
+// hap_block_from_partition; the epilogue derives the is-max planes the sweep consumes (consensus of utils_frags.rs:53-69).
+// ---------------------------------------------------------------------------------------------------------------------
+#define FB_HIST_THREADS 256
+#define FB_HIST_TILE_GROUPS 64  // 1024 positions
+
+struct HistArgs {
+    DFragsDev fr;
+    const InstDev *inst;
+    const InstState *st;
+    int n_inst;
+    const uint64_t *tile_prefix;  // [n_inst+1] prefix of tiles(i) * ploidy(i)
+    const RInfo *rinfo;
+    const uint8_t *assign[2];
+    uint64_t *cnt[2];
+    uint2 *masks[2];
+    const uint32_t *lut;
+    int use_phred;    // 0: every cell weighs 1.0 (get_mec_stats_epsilon_no_phred / get_errors_cov_from_frags)
+    int which;        // 0: the instance's current buffer, 1: the other ("new") one, 2: explicit buffer `buf`
+    int buf;
+    int only_active;  // skip instances whose optimize loop has finished
+    int assign_cur;   // 1: read the partition from the CURRENT buffer whatever buffer the table is written to
+};
+
+__global__ void __launch_bounds__(FB_HIST_THREADS) k_hist(HistArgs a) {
+    __shared__ unsigned long long cnt_s[16 * FB_HIST_THREADS];  // [k*4 + allele][thread]
+    __shared__ uint32_t lut_s[256];
+    const int t = threadIdx.x;
+    for (int i = t; i < 256; i += FB_HIST_THREADS) lut_s[i] = a.use_phred ? a.lut[i] : (1u << 26);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) cnt_s[i * FB_HIST_THREADS + t] = 0ULL;
+    const uint64_t cta = blockIdx.x;
+    const int ii = fb_upper_seg(a.tile_prefix, a.n_inst, cta);
+    const InstDev in = a.inst[ii];
+    if (a.only_active && !a.st[ii].active) return;
+    const uint32_t rel = (uint32_t)(cta - a.tile_prefix[ii]);
+    const uint32_t tile = rel / in.ploidy, h = rel % in.ploidy;
+    const int cur = a.st[ii].cur;
+    const int buf = a.which == 0 ? cur : (a.which == 1 ? (cur ^ 1) : a.buf);
+    const uint8_t *__restrict__ assign = a.assign[a.assign_cur ? cur : buf] + in.assign_off;
+    const RInfo *__restrict__ rinfo = a.rinfo + in.read_off;
+    const uint32_t tg0 = tile * FB_HIST_TILE_GROUPS;       // first block-local group of the tile
+    const uint32_t G = tg0 + (t >> 2);                     // this thread's block-local group
+    const uint32_t sub = t & 3;                            // which 4 cells of the group
+    __syncthreads();
+    const uint32_t *__restrict__ qual32 = reinterpret_cast<const uint32_t *>(a.fr.qual);
+    for (uint32_t rl = 0; rl < in.n_reads; ++rl) {
+        const RInfo ri = rinfo[rl];
+        if (ri.lg0 >= tg0 + FB_HIST_TILE_GROUPS) break;  // reads are sorted by first position
+        if (ri.lg1 <= tg0) continue;
+        if (assign[rl] != h) continue;
+        if (G < ri.lg0 || G >= ri.lg1) continue;
+        const uint32_t g = ri.gbase + G;
+        const uint32_t q = qual32[(uint64_t)g * 4 + sub];
+        const uint32_t al = a.fr.allele[g];
+        const uint32_t pr = a.fr.present[g];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t c = sub * 4 + k;
+            if ((pr >> c) & 1u) {
+                const uint32_t w = lut_s[(q >> (8 * k)) & 0xFFu];
+                const uint32_t av = ((al >> c) & 1u) | (((al >> (16 + c)) & 1u) << 1);
+                unsigned long long *p = &cnt_s[(k * 4 + av) * FB_HIST_THREADS + t];
+                *p = (*p + w) | FB_PRESENT;
+            }
+        }
+    }
+    // epilogue: counts -> global [h][pos][4]; is-max planes -> global [h][group]
+    const bool in_range = G < in.ng;
+    uint32_t pl[4] = {0, 0, 0, 0};
+    if (in_range) {
+        uint64_t *out = a.cnt[buf] + in.cnt_off + (((uint64_t)h * in.ng + G) * 16 + sub * 4) * 4;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            unsigned long long c4[4];
+            unsigned long long mx = 0;
+#pragma unroll
+            for (int av = 0; av < 4; ++av) {
+                c4[av] = cnt_s[(k * 4 + av) * FB_HIST_THREADS + t];
+                unsigned long long v = c4[av] & FB_CNT_MASK;
+                mx = v > mx ? v : mx;
+            }
+            reinterpret_cast<ulonglong2 *>(out + k * 4)[0] = make_ulonglong2(c4[0], c4[1]);
+            reinterpret_cast<ulonglong2 *>(out + k * 4)[1] = make_ulonglong2(c4[2], c4[3]);
+            if (mx > 0) {
+#pragma unroll
+                for (int av = 0; av < 4; ++av)
+                    if ((c4[av] & FB_CNT_MASK) == mx) pl[av] |= 1u << (sub * 4 + k);
+            }
+        }
+    }
+    // combine the 4 threads of a group
+#pragma unroll
+    for (int av = 0; av < 4; ++av) {
+        pl[av] |= __shfl_xor_sync(0xFFFFFFFFu, pl[av], 1);
+        pl[av] |= __shfl_xor_sync(0xFFFFFFFFu, pl[av], 2);
+    }
+    if (in_range && sub == 0)
+        a.masks[buf][in.mask_off + (uint64_t)h * in.ng + G] = make_uint2(pl[0] | (pl[1] << 16), pl[2] | (pl[3] << 16));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K3 mec_reduce.  One warp per (instance, haplotype).  Reproduces local_clustering.rs:218-260 get_mec_stats_epsilon
+// (and :187-215 on the unweighted table): per position in ascending order: bases += max count; errors += the other
+// counts in ascending-count order; errors += epsilon when max <= 1.0.  The two f64 accumulators are emulated exactly
+// (SeqSum) in canonical position order.
+// ---------------------------------------------------------------------------------------------------------------------
+struct MecArgs {
+    const InstDev *inst;
+    const InstState *st;
+    int n_inst;
+    const uint64_t *hap_prefix;  // [n_inst+1] prefix of ploidy(i)
+    const uint64_t *cnt[2];
+    double *mec[2];  // [mec_off + h][2] = (bases, errors)
+    double eps;
+    int eps_safe;
+    int which, buf, only_active;
+};
+
+__device__ __forceinline__ void fb_sort4(unsigned long long (&v)[4], int n) {
+    // stable insertion sort ascending of the first n entries
+    for (int i = 1; i < n; ++i) {
+        unsigned long long x = v[i];
+        int j = i - 1;
+        while (j >= 0 && v[j] > x) {
+            v[j + 1] = v[j];
+            --j;
+        }
+        v[j + 1] = x;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_mec(MecArgs a) {
+    const uint64_t wid = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wid >= a.hap_prefix[a.n_inst]) return;
+    const uint32_t lane = fb_lane();
+    const int ii = fb_upper_seg(a.hap_prefix, a.n_inst, wid);
+    const InstDev in = a.inst[ii];
+    if (a.only_active && !a.st[ii].active) return;
+    const uint32_t h = (uint32_t)(wid - a.hap_prefix[ii]);
+    const int cur = a.st[ii].cur;
+    const int buf = a.which == 0 ? cur : (a.which == 1 ? (cur ^ 1) : a.buf);
+    const ulonglong2 *__restrict__ c2 =
+        reinterpret_cast<const ulonglong2 *>(a.cnt[buf] + in.cnt_off + (uint64_t)h * in.ng * 64);
+    const uint32_t npos = in.ng * 16;
+    SeqSum bases, errors;
+    bases.init();
+    errors.init();
+    for (uint32_t p0 = 0; p0 < npos; p0 += 32) {
+        const uint32_t p = p0 + lane;
+        unsigned long long v[4];
+        int n = 0;
+        if (p < npos) {
+            ulonglong2 x = c2[(uint64_t)p * 2], y = c2[(uint64_t)p * 2 + 1];
+            unsigned long long c[4] = {x.x, x.y, y.x, y.y};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (c[k] & FB_PRESENT) v[n++] = c[k] & FB_CNT_MASK;  // allele_counts (keys present), ascending allele
+        }
+        for (int k = n; k < 4; ++k) v[k] = 0;
+        fb_sort4(v, n);  // allele_counts.sort_by(count): stable, ascending
+        long long mx = n ? (long long)v[n - 1] : 0;
+        long long others = 0;
+        for (int k = 0; k + 1 < n; ++k) others += (long long)v[k];
+        const bool has_eps = n > 0 && mx <= (1LL << 26);  // cons_bases <= 1.0
+        const unsigned any = __ballot_sync(0xFFFFFFFFu, n > 0);
+        if (!any) continue;
+        // bases: one dyadic item per position
+        {
+            long long tot = (long long)fb_warp_sum_u64((unsigned long long)mx);
+            if (!bases.add_dyadic_run(tot)) {
+                for (int l = 0; l < 32; ++l) {
+                    long long m_l = __shfl_sync(0xFFFFFFFFu, mx, l);
+                    int n_l = __shfl_sync(0xFFFFFFFFu, n, l);
+                    if (n_l) bases.add_dyadic(m_l);
+                }
+            }
+        }
+        // errors: up to 3 dyadic items then an optional epsilon per position
+        {
+            const unsigned anyE = __ballot_sync(0xFFFFFFFFu, has_eps);
+            bool done = false;
+            if (!anyE) {
+                long long tot = (long long)fb_warp_sum_u64((unsigned long long)others);
+                done = errors.add_dyadic_run(tot);
+            }
+            if (!done) {
+                for (int l = 0; l < 32; ++l) {
+                    int n_l = __shfl_sync(0xFFFFFFFFu, n, l);
+                    long long o_l = __shfl_sync(0xFFFFFFFFu, others, l);
+                    long long v0 = __shfl_sync(0xFFFFFFFFu, (long long)v[0], l);
+                    long long v1 = __shfl_sync(0xFFFFFFFFu, (long long)v[1], l);
+                    long long v2 = __shfl_sync(0xFFFFFFFFu, (long long)v[2], l);
+                    int e_l = __shfl_sync(0xFFFFFFFFu, (int)has_eps, l);
+                    if (n_l == 0) continue;
+                    if (!errors.add_dyadic_run(o_l)) {
+                        if (n_l > 1) errors.add_dyadic(v0);
+                        if (n_l > 2) errors.add_dyadic(v1);
+                        if (n_l > 3) errors.add_dyadic(v2);
+                    }
+                    if (e_l) errors.add_eps(a.eps, a.eps_safe);
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+        a.mec[buf][((uint64_t)in.mec_off + h) * 2 + 0] = bases.S;
+        a.mec[buf][((uint64_t)in.mec_off + h) * 2 + 1] = errors.S;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// reads per haplotype of a buffer (thread per instance-hap would be enough; one warp per instance keeps it simple)
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void k_sizes(const InstDev *inst, InstState *st, int n_inst, const uint8_t *assign0, const uint8_t *assign1,
+                        int which /*0 cur, 1 other*/) {
+    const int ii = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (ii >= n_inst) return;
+    const uint32_t lane = fb_lane();
+    const InstDev in = inst[ii];
+    const int buf = which == 0 ? st[ii].cur : (st[ii].cur ^ 1);
+    const uint8_t *as = (buf == 0 ? assign0 : assign1) + in.assign_off;
+    uint32_t cnt[FB_MAXP];
+#pragma unroll
+    for (int h = 0; h < FB_MAXP; ++h) cnt[h] = 0;
+    for (uint32_t r = lane; r < in.n_reads; r += 32) {
+        const uint32_t hv = as[r];
+#pragma unroll
+        for (int h = 0; h < FB_MAXP; ++h) cnt[h] += (hv == (uint32_t)h);
+    }
+#pragma unroll
+    for (int h = 0; h < FB_MAXP; ++h) {
+        cnt[h] = fb_warp_sum_u32(cnt[h]);
+        if (lane == 0) st[ii].sizes[buf][h] = cnt[h];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K4 move selection + application.  One CTA per instance.  Reproduces opt_iterate, local_clustering.rs:327-357:
+// stable sort of the candidate moves by gain (descending; ties keep generation order = haplotype i asc, read asc,
+// j asc under the canonical set order), number_of_moves = len/10 (len/3+1 when that is 0), then the sequential walk
+// with the "already moved" / "source haplotype would become empty" guards and the `mv_num > number_of_moves` break.
+// ---------------------------------------------------------------------------------------------------------------------
+struct MoveRec {
+    unsigned long long key;  // ~gain bits: ascending key == descending gain
+    uint32_t gen;            // generation index (tie-break, ascending)
+    uint32_t info;           // read_local | j << 24 | i << 28
+};
+
+struct SelectArgs {
+    const InstDev *inst;
+    InstState *st;
+    int n_inst;
+    const double *gain;
+    uint8_t *assign[2];
+    MoveRec *moves;                // scratch, [gain_off ... ) rounded to pow2 per instance by the host
+    const uint64_t *moves_off;     // [n_inst] offset into moves
+    const uint32_t *moves_cap;     // [n_inst] pow2 capacity
+};
+
+__device__ __forceinline__ bool fb_move_less(const MoveRec &x, const MoveRec &y) {
+    return x.key < y.key || (x.key == y.key && x.gen < y.gen);
+}
+
+#define FB_SELECT_THREADS 256
+
+__global__ void __launch_bounds__(FB_SELECT_THREADS) k_select(SelectArgs a) {
+    const int ii = blockIdx.x;
+    InstState &st = a.st[ii];
+    if (!st.active) return;
+    const InstDev in = a.inst[ii];
+    const int cur = st.cur;
+    const uint32_t P = in.ploidy;
+    const uint8_t *__restrict__ as_cur = a.assign[cur] + in.assign_off;
+    uint8_t *__restrict__ as_new = a.assign[cur ^ 1] + in.assign_off;
+    const double *__restrict__ gain = a.gain + in.gain_off;
+    MoveRec *mv = a.moves + a.moves_off[ii];
+    const uint32_t cap = a.moves_cap[ii];
+    const int t = threadIdx.x;
+    __shared__ uint32_t s_scan[FB_SELECT_THREADS];
+    __shared__ uint32_t s_base;
+    __shared__ uint32_t s_M;
+    if (t == 0) s_base = 0;
+    __syncthreads();
+    // 1. compaction in generation order: for i in 0..P, reads ascending, j ascending
+    for (uint32_t i = 0; i < P; ++i) {
+        for (uint32_t r0 = 0; r0 < in.n_reads; r0 += FB_SELECT_THREADS) {
+            const uint32_t r = r0 + t;
+            uint32_t cnt = 0;
+            if (r < in.n_reads && as_cur[r] == i)
+                for (uint32_t j = 0; j < P; ++j) cnt += gain[(uint64_t)r * P + j] > 0.0;
+            s_scan[t] = cnt;
+            __syncthreads();
+            // inclusive scan (Hillis-Steele)
+            for (int o = 1; o < FB_SELECT_THREADS; o <<= 1) {
+                uint32_t v = t >= o ? s_scan[t - o] : 0;
+                __syncthreads();
+                s_scan[t] += v;
+                __syncthreads();
+            }
+            uint32_t off = s_base + s_scan[t] - cnt;
+            if (cnt) {
+                for (uint32_t j = 0; j < P; ++j) {
+                    double g = gain[(uint64_t)r * P + j];
+                    if (g > 0.0) {
+                        MoveRec m;
+                        m.key = ~(unsigned long long)__double_as_longlong(g);
+                        m.gen = off;
+                        m.info = r | (j << 24) | (i << 28);
+                        mv[off++] = m;
+                    }
+                }
+            }
+            __syncthreads();
+            if (t == FB_SELECT_THREADS - 1) s_base += s_scan[t];
+            __syncthreads();
+        }
+    }
+    const uint32_t M = s_base;
+    if (t == 0) {
+        s_M = M;
+        st.n_moves = (int)M;
+    }
+    // new_part = partition.clone()
+    for (uint32_t r = t; r < in.n_reads; r += FB_SELECT_THREADS) as_new[r] = as_cur[r];
+    if (M == 0) {
+        if (t == 0)
+            for (uint32_t h = 0; h < FB_MAXP; ++h) st.sizes[cur ^ 1][h] = st.sizes[cur][h];
+        return;
+    }
+    // 2. bitonic sort of (key, gen) ascending over the next power of two >= M (padding sorts last)
+    uint32_t n2 = 1;
+    while (n2 < M) n2 <<= 1;
+    if (n2 > cap) n2 = cap;  // host guarantees cap >= next_pow2(max moves)
+    for (uint32_t x = M + t; x < n2; x += FB_SELECT_THREADS) {
+        MoveRec m;
+        m.key = ~0ULL;
+        m.gen = 0xFFFFFFFFu;
+        m.info = 0xFFFFFFFFu;
+        mv[x] = m;
+    }
+    __syncthreads();
+    for (uint32_t k = 2; k <= n2; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t x = t; x < n2; x += FB_SELECT_THREADS) {
+                uint32_t y = x ^ j;
+                if (y > x) {
+                    MoveRec mx = mv[x], my = mv[y];
+                    bool up = (x & k) == 0;
+                    bool sw = up ? fb_move_less(my, mx) : fb_move_less(mx, my);
+                    if (sw) {
+                        mv[x] = my;
+                        mv[y] = mx;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // 3. sequential application
+    if (t == 0) {
+        uint32_t sizes[FB_MAXP];
+        for (uint32_t h = 0; h < FB_MAXP; ++h) sizes[h] = st.sizes[cur][h];
+        uint32_t number_of_moves = M / 10;
+        if (number_of_moves == 0 && M > 0) number_of_moves = M / 3 + 1;
+        for (uint32_t mv_num = 0; mv_num < M; ++mv_num) {
+            const uint32_t info = mv[mv_num].info;
+            const uint32_t r = info & 0xFFFFFFu, j = (info >> 24) & 0xFu, i = info >> 28;
+            if (as_new[r] != as_cur[r]) continue;  // moved_reads.contains(read): a moved read always changes haplotype
+            if (sizes[i] == 1) continue;
+            as_new[r] = (uint8_t)j;
+            sizes[j] += 1;
+            sizes[i] -= 1;
+            if (mv_num > number_of_moves) break;
+        }
+        for (uint32_t h = 0; h < FB_MAXP; ++h) st.sizes[cur ^ 1][h] = sizes[h];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// accept / reject of optimize_clustering (local_clustering.rs:97-99, 105-127).  One thread per instance.
+// ---------------------------------------------------------------------------------------------------------------------
+struct AcceptArgs {
+    const InstDev *inst;
+    InstState *st;
+    int n_inst;
+    const double *mec[2];
+    int init;  // 1: set prev_score from the current buffer (lines 97-99)
+    uint32_t iter, max_iters;
+    int *n_active;  // device counter of instances still iterating
+};
+
+__global__ void k_accept(AcceptArgs a) {
+    const int ii = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ii >= a.n_inst) return;
+    InstState &st = a.st[ii];
+    const InstDev in = a.inst[ii];
+    if (a.init) {
+        double s = 0.0;  // binom_vec.iter().map(|x| x.1).sum()
+        for (uint32_t h = 0; h < in.ploidy; ++h) s += a.mec[st.cur][((uint64_t)in.mec_off + h) * 2 + 1];
+        st.prev_score = s * -1.;
+        st.n_hist += 1;
+        return;
+    }
+    if (!st.active) return;
+    const int nb = st.cur ^ 1;
+    double s = 0.0;
+    for (uint32_t h = 0; h < in.ploidy; ++h) s += a.mec[nb][((uint64_t)in.mec_off + h) * 2 + 1];
+    const double new_score = s * -1.;
+    st.new_score = new_score;
+    st.n_opt_iterate += 1;
+    st.n_hist += 1;
+    if (new_score > st.prev_score) {
+        st.prev_score = new_score;
+        st.cur = nb;
+        st.accepted += 1;
+        if (a.iter + 1 >= a.max_iters)
+            st.active = 0;
+        else
+            atomicAdd(a.n_active, 1);
+    } else {
+        st.active = 0;
+    }
+}

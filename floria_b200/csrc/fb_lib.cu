@@ -1,0 +1,700 @@
+// fb_lib.cu — the C-ABI of include/floria_b200.h.  Host logic only; kernels live in fb_kernels.cuh / fb_beam.cuh.
+#include <math.h>
+#include <stdlib.h>
+
+#include <memory>
+
+#include "fb_engine.cuh"
+#include "fb_beam_host.cuh"
+
+// ======================================================================================================================
+// context
+// ======================================================================================================================
+static int fb_set_lut(fb_ctx *ctx, const fb_params *prm) {
+    float lut[256];
+    if (prm && prm->phred_lut) {
+        memcpy(lut, prm->phred_lut, sizeof(lut));
+    } else {
+        // utils_frags.rs:702-711 phred_scale: 1f32 - 10f32.powf(q as f32 / -10.)
+        for (int q = 0; q < 256; ++q) lut[q] = 1.0f - powf(10.0f, (float)q / -10.0f);
+    }
+    if (ctx->lut_valid && memcmp(lut, ctx->h_lut_f, sizeof(lut)) == 0) return FB_OK;
+    for (int q = 0; q < 256; ++q) {
+        double x = (double)lut[q] * FB_Q26;
+        if (!(x >= 0.0) || x > FB_Q26 || x != floor(x))
+            FB_FAIL(FB_ERR_ARG, "phred_lut[%d] = %g is not a multiple of 2^-26 in [0,1]", q, (double)lut[q]);
+        ctx->h_lut[q] = (uint32_t)x;
+    }
+    memcpy(ctx->h_lut_f, lut, sizeof(lut));
+    FB_CK(cudaMemcpyAsync(ctx->d_lut, ctx->h_lut, sizeof(ctx->h_lut), cudaMemcpyHostToDevice, ctx->stream));
+    FB_CK(cudaStreamSynchronize(ctx->stream));
+    ctx->lut_valid = true;
+    return FB_OK;
+}
+
+static int fb_check_params(fb_ctx *ctx, const fb_params *p, uint32_t ploidy_needed) {
+    if (!p) FB_FAIL(FB_ERR_ARG, "params is NULL");
+    if (p->order_model != 0) FB_FAIL(FB_ERR_ARG, "order_model %u is not implemented (only 0 = canonical)", p->order_model);
+    if (!(p->epsilon > 0.0) || !(p->epsilon < 1.0)) FB_FAIL(FB_ERR_ARG, "epsilon must be in (0,1)");
+    if (ploidy_needed > FB_MAXP) FB_FAIL(FB_ERR_LIMIT, "ploidy %u exceeds the compiled maximum %d", ploidy_needed, FB_MAXP);
+    if (p->reassign_short) FB_FAIL(FB_ERR_ARG, "reassign_short is not implemented on the device path");
+    return fb_set_lut(ctx, p);
+}
+
+extern "C" {
+
+int fb_init(int device, fb_ctx **out) {
+    if (!out) return FB_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_init_err = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                     " (floria_b200 has no CPU fallback)";
+        return FB_ERR_NODEV;
+    }
+    if (device < 0 || device >= n) {
+        g_init_err = "device index out of range";
+        return FB_ERR_ARG;
+    }
+    fb_ctx *ctx = new fb_ctx();
+    ctx->device = device;
+    memset(&ctx->tim, 0, sizeof(ctx->tim));
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreate(&ctx->stream)) != cudaSuccess ||
+        (e = cudaMalloc((void **)&ctx->d_lut, 256 * sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaMalloc((void **)&ctx->d_n_active, sizeof(int))) != cudaSuccess ||
+        (e = cudaMallocHost((void **)&ctx->h_n_active, sizeof(int))) != cudaSuccess) {
+        g_init_err = std::string("fb_init: ") + cudaGetErrorString(e);
+        delete ctx;
+        return FB_ERR_CUDA;
+    }
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    *out = ctx;
+    return FB_OK;
+}
+
+void fb_destroy(fb_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    cudaFree(ctx->d_lut);
+    cudaFree(ctx->d_n_active);
+    if (ctx->h_n_active) cudaFreeHost(ctx->h_n_active);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *fb_last_error(const fb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_init_err.c_str(); }
+
+void fb_params_default(fb_params *p) {
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->epsilon = 0.04;
+    p->div_factor = 0.25;        // constants.rs:5
+    p->prob_cutoff_ln = log(0.01);  // constants.rs:6
+    p->max_number_solns = 10;    // parse_cmd_line.rs:34
+    p->max_ploidy = 5;           // parse_cmd_line.rs:43
+    p->num_iter_optimize = 20;   // constants.rs:3
+    p->ploidy_sensitivity = 2;   // parse_cmd_line.rs:160
+    p->stopping_heuristic = 1;
+    p->order_model = 0;
+    p->block_length = 10000;
+    p->reassign_short = 0;
+    p->phred_lut = nullptr;
+}
+
+int fb_last_timings(const fb_ctx *ctx, fb_timings *out) {
+    if (!ctx || !out) return FB_ERR_ARG;
+    *out = ctx->tim;
+    return FB_OK;
+}
+
+void *fb_stream(const fb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+// ======================================================================================================================
+// data movement
+// ======================================================================================================================
+int fb_frags_upload(fb_ctx *ctx, const fb_frags *fr, fb_dfrags **out) {
+    if (!ctx) return FB_ERR_ARG;
+    if (!fr || !out) FB_FAIL(FB_ERR_ARG, "null argument");
+    *out = nullptr;
+    FB_CK(cudaSetDevice(ctx->device));
+    const uint64_t R = fr->n_reads;
+    if (R >= (1ull << 31)) FB_FAIL(FB_ERR_LIMIT, "too many reads");
+    std::unique_ptr<fb_dfrags> df(new fb_dfrags());
+    df->ctx = ctx;
+    df->n_reads = R;
+    df->nnz = fr->nnz;
+    df->h_first.assign(fr->first, fr->first + R);
+    df->h_last.assign(fr->last, fr->last + R);
+    df->h_nnz.resize(R);
+    df->h_gstart.resize(R);
+    df->h_gptr.resize(R + 1);
+    df->h_prefmax_last.resize(R);
+    uint64_t ng = 0;
+    uint32_t pm = 0;
+    if (R && fr->row_ptr[0] != 0) FB_FAIL(FB_ERR_ARG, "row_ptr[0] must be 0");
+    if (R && fr->row_ptr[R] != fr->nnz) FB_FAIL(FB_ERR_ARG, "row_ptr[n_reads] must equal nnz");
+    for (uint64_t i = 0; i < R; ++i) {
+        uint64_t a = fr->row_ptr[i], b = fr->row_ptr[i + 1];
+        if (b <= a) FB_FAIL(FB_ERR_ARG, "read %llu has no cells", (unsigned long long)i);
+        uint32_t f = fr->first[i], l = fr->last[i];
+        if (f < 1 || l < f) FB_FAIL(FB_ERR_ARG, "read %llu: bad first/last", (unsigned long long)i);
+        if (fr->pos[a] != f || fr->pos[b - 1] != l)
+            FB_FAIL(FB_ERR_ARG, "read %llu: first/last_position must be the min/max of its positions",
+                    (unsigned long long)i);
+        for (uint64_t c = a; c < b; ++c) {
+            if (c > a && fr->pos[c] <= fr->pos[c - 1])
+                FB_FAIL(FB_ERR_ARG, "read %llu: positions must be strictly ascending", (unsigned long long)i);
+            if (fr->allele[c] > 3)
+                FB_FAIL(FB_ERR_ARG, "read %llu: allele %u > 3 (packed layout holds 2-bit alleles)",
+                        (unsigned long long)i, (unsigned)fr->allele[c]);
+        }
+        if (i > 0) {
+            // Frag::cmp (types_structs.rs:87-93): first asc, last desc, counter_id asc
+            uint32_t pf = fr->first[i - 1], pl = fr->last[i - 1];
+            if (f < pf || (f == pf && l > pl))
+                FB_FAIL(FB_ERR_ARG, "reads must be sorted by Frag::cmp (violated at read %llu)", (unsigned long long)i);
+        }
+        df->h_nnz[i] = (uint32_t)(b - a);
+        uint32_t g0 = (f - 1) >> 4, g1 = (l - 1) >> 4;
+        df->h_gstart[i] = g0;
+        df->h_gptr[i] = (uint32_t)ng;
+        ng += (uint64_t)(g1 - g0 + 1);
+        if (ng >= (1ull << 32) - 64) FB_FAIL(FB_ERR_LIMIT, "more than 2^32 groups");
+        pm = std::max(pm, l);
+        df->h_prefmax_last[i] = pm;
+    }
+    df->h_gptr[R] = (uint32_t)ng;
+    df->n_groups = ng;
+    int rc;
+    cudaEvent_t e0 = fb_event(ctx);
+    // temporary CSR on the device
+    uint64_t *d_row = nullptr;
+    uint32_t *d_pos = nullptr;
+    uint8_t *d_al = nullptr, *d_q = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_row);
+        cudaFree(d_pos);
+        cudaFree(d_al);
+        cudaFree(d_q);
+    };
+    if ((rc = fb_upload(ctx, &d_row, fr->row_ptr, R + 1)) || (rc = fb_upload(ctx, &d_pos, fr->pos, fr->nnz)) ||
+        (rc = fb_upload(ctx, &d_al, fr->allele, fr->nnz)) || (rc = fb_upload(ctx, &d_q, fr->qual, fr->nnz)) ||
+        (rc = fb_upload(ctx, &df->d_first, df->h_first)) || (rc = fb_upload(ctx, &df->d_last, df->h_last)) ||
+        (rc = fb_upload(ctx, &df->d_nnz, df->h_nnz)) || (rc = fb_upload(ctx, &df->d_gstart, df->h_gstart)) ||
+        (rc = fb_upload(ctx, &df->d_gptr, df->h_gptr)) || (rc = fb_dalloc(ctx, &df->d_qual, ng + 1)) ||
+        (rc = fb_dalloc(ctx, &df->d_allele, ng + 1)) || (rc = fb_dalloc(ctx, &df->d_present, ng + 2))) {
+        cleanup();
+        fb_frags_free(ctx, df.release());
+        return rc;
+    }
+    cudaEvent_t e1 = fb_event(ctx);
+    cudaMemsetAsync(df->d_qual, 0, (ng + 1) * sizeof(uint4), ctx->stream);
+    cudaMemsetAsync(df->d_allele, 0, (ng + 1) * sizeof(uint32_t), ctx->stream);
+    cudaMemsetAsync(df->d_present, 0, (ng + 2) * sizeof(uint16_t), ctx->stream);
+    if (fr->nnz) {
+        k_pack<<<(unsigned)((fr->nnz + 255) / 256), 256, 0, ctx->stream>>>(
+            fr->nnz, R, d_row, d_pos, d_al, d_q, df->d_gstart, df->d_gptr, reinterpret_cast<uint8_t *>(df->d_qual),
+            df->d_allele, reinterpret_cast<uint32_t *>(df->d_present));
+        ctx->tim.n_launches++;
+    }
+    cudaEvent_t e2 = fb_event(ctx);
+    cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+    if (ce == cudaSuccess) ce = cudaGetLastError();
+    cleanup();
+    if (ce != cudaSuccess) {
+        ctx->err = std::string("fb_frags_upload: ") + cudaGetErrorString(ce);
+        fb_frags_free(ctx, df.release());
+        return FB_ERR_CUDA;
+    }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ctx->tim.upload_ms += ms;
+    cudaEventElapsedTime(&ms, e1, e2);
+    ctx->tim.pack_ms += ms;
+    df->bytes = ng * 22;
+    *out = df.release();
+    return FB_OK;
+}
+
+void fb_frags_free(fb_ctx *ctx, fb_dfrags *df) {
+    if (!df) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    cudaFree(df->d_first);
+    cudaFree(df->d_last);
+    cudaFree(df->d_nnz);
+    cudaFree(df->d_gstart);
+    cudaFree(df->d_gptr);
+    cudaFree(df->d_qual);
+    cudaFree(df->d_allele);
+    cudaFree(df->d_present);
+    delete df;
+}
+
+uint64_t fb_dfrags_bytes(const fb_dfrags *df) { return df ? df->bytes : 0; }
+
+// ======================================================================================================================
+// host-side helpers
+// ======================================================================================================================
+// utils_frags.rs:405-463 get_range_with_lengths
+int64_t fb_get_range_with_lengths(const uint64_t *snp_to_genome_pos, uint64_t n, uint64_t block_length,
+                                  uint64_t overlap_len, double minimal_density, uint32_t *lo, uint32_t *hi,
+                                  uint64_t cap) {
+    if (n == 0) return 0;
+    int64_t cnt = 0;
+    auto emit = [&](uint32_t a, uint32_t b) {
+        if ((uint64_t)cnt < cap) {
+            lo[cnt] = a + 1;  // line 461: 1-indexed
+            hi[cnt] = b + 1;
+        }
+        cnt++;
+    };
+    uint64_t cum_pos = 0, last_pos = snp_to_genome_pos[0];
+    uint32_t left_endpoint = 0, new_left_end = 0;
+    bool hit_new_left = false;
+    for (uint64_t ii = 0; ii < n; ++ii) {
+        const uint64_t pos = snp_to_genome_pos[ii];
+        const uint32_t i = (uint32_t)ii;
+        if (ii == n - 1) {
+            emit(left_endpoint, i);
+            break;
+        }
+        if (pos < last_pos) return -1;  // "VCF malformed. Positions are not increasing" (process::exit in the reference)
+        cum_pos += pos - last_pos;
+        last_pos = pos;
+        if (cum_pos > block_length - overlap_len && !hit_new_left) {
+            new_left_end = i;
+            hit_new_left = true;
+        }
+        if (cum_pos > block_length) {
+            cum_pos = 0;
+            const double snp_density = (double)(i - left_endpoint) / (double)block_length;
+            if (snp_density > minimal_density) emit(left_endpoint, i - 1);
+            if (snp_to_genome_pos[new_left_end] + block_length < snp_to_genome_pos[new_left_end + 1])
+                left_endpoint = new_left_end;
+            else
+                left_endpoint = new_left_end + 1;
+            last_pos = snp_to_genome_pos[left_endpoint];
+            hit_new_left = false;
+        }
+    }
+    return cnt;
+}
+
+// local_clustering.rs:12-59 find_reads_in_interval
+int64_t fb_find_reads_in_interval(uint32_t start, uint32_t end, uint64_t n_reads, const uint32_t *first,
+                                  const uint32_t *last, uint32_t *out_ids, uint64_t cap) {
+    int64_t cnt = 0;
+    for (uint64_t i = 0; i < n_reads; ++i) {
+        if (last[i] < start) continue;
+        if (first[i] > end) break;
+        if (last[i] - first[i] > 10000) continue;
+        if ((uint64_t)cnt < cap) out_ids[cnt] = (uint32_t)i;
+        cnt++;
+    }
+    return cnt;
+}
+
+}  // extern "C"
+
+// ======================================================================================================================
+// single-instance helpers for the fine-grained entry points
+// ======================================================================================================================
+struct Single {
+    fb_ctx *ctx;
+    fb_dfrags *df = nullptr;
+    Engine eng;
+    bool own_df = false;
+    ~Single() {
+        eng.release();
+        if (own_df && df) fb_frags_free(ctx, df);
+    }
+};
+
+static int fb_check_sel(fb_ctx *ctx, const fb_dfrags *df, uint64_t n_sel, const uint32_t *sel) {
+    if (n_sel && !sel) FB_FAIL(FB_ERR_ARG, "sel is NULL");
+    for (uint64_t i = 0; i < n_sel; ++i) {
+        if (sel[i] >= df->n_reads) FB_FAIL(FB_ERR_ARG, "sel[%llu] out of range", (unsigned long long)i);
+        if (i && sel[i] <= sel[i - 1]) FB_FAIL(FB_ERR_ARG, "sel must be strictly ascending");
+    }
+    return FB_OK;
+}
+
+// upload frags, build a one-block / one-instance engine, upload the given assignment into buffer 0
+static int fb_single_setup(Single &s, fb_ctx *ctx, const fb_frags *fr, uint64_t n_sel, const uint32_t *sel,
+                           const uint8_t *hap, uint32_t ploidy, const fb_params *prm) {
+    s.ctx = ctx;
+    if (!ctx) return FB_ERR_ARG;
+    FB_CK(cudaSetDevice(ctx->device));
+    ctx->ev_used = 0;
+    int rc = fb_check_params(ctx, prm, ploidy);
+    if (rc) return rc;
+    if (ploidy < 1) FB_FAIL(FB_ERR_ARG, "ploidy must be >= 1");
+    if ((rc = fb_frags_upload(ctx, fr, &s.df))) return rc;
+    s.own_df = true;
+    if ((rc = fb_check_sel(ctx, s.df, n_sel, sel))) return rc;
+    s.eng.ctx = ctx;
+    s.eng.df = s.df;
+    std::vector<uint32_t> reads(sel, sel + n_sel);
+    int b = s.eng.add_block(reads);
+    s.eng.add_instance(b, ploidy);
+    if ((rc = s.eng.finalize_and_upload(prm->epsilon))) return rc;
+    if (hap && n_sel) {
+        FB_CK(cudaMemcpyAsync(s.eng.d_assign[0], hap, n_sel, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return FB_OK;
+}
+
+extern "C" {
+
+int fb_score_reads(fb_ctx *ctx, const fb_frags *fr, uint64_t n_sel, const uint32_t *sel, const uint8_t *hap,
+                   uint32_t ploidy, const fb_params *prm, double *same, double *diff, int64_t *same_q26,
+                   int64_t *diff_q26, uint32_t *n_empty) {
+    Single s;
+    int rc = fb_single_setup(s, ctx, fr, n_sel, sel, hap, ploidy, prm);
+    if (rc) return rc;
+    Engine &e = s.eng;
+    if ((rc = e.launch_hist(0, 1, 0))) return rc;
+    const uint64_t n = n_sel * ploidy;
+    double *d_same = nullptr, *d_diff = nullptr;
+    long long *d_sq = nullptr, *d_dq = nullptr;
+    uint32_t *d_ne = nullptr;
+    if ((rc = fb_dalloc(ctx, &d_same, n)) || (rc = fb_dalloc(ctx, &d_diff, n)) || (rc = fb_dalloc(ctx, &d_sq, n)) ||
+        (rc = fb_dalloc(ctx, &d_dq, n)) || (rc = fb_dalloc(ctx, &d_ne, n)))
+        return rc;
+    SweepArgs a = e.sweep_args(FB_SWEEP_SCORE);
+    a.o_same = d_same;
+    a.o_diff = d_diff;
+    a.o_same_q26 = d_sq;
+    a.o_diff_q26 = d_dq;
+    a.o_nempty = d_ne;
+    rc = e.launch_sweep(a);
+    if (!rc) {
+        if (same) cudaMemcpyAsync(same, d_same, n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (diff) cudaMemcpyAsync(diff, d_diff, n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (same_q26) cudaMemcpyAsync(same_q26, d_sq, n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (diff_q26) cudaMemcpyAsync(diff_q26, d_dq, n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (n_empty) cudaMemcpyAsync(n_empty, d_ne, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+        if (ce != cudaSuccess) {
+            ctx->err = std::string("fb_score_reads: ") + cudaGetErrorString(ce);
+            rc = FB_ERR_CUDA;
+        }
+    }
+    cudaFree(d_same);
+    cudaFree(d_diff);
+    cudaFree(d_sq);
+    cudaFree(d_dq);
+    cudaFree(d_ne);
+    e.collect_timings();
+    return rc;
+}
+
+int fb_hap_block_from_partition(fb_ctx *ctx, const fb_frags *fr, uint64_t n_sel, const uint32_t *sel,
+                                const uint8_t *hap, uint32_t ploidy, int use_qual, const fb_params *prm,
+                                uint32_t pos_lo, uint32_t n_pos, double *counts, uint8_t *key_mask) {
+    Single s;
+    int rc = fb_single_setup(s, ctx, fr, n_sel, sel, hap, ploidy, prm);
+    if (rc) return rc;
+    Engine &e = s.eng;
+    if ((rc = e.launch_hist(0, use_qual ? 1 : 0, 0))) return rc;
+    std::vector<uint64_t> h(e.tot_cnt);
+    FB_CK(cudaMemcpyAsync(h.data(), e.d_cnt[0], e.tot_cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FB_CK(cudaStreamSynchronize(ctx->stream));
+    const InstDev &in = e.inst[0];
+    const uint64_t npos_blk = (uint64_t)in.ng * 16;
+    const uint64_t base0 = (uint64_t)in.ag0 * 16;  // position0 of table row 0
+    if (counts) memset(counts, 0, sizeof(double) * (size_t)ploidy * n_pos * 4);
+    if (key_mask) memset(key_mask, 0, (size_t)ploidy * n_pos);
+    for (uint32_t hh = 0; hh < ploidy; ++hh)
+        for (uint64_t p = 0; p < npos_blk; ++p) {
+            uint64_t pos1 = base0 + p + 1;  // 1-based SNP position
+            if (pos1 < pos_lo || pos1 >= (uint64_t)pos_lo + n_pos) continue;
+            uint64_t o = pos1 - pos_lo;
+            for (int a = 0; a < 4; ++a) {
+                uint64_t w = h[((uint64_t)hh * npos_blk + p) * 4 + a];
+                if (counts) counts[((uint64_t)hh * n_pos + o) * 4 + a] = fb_q26_to_f64((int64_t)(w & FB_CNT_MASK));
+                if (key_mask && (w & FB_PRESENT)) key_mask[(uint64_t)hh * n_pos + o] |= (uint8_t)(1u << a);
+            }
+        }
+    e.collect_timings();
+    return FB_OK;
+}
+
+int fb_get_mec_stats_epsilon(fb_ctx *ctx, const fb_frags *fr, uint64_t n_sel, const uint32_t *sel, const uint8_t *hap,
+                             uint32_t ploidy, int use_phred, const fb_params *prm, double *bases, double *errors) {
+    Single s;
+    int rc = fb_single_setup(s, ctx, fr, n_sel, sel, hap, ploidy, prm);
+    if (rc) return rc;
+    Engine &e = s.eng;
+    if ((rc = e.launch_hist(0, use_phred ? 1 : 0, 0))) return rc;
+    if ((rc = e.launch_mec(0, 0))) return rc;
+    std::vector<double> h(ploidy * 2);
+    FB_CK(cudaMemcpyAsync(h.data(), e.d_mec[0], ploidy * 2 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FB_CK(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t i = 0; i < ploidy; ++i) {
+        if (bases) bases[i] = h[i * 2];
+        if (errors) errors[i] = h[i * 2 + 1];
+    }
+    e.collect_timings();
+    return FB_OK;
+}
+
+int fb_optimize_clustering(fb_ctx *ctx, const fb_frags *fr, uint64_t n_sel, const uint32_t *sel, const uint8_t *hap_in,
+                           uint32_t ploidy, const fb_params *prm, uint8_t *hap_out, double *score,
+                           uint32_t *n_rounds) {
+    Single s;
+    int rc = fb_single_setup(s, ctx, fr, n_sel, sel, hap_in, ploidy, prm);
+    if (rc) return rc;
+    Engine &e = s.eng;
+    for (uint64_t i = 0; i < n_sel; ++i)
+        if (hap_in[i] >= ploidy) FB_FAIL(FB_ERR_ARG, "hap_in[%llu] >= ploidy", (unsigned long long)i);
+    if ((rc = e.run_optimize(prm->num_iter_optimize))) return rc;
+    InstState st;
+    FB_CK(cudaMemcpyAsync(&st, e.d_st, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+    FB_CK(cudaStreamSynchronize(ctx->stream));
+    if (hap_out && n_sel) FB_CK(cudaMemcpy(hap_out, e.d_assign[st.cur], n_sel, cudaMemcpyDeviceToHost));
+    if (score) *score = st.prev_score;
+    if (n_rounds) *n_rounds = st.accepted;
+    e.collect_timings();
+    return FB_OK;
+}
+
+int fb_beam_search_phasing(fb_ctx *ctx, const fb_frags *fr, uint64_t n_sel, const uint32_t *sel, uint32_t ploidy,
+                           const fb_params *prm, uint8_t *hap_out, double *best_score, double *tap_same,
+                           double *tap_diff, double *tap_logp, uint64_t tap_cap, uint64_t *tap_n) {
+    Single s;
+    int rc = fb_single_setup(s, ctx, fr, n_sel, sel, nullptr, ploidy, prm);
+    if (rc) return rc;
+    Engine &e = s.eng;
+    BeamTapDev tap;
+    memset(&tap, 0, sizeof(tap));
+    double *d_ts = nullptr, *d_td = nullptr, *d_tp = nullptr;
+    if (tap_cap) {
+        if ((rc = fb_dalloc(ctx, &d_ts, tap_cap)) || (rc = fb_dalloc(ctx, &d_td, tap_cap)) ||
+            (rc = fb_dalloc(ctx, &d_tp, tap_cap)))
+            return rc;
+        tap.same = d_ts;
+        tap.diff = d_td;
+        tap.logp = d_tp;
+        tap.cap = tap_cap;
+    }
+    BeamRun br;
+    rc = fb_run_beam(ctx, e, prm, &tap, br);
+    if (!rc) {
+        if (hap_out && n_sel) cudaMemcpyAsync(hap_out, e.d_assign[0], n_sel, cudaMemcpyDeviceToHost, ctx->stream);
+        if (tap_cap) {
+            uint64_t n = std::min<uint64_t>(tap_cap, br.tap_n.empty() ? 0 : br.tap_n[0]);
+            if (tap_same) cudaMemcpyAsync(tap_same, d_ts, n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+            if (tap_diff) cudaMemcpyAsync(tap_diff, d_td, n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+            if (tap_logp) cudaMemcpyAsync(tap_logp, d_tp, n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        }
+        cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+        if (ce != cudaSuccess) {
+            ctx->err = std::string("fb_beam_search_phasing: ") + cudaGetErrorString(ce);
+            rc = FB_ERR_CUDA;
+        }
+        if (best_score) *best_score = br.best_score.empty() ? 0.0 : br.best_score[0];
+        if (tap_n) *tap_n = br.tap_n.empty() ? 0 : br.tap_n[0];
+    }
+    cudaFree(d_ts);
+    cudaFree(d_td);
+    cudaFree(d_tp);
+    e.collect_timings();
+    return rc;
+}
+
+// ======================================================================================================================
+// batched hot path: get_local_hap_blocks for every block (graph_processing.rs:103-304, 345-362)
+// ======================================================================================================================
+int fb_phase_blocks_resident(fb_ctx *ctx, const fb_dfrags *df, uint64_t n_blocks, const uint32_t *blk_lo,
+                             const uint32_t *blk_hi, const fb_params *prm, fb_block_results **out) {
+    if (!ctx) return FB_ERR_ARG;
+    if (!df || !out || (n_blocks && (!blk_lo || !blk_hi))) FB_FAIL(FB_ERR_ARG, "null argument");
+    *out = nullptr;
+    FB_CK(cudaSetDevice(ctx->device));
+    int rc = fb_check_params(ctx, prm, prm ? prm->max_ploidy : 0);
+    if (rc) return rc;
+    const uint32_t mp = prm->max_ploidy;
+    if (mp < 1) FB_FAIL(FB_ERR_ARG, "max_ploidy must be >= 1");
+    ctx->ev_used = 0;
+    cudaEvent_t ev_start = fb_event(ctx);
+
+    Engine e;
+    e.ctx = ctx;
+    e.df = df;
+    std::vector<int> blk_index(n_blocks, -1);          // block j -> engine block
+    std::vector<int> first_inst(n_blocks, -1);         // block j -> its ploidy-1 instance
+    std::vector<uint32_t> reads;
+    for (uint64_t j = 0; j < n_blocks; ++j) {
+        fb_find_reads(df, blk_lo[j], blk_hi[j], reads);  // graph_processing.rs:121-126
+        if (reads.empty()) continue;                     // :129-131 -> None
+        int b = e.add_block(reads);
+        blk_index[j] = b;
+        for (uint32_t p = 1; p <= mp; ++p) {
+            int ii = e.add_instance(b, p);
+            if (p == 1) first_inst[j] = ii;
+        }
+    }
+    if ((rc = e.finalize_and_upload(prm->epsilon))) return rc;
+
+    // beam_search_phasing for every instance with ploidy > 1 (ploidy 1: every read lands in haplotype 0)
+    BeamRun br;
+    if ((rc = fb_run_beam(ctx, e, prm, nullptr, br))) return rc;
+    // optimize_clustering
+    if ((rc = e.run_optimize(prm->num_iter_optimize))) return rc;
+    // get_mec_stats_epsilon_no_phred on the optimized partition: unweighted histogram into the spare buffer
+    if ((rc = e.launch_hist(1, 0, 0, 0, 1))) return rc;
+    if ((rc = e.launch_mec(1, 0))) return rc;
+    cudaEvent_t ev_compute = fb_event(ctx);
+
+    const int n_inst = e.n_inst();
+    std::vector<InstState> st(n_inst);
+    std::vector<double> mec0(e.tot_mec * 2), mec1(e.tot_mec * 2);
+    std::vector<uint8_t> as0(e.tot_assign), as1(e.tot_assign);
+    if (n_inst) {
+        FB_CK(cudaMemcpyAsync(st.data(), e.d_st, sizeof(InstState) * n_inst, cudaMemcpyDeviceToHost, ctx->stream));
+        FB_CK(cudaMemcpyAsync(mec0.data(), e.d_mec[0], mec0.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        FB_CK(cudaMemcpyAsync(mec1.data(), e.d_mec[1], mec1.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        FB_CK(cudaMemcpyAsync(as0.data(), e.d_assign[0], as0.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        FB_CK(cudaMemcpyAsync(as1.data(), e.d_assign[1], as1.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    cudaEvent_t ev_end = fb_event(ctx);
+    FB_CK(cudaStreamSynchronize(ctx->stream));
+    FB_CK(cudaGetLastError());
+
+    // ---- the ploidy loop and stopping rule of get_local_hap_blocks (graph_processing.rs:132-252), on the host -------------
+    fb_block_results *r = (fb_block_results *)calloc(1, sizeof(fb_block_results));
+    r->n_blocks = n_blocks;
+    r->max_ploidy = mp;
+    r->best_ploidy = (uint32_t *)calloc(n_blocks + 1, sizeof(uint32_t));
+    r->ploidies_run = (uint32_t *)calloc(n_blocks + 1, sizeof(uint32_t));
+    r->mec_vector = (double *)calloc(n_blocks * mp + 1, sizeof(double));
+    r->expected_errors = (double *)calloc(n_blocks * mp + 1, sizeof(double));
+    r->read_ptr = (uint64_t *)calloc(n_blocks + 1, sizeof(uint64_t));
+    uint64_t tot = 0;
+    for (uint64_t j = 0; j < n_blocks; ++j) {
+        r->read_ptr[j] = tot;
+        if (blk_index[j] >= 0) tot += e.blocks[blk_index[j]].reads.size();
+    }
+    r->read_ptr[n_blocks] = tot;
+    r->read_ids = (uint32_t *)calloc(tot + 1, sizeof(uint32_t));
+    r->hap = (uint8_t *)calloc(tot + 1, 1);
+    const double epsilon = prm->epsilon;
+    uint64_t sweep_cells_all = 0, hist_cells_all = 0;
+    for (uint64_t j = 0; j < n_blocks; ++j) {
+        if (blk_index[j] < 0) continue;
+        const BlockPlan &b = e.blocks[blk_index[j]];
+        double *mec_vector = r->mec_vector + j * mp;
+        double *expected = r->expected_errors + j * mp;
+        uint32_t best_ploidy = 1;
+        for (uint32_t ploidy = 1; ploidy <= mp; ++ploidy) {
+            const int ii = first_inst[j] + (int)(ploidy - 1);
+            const InstDev &in = e.inst[ii];
+            const InstState &s = st[ii];
+            best_ploidy = ploidy;
+            r->ploidies_run[j] += 1;
+            // the no-phred stats were written to the buffer opposite to the accepted one
+            const std::vector<double> &mec = (s.cur ^ 1) == 0 ? mec0 : mec1;
+            double num_alleles = 0.0;
+            for (uint32_t h = 0; h < ploidy; ++h) {
+                const double good = mec[((uint64_t)in.mec_off + h) * 2 + 0];
+                const double bad = mec[((uint64_t)in.mec_off + h) * 2 + 1];
+                mec_vector[ploidy - 1] += bad;  // :159
+                num_alleles += good;
+                num_alleles += bad;
+            }
+            expected[ploidy - 1] = num_alleles * epsilon;  // :196
+            r->cells_sweep += (uint64_t)s.n_opt_iterate * b.nnz;
+            r->cells_hist += (uint64_t)(s.n_hist + 1) * b.nnz;
+            r->cells_beam += ploidy == 1 ? b.nnz : br.cells_beam[ii];
+            if (ploidy > 1) {
+                const double thr = fb_mec_threshold(ploidy, epsilon, prm->ploidy_sensitivity);
+                if ((mec_vector[ploidy - 1] / mec_vector[ploidy - 2]) < thr) {
+                } else if (prm->stopping_heuristic) {
+                    best_ploidy -= 1;
+                    break;
+                }
+                if (mec_vector[ploidy - 1] < expected[ploidy - 1]) break;
+            } else {
+                if (mec_vector[ploidy - 1] < expected[ploidy - 1]) break;
+            }
+        }
+        r->best_ploidy[j] = best_ploidy;
+        const int ib = first_inst[j] + (int)(best_ploidy - 1);
+        const std::vector<uint8_t> &as = st[ib].cur == 0 ? as0 : as1;
+        const uint64_t o = r->read_ptr[j];
+        for (size_t k = 0; k < b.reads.size(); ++k) {
+            r->read_ids[o + k] = b.reads[k];
+            r->hap[o + k] = as[e.inst[ib].assign_off + k];
+        }
+    }
+    for (int ii = 0; ii < n_inst; ++ii) {
+        const uint64_t nnz = e.blocks[e.inst[ii].block].nnz;
+        sweep_cells_all += (uint64_t)st[ii].n_opt_iterate * nnz;
+        hist_cells_all += (uint64_t)(st[ii].n_hist + 1) * nnz;
+    }
+    ctx->tim.sweep_cells += sweep_cells_all;
+    ctx->tim.hist_cells += hist_cells_all;
+    e.collect_timings();
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev_start, ev_compute);
+    ctx->tim.total_ms += ms;
+    cudaEventElapsedTime(&ms, ev_compute, ev_end);
+    ctx->tim.download_ms += ms;
+    ctx->tim.beam_ms += br.beam_ms;
+    *out = r;
+    return FB_OK;
+}
+
+int fb_phase_blocks(fb_ctx *ctx, const fb_frags *fr, uint64_t n_blocks, const uint32_t *blk_lo, const uint32_t *blk_hi,
+                    const fb_params *prm, fb_block_results **out) {
+    if (!ctx) return FB_ERR_ARG;
+    fb_dfrags *df = nullptr;
+    int rc = fb_frags_upload(ctx, fr, &df);
+    if (rc) return rc;
+    rc = fb_phase_blocks_resident(ctx, df, n_blocks, blk_lo, blk_hi, prm, out);
+    fb_frags_free(ctx, df);
+    return rc;
+}
+
+void fb_free_block_results(fb_block_results *r) {
+    if (!r) return;
+    free(r->best_ploidy);
+    free(r->ploidies_run);
+    free(r->mec_vector);
+    free(r->expected_errors);
+    free(r->read_ptr);
+    free(r->read_ids);
+    free(r->hap);
+    free(r);
+}
+
+// ---- rows still to come (a14, a15, f1): exported so the boundary is complete; they fail loudly --------------------------
+int fb_process_reads_for_final_parts(fb_ctx *ctx, const fb_frags *, uint64_t, const uint64_t *, const uint32_t *,
+                                     const uint32_t *, const uint32_t *, const fb_params *, fb_parts **) {
+    if (!ctx) return FB_ERR_ARG;
+    FB_FAIL(FB_ERR_ARG, "fb_process_reads_for_final_parts: not implemented yet");
+}
+void fb_free_parts(fb_parts *r) {
+    if (!r) return;
+    free(r->part_ptr);
+    free(r->read_ids);
+    free(r->range_lo);
+    free(r->range_hi);
+    free(r);
+}
+int fb_get_hapq(fb_ctx *ctx, const fb_frags *, uint64_t, const uint64_t *, const uint32_t *, const uint32_t *,
+                const uint32_t *, const uint64_t *, uint64_t, const fb_params *, uint8_t *, double *, double *) {
+    if (!ctx) return FB_ERR_ARG;
+    FB_FAIL(FB_ERR_ARG, "fb_get_hapq: not implemented yet");
+}
+int fb_update_hap_graph(fb_ctx *ctx, const fb_frags *, uint64_t, const uint64_t *, const uint64_t *, const uint32_t *,
+                        const uint32_t *, const uint32_t *, const fb_params *, double *) {
+    if (!ctx) return FB_ERR_ARG;
+    FB_FAIL(FB_ERR_ARG, "fb_update_hap_graph: not implemented yet");
+}
+
+}  // extern "C"

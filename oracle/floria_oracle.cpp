@@ -1205,6 +1205,25 @@ extern "C" {
 
 const char *orc_last_error(void) { return g_err.c_str(); }
 
+// test hook: drive the oracle's BinaryHeap like global_clustering.rs:128-135 / 149 do
+struct HeapProbe {
+    double s;
+    int id;
+    double score() const { return s; }
+};
+int orc_heap_trace(const double *scores, int n, int width, int *data_out, int *sorted_out) {
+    BinaryHeap<HeapProbe> h;
+    for (int c = 0; c < n; ++c) {
+        h.push(HeapProbe{scores[c], c});
+        if ((int)h.len() > width) h.pop();
+    }
+    int len = (int)h.len();
+    for (int e = 0; e < len; ++e) data_out[e] = h.data[e].id;
+    std::vector<HeapProbe> v = h.into_sorted_vec();
+    for (int e = 0; e < len; ++e) sorted_out[e] = v[e].id;
+    return len;
+}
+
 void orc_phred_lut(float *out256) {
     for (int q = 0; q < 256; ++q) out256[q] = (float)default_lut().w[q];
 }

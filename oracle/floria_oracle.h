@@ -63,6 +63,7 @@ int orc_update_hap_graph(const fb_frags *, uint64_t n_cols, const uint64_t *col_
                          const uint32_t *node_reads, const uint32_t *node_lo, const uint32_t *node_hi,
                          const fb_params *, double *out_weights);
 const char *orc_last_error(void);
+int orc_heap_trace(const double *scores, int n, int width, int *data_out, int *sorted_out);
 
 #ifdef __cplusplus
 }
