@@ -52,6 +52,7 @@ struct BeamParams {
     double *best_out;               // [n_inst]
     unsigned long long *tapn_out;   // [n_inst]
     BeamTapDev tap;                 // only meaningful for single-instance calls
+    unsigned long long *prof;       // optional [8] cycle counters per phase (FB_BEAM_PROF=1), else NULL
 };
 
 // shared-memory carve-up (same arithmetic on host and device)
@@ -246,6 +247,14 @@ __global__ void __launch_bounds__(FB_BEAM_THREADS) k_beam(BeamParams bp) {
                 ND_REF(0, 0, h) = 0;
             }
         }
+        long long pt[6] = {0, 0, 0, 0, 0, 0};
+        long long tc = clock64();
+#define PROF(i)                         \
+    if (bp.prof && tid == 0) {          \
+        long long n_ = clock64();       \
+        pt[i] += n_ - tc;               \
+        tc = n_;                        \
+    }
         int gen = 0;
         uint32_t prev_start = 0;  // block-local position0 from which the hashes are valid
         int gmax = -1;            // last block-local group touched so far
@@ -352,6 +361,7 @@ __global__ void __launch_bounds__(FB_BEAM_THREADS) k_beam(BeamParams bp) {
                 }
             }
             __syncthreads();
+            PROF(0)
 
             // ---- P3: per node p-values, pruning, child scores (global_clustering.rs:71-115, 181-208) ----------------------
             if (tid < n_nodes) {
@@ -387,6 +397,7 @@ __global__ void __launch_bounds__(FB_BEAM_THREADS) k_beam(BeamParams bp) {
                 }
             }
             __syncthreads();
+            PROF(1)
 
             // ---- P4 (warp 0): compaction, equality classes, exact BinaryHeap emulation -------------------------------------
             if (warp == 0) {
@@ -587,6 +598,7 @@ __global__ void __launch_bounds__(FB_BEAM_THREADS) k_beam(BeamParams bp) {
                 }
             }
             __syncthreads();
+            PROF(2)
 
             // ---- P5: materialise the new states (types_structs.rs:368-373 on the dense layout) ------------------------------
             {
@@ -673,6 +685,7 @@ __global__ void __launch_bounds__(FB_BEAM_THREADS) k_beam(BeamParams bp) {
                     }
                 }
                 __syncthreads();
+                PROF(3)
                 // per-state bookkeeping of the new states
                 const int njt = nj_copy + nj_inpl;
                 if (tid < njt) {
@@ -716,6 +729,7 @@ __global__ void __launch_bounds__(FB_BEAM_THREADS) k_beam(BeamParams bp) {
             prev_start = cur_start;
             gmax = gmax_new;
             __syncthreads();
+            PROF(4)
         }
 
         // ---- global_clustering.rs:149-176: best = into_sorted_vec()[0]; walk the parent pointers ------------------------------
@@ -740,7 +754,13 @@ __global__ void __launch_bounds__(FB_BEAM_THREADS) k_beam(BeamParams bp) {
             }
             bp.cells_out[ii] = cells;
             bp.tapn_out[ii] = tapn;
+            if (bp.prof) {
+                PROF(5)
+                for (int i = 0; i < 6; ++i) atomicAdd(bp.prof + i, (unsigned long long)pt[i]);
+                atomicAdd(bp.prof + 6, (unsigned long long)in.n_reads);
+            }
         }
+#undef PROF
 #undef ST_CNT
 #undef ST_MASK
 #undef ND_SCORE

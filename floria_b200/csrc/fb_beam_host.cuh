@@ -2,6 +2,7 @@
 #pragma once
 #include "fb_beam.cuh"
 #include "fb_engine.cuh"
+#include <stdlib.h>
 
 struct BeamRun {
     std::vector<unsigned long long> cells_beam, tap_n;
@@ -104,6 +105,16 @@ static int fb_run_beam(fb_ctx *ctx, Engine &e, const fb_params *prm, const BeamT
     bp.best_out = d_best;
     bp.tapn_out = d_tapn;
     if (tap) bp.tap = *tap;
+    unsigned long long *d_prof = nullptr;
+    const bool prof = getenv("FB_BEAM_PROF") != nullptr;
+    if (prof) {
+        if ((rc = fb_dalloc(ctx, &d_prof, 8))) {
+            cleanup();
+            return rc;
+        }
+        cudaMemsetAsync(d_prof, 0, 64, ctx->stream);
+        bp.prof = d_prof;
+    }
     cudaEvent_t e0 = fb_event(ctx);
     k_beam<<<(unsigned)n_slots, FB_BEAM_THREADS, L.total, ctx->stream>>>(bp);
     cudaEvent_t e1 = fb_event(ctx);
@@ -122,6 +133,15 @@ static int fb_run_beam(fb_ctx *ctx, Engine &e, const fb_params *prm, const BeamT
         return FB_ERR_CUDA;
     }
     cudaEventElapsedTime(&br.beam_ms, e0, e1);
+    if (prof) {
+        unsigned long long h[8];
+        cudaMemcpy(h, d_prof, 64, cudaMemcpyDeviceToHost);
+        cudaFree(d_prof);
+        double steps = (double)std::max<unsigned long long>(h[6], 1);
+        fprintf(stderr, "[k_beam prof] %.3f ms, %d instances on %llu CTAs, %.0f steps; cycles/step: score %.0f  pvals %.0f  heap %.0f  copy %.0f  lists %.0f  (backtrack total %.0f)\n",
+                br.beam_ms, (int)order.size(), (unsigned long long)n_slots, steps, h[0] / steps, h[1] / steps, h[2] / steps, h[3] / steps,
+                h[4] / steps, (double)h[5]);
+    }
     cleanup();
     return FB_OK;
 }

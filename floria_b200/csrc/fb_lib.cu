@@ -6,6 +6,7 @@
 
 #include "fb_engine.cuh"
 #include "fb_beam_host.cuh"
+#include "fb_final.cuh"
 
 // ======================================================================================================================
 // context
@@ -672,12 +673,196 @@ void fb_free_block_results(fb_block_results *r) {
     free(r);
 }
 
-// ---- rows still to come (a14, a15, f1): exported so the boundary is complete; they fail loudly --------------------------
-int fb_process_reads_for_final_parts(fb_ctx *ctx, const fb_frags *, uint64_t, const uint64_t *, const uint32_t *,
-                                     const uint32_t *, const uint32_t *, const fb_params *, fb_parts **) {
-    if (!ctx) return FB_ERR_ARG;
-    FB_FAIL(FB_ERR_ARG, "fb_process_reads_for_final_parts: not implemented yet");
+// ======================================================================================================================
+// rows a14 / a15: final read refinement and HAPQ (part_block_manip.rs)
+// ======================================================================================================================
+}  // extern "C" (helpers below are C++)
+
+// one engine instance (ploidy 1) per part; returns the per-part sorted read lists
+static int fb_parts_engine(fb_ctx *ctx, Engine &e, const fb_dfrags *df, uint64_t n_parts, const uint64_t *part_ptr,
+                           const uint32_t *part_reads, std::vector<std::vector<uint32_t>> &parts) {
+    parts.assign(n_parts, std::vector<uint32_t>());
+    for (uint64_t i = 0; i < n_parts; ++i) {
+        std::vector<uint32_t> &v = parts[i];
+        v.assign(part_reads + part_ptr[i], part_reads + part_ptr[i + 1]);
+        std::sort(v.begin(), v.end());
+        v.erase(std::unique(v.begin(), v.end()), v.end());  // a FxHashSet holds a read once
+        for (uint32_t r : v)
+            if (r >= df->n_reads) FB_FAIL(FB_ERR_ARG, "part %llu: read id %u out of range", (unsigned long long)i, r);
+        int b = e.add_block(v);
+        e.add_instance(b, 1);
+    }
+    return FB_OK;
 }
+
+// part_block_manip.rs:27-98 separate_broken_haplogroups (host logic, restated on counter_ids)
+static void fb_separate_broken_haplogroups(const fb_dfrags *df, std::vector<std::vector<uint32_t>> &parts,
+                                           std::vector<std::pair<uint32_t, uint32_t>> &ranges) {
+    const std::vector<uint32_t> &first = df->h_first, &last = df->h_last;
+    auto sorted_by_first = [&](const std::vector<uint32_t> &part) {
+        std::vector<uint32_t> v = part;  // ascending counter_id == canonical set order
+        std::stable_sort(v.begin(), v.end(), [&](uint32_t x, uint32_t y) { return first[x] < first[y]; });
+        return v;
+    };
+    std::vector<std::pair<size_t, std::vector<uint32_t>>> all_breaks;
+    for (size_t i = 0; i < ranges.size(); ++i) {
+        std::vector<uint32_t> v = sorted_by_first(parts[i]);
+        uint32_t current_lastest_pos = 0;
+        std::vector<uint32_t> breaks;
+        for (uint32_t f : v) {
+            if (current_lastest_pos != 0 && first[f] > current_lastest_pos) {
+                if (current_lastest_pos >= ranges[i].first && current_lastest_pos < ranges[i].second)
+                    breaks.push_back(current_lastest_pos);
+            }
+            if (last[f] > current_lastest_pos) current_lastest_pos = last[f];
+        }
+        if (!breaks.empty()) all_breaks.push_back(std::make_pair(i, breaks));
+    }
+    std::vector<std::vector<uint32_t>> new_parts;
+    std::vector<std::pair<uint32_t, uint32_t>> new_ranges;
+    for (auto &bi : all_breaks) {
+        size_t spot_index = 0;
+        const std::vector<uint32_t> &break_spots = bi.second;
+        uint32_t break_start = ranges[bi.first].first;
+        std::vector<uint32_t> v = sorted_by_first(parts[bi.first]);
+        uint32_t end_spot = break_spots[spot_index];
+        std::vector<uint32_t> new_part;
+        for (uint32_t f : v) {
+            if (last[f] <= end_spot) {
+                new_part.push_back(f);
+            } else {
+                // faithful to :71-84: the fragment that triggers the switch is not inserted anywhere
+                new_ranges.push_back(std::make_pair(break_start, end_spot));
+                new_parts.push_back(std::move(new_part));
+                break_start = end_spot + 1;
+                spot_index += 1;
+                end_spot = spot_index != break_spots.size() ? break_spots[spot_index] : 0xFFFFFFFFu;
+                new_part = std::vector<uint32_t>();
+            }
+        }
+        new_ranges.push_back(std::make_pair(break_start, ranges[bi.first].second));
+        new_parts.push_back(std::move(new_part));
+    }
+    for (auto &bi : all_breaks) parts[bi.first].clear();
+    for (size_t i = 0; i < new_parts.size(); ++i) {
+        std::sort(new_parts[i].begin(), new_parts[i].end());
+        parts.push_back(std::move(new_parts[i]));
+        ranges.push_back(new_ranges[i]);
+    }
+}
+
+extern "C" {
+
+int fb_process_reads_for_final_parts(fb_ctx *ctx, const fb_frags *fr, uint64_t n_parts, const uint64_t *part_ptr,
+                                     const uint32_t *part_reads, const uint32_t *range_lo, const uint32_t *range_hi,
+                                     const fb_params *prm, fb_parts **out) {
+    if (!ctx) return FB_ERR_ARG;
+    if (!fr || !out || (n_parts && (!part_ptr || !range_lo || !range_hi))) FB_FAIL(FB_ERR_ARG, "null argument");
+    *out = nullptr;
+    FB_CK(cudaSetDevice(ctx->device));
+    ctx->ev_used = 0;
+    int rc = fb_check_params(ctx, prm, 1);
+    if (rc) return rc;
+    Single s;
+    s.ctx = ctx;
+    if ((rc = fb_frags_upload(ctx, fr, &s.df))) return rc;
+    s.own_df = true;
+    Engine &e = s.eng;
+    e.ctx = ctx;
+    e.df = s.df;
+    std::vector<std::vector<uint32_t>> parts;
+    if ((rc = fb_parts_engine(ctx, e, s.df, n_parts, part_ptr, part_reads, parts))) return rc;
+    if ((rc = e.finalize_and_upload(prm->epsilon))) return rc;
+    // read -> candidate parts (read_to_parts_map, part_block_manip.rs:185-193), canonical orders
+    std::vector<std::pair<uint32_t, uint32_t>> rp;  // (read, part)
+    for (uint64_t i = 0; i < n_parts; ++i)
+        for (uint32_t r : parts[i]) rp.push_back(std::make_pair(r, (uint32_t)i));
+    std::sort(rp.begin(), rp.end());
+    std::vector<uint32_t> read_ids, cand;
+    std::vector<uint64_t> cand_ptr;
+    for (size_t k = 0; k < rp.size(); ++k) {
+        if (k == 0 || rp[k].first != rp[k - 1].first) {
+            read_ids.push_back(rp[k].first);
+            cand_ptr.push_back(cand.size());
+        }
+        cand.push_back(rp[k].second);
+    }
+    cand_ptr.push_back(cand.size());
+    for (size_t x = 0; x + 1 < cand_ptr.size(); ++x)
+        if (cand_ptr[x + 1] - cand_ptr[x] > FB_FINAL_MAXCAND)
+            FB_FAIL(FB_ERR_LIMIT, "a read belongs to more than %d haplosets", FB_FINAL_MAXCAND);
+    std::vector<uint32_t> chosen(read_ids.size());
+    if (!read_ids.empty()) {
+        uint32_t *d_ids = nullptr, *d_cand = nullptr, *d_chosen = nullptr;
+        uint64_t *d_cptr = nullptr;
+        auto cleanup = [&]() {
+            cudaFree(d_ids);
+            cudaFree(d_cand);
+            cudaFree(d_chosen);
+            cudaFree(d_cptr);
+        };
+        if ((rc = fb_upload(ctx, &d_ids, read_ids)) || (rc = fb_upload(ctx, &d_cand, cand)) ||
+            (rc = fb_upload(ctx, &d_cptr, cand_ptr)) || (rc = fb_dalloc(ctx, &d_chosen, read_ids.size()))) {
+            cleanup();
+            return rc;
+        }
+        // every read removed from every haploset: all tables start empty (part_block_manip.rs:195-200)
+        cudaMemsetAsync(e.d_cnt[0], 0, std::max<uint64_t>(e.tot_cnt, 1) * 8, ctx->stream);
+        cudaMemsetAsync(e.d_masks[0], 0, std::max<uint64_t>(e.tot_mask, 1) * 8, ctx->stream);
+        FinalArgs a;
+        a.fr = s.df->dev();
+        a.inst = e.d_inst;
+        a.cnt = e.d_cnt[0];
+        a.masks = e.d_masks[0];
+        a.lut = ctx->d_lut;
+        a.n_active = (uint32_t)read_ids.size();
+        a.read_ids = d_ids;
+        a.cand_ptr = d_cptr;
+        a.cand = d_cand;
+        a.chosen = d_chosen;
+        a.eps = prm->epsilon;
+        a.eps_safe = fb_eps_is_safe(prm->epsilon);
+        k_final_assign<<<1, FB_FINAL_THREADS, 0, ctx->stream>>>(a);
+        ctx->tim.n_launches++;
+        cudaMemcpyAsync(chosen.data(), d_chosen, chosen.size() * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+        if (ce == cudaSuccess) ce = cudaGetLastError();
+        cleanup();
+        if (ce != cudaSuccess) {
+            ctx->err = std::string("fb_process_reads_for_final_parts: ") + cudaGetErrorString(ce);
+            return FB_ERR_CUDA;
+        }
+    }
+    std::vector<std::vector<uint32_t>> np(n_parts);
+    for (size_t x = 0; x < read_ids.size(); ++x) np[chosen[x]].push_back(read_ids[x]);  // ascending by construction
+    std::vector<std::pair<uint32_t, uint32_t>> ranges;
+    for (uint64_t i = 0; i < n_parts; ++i) ranges.push_back(std::make_pair(range_lo[i], range_hi[i]));
+    fb_separate_broken_haplogroups(s.df, np, ranges);  // constants.rs:17 SEPARATE_BROKEN_HAPLOGROUPS = true
+    // sort_parts (part_block_manip.rs:276-288): stable sort by range
+    std::vector<size_t> idx(np.size());
+    for (size_t i = 0; i < idx.size(); ++i) idx[i] = i;
+    std::stable_sort(idx.begin(), idx.end(), [&](size_t x, size_t y) { return ranges[x] < ranges[y]; });
+    fb_parts *r = (fb_parts *)calloc(1, sizeof(fb_parts));
+    r->n_parts = np.size();
+    r->part_ptr = (uint64_t *)calloc(np.size() + 1, sizeof(uint64_t));
+    r->range_lo = (uint32_t *)calloc(np.size() + 1, sizeof(uint32_t));
+    r->range_hi = (uint32_t *)calloc(np.size() + 1, sizeof(uint32_t));
+    uint64_t tot = 0;
+    for (size_t k = 0; k < idx.size(); ++k) {
+        r->part_ptr[k] = tot;
+        tot += np[idx[k]].size();
+        r->range_lo[k] = ranges[idx[k]].first;
+        r->range_hi[k] = ranges[idx[k]].second;
+    }
+    r->part_ptr[np.size()] = tot;
+    r->read_ids = (uint32_t *)calloc(tot + 1, sizeof(uint32_t));
+    uint64_t o = 0;
+    for (size_t k = 0; k < idx.size(); ++k)
+        for (uint32_t rd : np[idx[k]]) r->read_ids[o++] = rd;
+    *out = r;
+    return FB_OK;
+}
+
 void fb_free_parts(fb_parts *r) {
     if (!r) return;
     free(r->part_ptr);
@@ -686,11 +871,161 @@ void fb_free_parts(fb_parts *r) {
     free(r->range_hi);
     free(r);
 }
-int fb_get_hapq(fb_ctx *ctx, const fb_frags *, uint64_t, const uint64_t *, const uint32_t *, const uint32_t *,
-                const uint32_t *, const uint64_t *, uint64_t, const fb_params *, uint8_t *, double *, double *) {
+
+int fb_get_hapq(fb_ctx *ctx, const fb_frags *fr, uint64_t n_parts, const uint64_t *part_ptr, const uint32_t *part_reads,
+                const uint32_t *range_lo, const uint32_t *range_hi, const uint64_t *snp_to_genome_pos, uint64_t n_snps,
+                const fb_params *prm, uint8_t *hapq, double *rel_err, double *avg_err) {
     if (!ctx) return FB_ERR_ARG;
-    FB_FAIL(FB_ERR_ARG, "fb_get_hapq: not implemented yet");
+    if (!fr || (n_parts && (!part_ptr || !range_lo || !range_hi || !hapq || !rel_err)) || !snp_to_genome_pos || !avg_err)
+        FB_FAIL(FB_ERR_ARG, "null argument");
+    FB_CK(cudaSetDevice(ctx->device));
+    ctx->ev_used = 0;
+    int rc = fb_check_params(ctx, prm, 1);
+    if (rc) return rc;
+    for (uint64_t i = 0; i < n_parts; ++i)
+        if (range_lo[i] < 1 || range_hi[i] > n_snps || range_lo[i] > range_hi[i])
+            FB_FAIL(FB_ERR_ARG, "part %llu: snp range outside snp_to_genome_pos", (unsigned long long)i);
+    Single s;
+    s.ctx = ctx;
+    if ((rc = fb_frags_upload(ctx, fr, &s.df))) return rc;
+    s.own_df = true;
+    Engine &e = s.eng;
+    e.ctx = ctx;
+    e.df = s.df;
+    std::vector<std::vector<uint32_t>> parts;
+    if ((rc = fb_parts_engine(ctx, e, s.df, n_parts, part_ptr, part_reads, parts))) return rc;
+    if ((rc = e.finalize_and_upload(prm->epsilon))) return rc;
+    if (n_parts == 0) {
+        *avg_err = 0.0 / 0.0;
+        return FB_OK;
+    }
+    // unweighted tables -> buffer 0 (get_errors_cov_from_frags, :529-539); phred tables -> buffer 1 (:541)
+    if ((rc = e.launch_hist(2, 0, 0, 0))) return rc;
+    if ((rc = e.launch_hist(2, 1, 0, 1))) return rc;
+    // find_overlapping_blocks(parts, 0.05, ranges) (part_block_manip.rs:454-515); rust-lapper semantics restated:
+    // Lapper::new sorts by (start, stop) (stable); find(start, stop) yields iv.start < stop && iv.stop > start in order.
+    struct Iv {
+        uint32_t start, stop, val;
+    };
+    std::vector<Iv> sorted(n_parts);
+    for (uint64_t i = 0; i < n_parts; ++i) sorted[i] = Iv{range_lo[i], range_hi[i], (uint32_t)i};
+    std::stable_sort(sorted.begin(), sorted.end(), [](const Iv &x, const Iv &y) {
+        return x.start != y.start ? x.start < y.start : x.stop < y.stop;
+    });
+    std::vector<uint32_t> prefmax(n_parts);
+    for (uint64_t k = 0; k < n_parts; ++k) prefmax[k] = std::max(k ? prefmax[k - 1] : 0u, sorted[k].stop);
+    std::vector<uint32_t> pair_i, pair_j;
+    std::vector<double> pair_ol;
+    std::vector<uint64_t> ov_ptr(n_parts + 1, 0);
+    for (uint64_t i = 0; i < n_parts; ++i) {
+        const uint32_t x1 = range_lo[i], x2 = range_hi[i];
+        // candidates: start < x2 (upper bound by bisection) and stop > x1 (none before the first prefix max > x1)
+        size_t ub = std::lower_bound(sorted.begin(), sorted.end(), x2,
+                                     [](const Iv &iv, uint32_t v) { return iv.start < v; }) - sorted.begin();
+        size_t lb = std::upper_bound(prefmax.begin(), prefmax.begin() + ub, x1) - prefmax.begin();
+        for (size_t k = lb; k < ub; ++k) {
+            const Iv &f = sorted[k];
+            if (!(f.start < x2 && f.stop > x1)) continue;
+            // overlap_percent (part_block_manip.rs:13-24), u32 arithmetic
+            const uint32_t aa = x2 - f.start + 1, bb = f.stop - x1 + 1;
+            const uint32_t intersect = std::min(aa, bb);
+            const uint32_t min_length = x2 - x1 + 1;
+            double p = (double)intersect / (double)min_length;
+            if (p > 1.) p = 1.;
+            if (p > 0.05 && f.val != (uint32_t)i) {
+                pair_i.push_back((uint32_t)i);
+                pair_j.push_back(f.val);
+                pair_ol.push_back(p);
+            }
+        }
+        ov_ptr[i + 1] = pair_i.size();
+    }
+    const int n_pairs = (int)pair_i.size();
+    long long *d_ec = nullptr, *d_pd = nullptr;
+    uint32_t *d_lo = nullptr, *d_hi = nullptr, *d_pi = nullptr, *d_pj = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_ec);
+        cudaFree(d_pd);
+        cudaFree(d_lo);
+        cudaFree(d_hi);
+        cudaFree(d_pi);
+        cudaFree(d_pj);
+    };
+    if ((rc = fb_dalloc(ctx, &d_ec, n_parts * 2)) || (rc = fb_dalloc(ctx, &d_pd, (size_t)n_pairs * 2)) ||
+        (rc = fb_upload(ctx, &d_lo, range_lo, n_parts)) || (rc = fb_upload(ctx, &d_hi, range_hi, n_parts)) ||
+        (rc = fb_upload(ctx, &d_pi, pair_i)) || (rc = fb_upload(ctx, &d_pj, pair_j))) {
+        cleanup();
+        return rc;
+    }
+    ErrCovArgs ea;
+    ea.inst = e.d_inst;
+    ea.n_parts = (int)n_parts;
+    ea.cnt = e.d_cnt[0];
+    ea.range_lo = d_lo;
+    ea.range_hi = d_hi;
+    ea.out = d_ec;
+    k_errors_cov<<<(unsigned)((n_parts + 7) / 8), 256, 0, ctx->stream>>>(ea);
+    ctx->tim.n_launches++;
+    if (n_pairs) {
+        HapDistArgs ha;
+        ha.inst = e.d_inst;
+        ha.cnt = e.d_cnt[1];
+        ha.pair_i = d_pi;
+        ha.pair_j = d_pj;
+        ha.n_pairs = n_pairs;
+        ha.out = d_pd;
+        k_hap_distance<<<(unsigned)((n_pairs + 7) / 8), 256, 0, ctx->stream>>>(ha);
+        ctx->tim.n_launches++;
+    }
+    std::vector<long long> ec(n_parts * 2), pd((size_t)n_pairs * 2 + 1);
+    cudaMemcpyAsync(ec.data(), d_ec, n_parts * 16, cudaMemcpyDeviceToHost, ctx->stream);
+    if (n_pairs) cudaMemcpyAsync(pd.data(), d_pd, (size_t)n_pairs * 16, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+    if (ce == cudaSuccess) ce = cudaGetLastError();
+    cleanup();
+    if (ce != cudaSuccess) {
+        ctx->err = std::string("fb_get_hapq: ") + cudaGetErrorString(ce);
+        return FB_ERR_CUDA;
+    }
+    // part_block_manip.rs:523-540
+    double weight = 0., error = 0.;
+    std::vector<double> errs(n_parts);
+    for (uint64_t i = 0; i < n_parts; ++i) {
+        const double total_cov = (double)ec[i * 2], total_err = (double)ec[i * 2 + 1];
+        weight += total_cov;
+        error += total_err;
+        errs[i] = total_err / total_cov;
+    }
+    const double avg = error / weight;
+    const double HAPQ_CONSTANT = 40.;  // constants.rs:22
+    for (uint64_t i = 0; i < n_parts; ++i) {
+        double max_penalty = 0.;
+        for (uint64_t k = ov_ptr[i]; k < ov_ptr[i + 1]; ++k) {
+            const double same = (double)pd[k * 2], diff = (double)pd[k * 2 + 1];
+            const double dist = (same + diff) == 0. ? 1. : diff / (same + diff);
+            const double ol = pair_ol[k];
+            if (ol * (1. - dist) > max_penalty) max_penalty = ol * (1. - dist);
+        }
+        uint32_t r0 = 0xFFFFFFFFu, r1 = 0;
+        for (uint32_t rd : parts[i]) {
+            if (s.df->h_first[rd] < r0) r0 = s.df->h_first[rd];
+            if (s.df->h_last[rd] >= r1) r1 = s.df->h_last[rd];
+        }
+        uint64_t base_range = 0;
+        if (!(r0 > r1)) base_range = snp_to_genome_pos[range_hi[i] - 1] - snp_to_genome_pos[range_lo[i] - 1];
+        const double t1 = HAPQ_CONSTANT * (1. - max_penalty);
+        const double t2 = std::min(1., (double)parts[i].size() / 3.);
+        const double t3 = std::max(0.0, log(((double)base_range / (double)prm->block_length) + 1.));
+        unsigned long long hq = fb_as_usize(t1 * t2 * t3);
+        if (parts[i].size() == 1) hq = 0;
+        hapq[i] = (uint8_t)std::min<unsigned long long>(hq, 60);
+        rel_err[i] = errs[i] / avg;
+    }
+    *avg_err = avg;
+    e.collect_timings();
+    return FB_OK;
 }
+
 int fb_update_hap_graph(fb_ctx *ctx, const fb_frags *, uint64_t, const uint64_t *, const uint64_t *, const uint32_t *,
                         const uint32_t *, const uint32_t *, const fb_params *, double *) {
     if (!ctx) return FB_ERR_ARG;
