@@ -183,19 +183,13 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def gather(res):
-        """final gather of the partition records on rank 0 (NCCL over NVLink); returns bytes moved"""
+        """final gather of the partition records on rank 0 (NCCL over NVLink); units = this rank's blocks"""
         if world == 1:
-            return 0
-        n = torch.tensor([len(res.read_ids)], device=dev, dtype=torch.int64)
-        sizes = [torch.zeros_like(n) for _ in range(world)]
-        dist.all_gather(sizes, n)
-        mx = int(max(int(s.item()) for s in sizes))
-        rec = torch.zeros(mx * 5, dtype=torch.uint8, device=dev)
-        payload = np.concatenate([res.read_ids.view(np.uint8), res.hap])
-        rec[: len(payload)] = torch.from_numpy(payload).to(dev)
-        out = [torch.zeros_like(rec) for _ in range(world)] if rank == 0 else None
-        dist.gather(rec, out, dst=0)
-        return int(rec.numel())
+            return None
+        from floria_b200 import shard
+
+        unit_ids = np.arange(res.n_blocks, dtype=np.int64) + rank * 1000000
+        return shard.gather_records(unit_ids, res.read_ptr, res.read_ids, res.hap, res.best_ploidy, dev, dst=0)
 
     def one_pass(fn, steps, timed):
         ev = []

@@ -1,0 +1,76 @@
+"""Multi-GPU plumbing: contigs / SNP blocks are independent units (graph_processing.rs:345-362 pushes them under a
+Mutex and re-sorts by index), so ranks take disjoint units of a static work queue and only the final partition
+records are gathered (torch.distributed: NCCL on GPUs, gloo in the CPU tests).  No data-path collective."""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def lpt_assign(costs, n_ranks):
+    """Static longest-processing-time-first assignment of units to ranks.  Returns rank index per unit; deterministic
+    (ties broken by unit index) so every rank computes the same schedule without communication."""
+    costs = np.asarray(costs, dtype=np.float64)
+    order = np.lexsort((np.arange(len(costs)), -costs))
+    load = np.zeros(n_ranks)
+    owner = np.zeros(len(costs), dtype=np.int64)
+    for u in order:
+        r = int(np.argmin(load))  # first minimum
+        owner[u] = r
+        load[r] += costs[u]
+    return owner
+
+
+def block_costs(frags, blk_lo, blk_hi, max_ploidy):
+    """cost estimate of a block: sum_p (beam * p * nnz) ~ nnz * p(p+1)/2"""
+    first = frags.first.astype(np.int64)
+    last = frags.last.astype(np.int64)
+    nnz = (frags.row_ptr[1:] - frags.row_ptr[:-1]).astype(np.int64)
+    cs = np.concatenate([[0], np.cumsum(nnz)])
+    out = np.zeros(len(blk_lo))
+    for j, (a, b) in enumerate(zip(blk_lo, blk_hi)):
+        hi = np.searchsorted(first, int(b), side="right")
+        sel = np.nonzero(last[:hi] >= int(a))[0]
+        out[j] = float(nnz[sel].sum()) * max_ploidy * (max_ploidy + 1) / 2
+    return out
+
+
+def gather_records(unit_ids, read_ptr, read_ids, hap, best_ploidy, device, dst=0):
+    """Variable-length gather of per-unit partition records to rank `dst`.
+    Every rank passes the records of the units it owns; returns on dst a dict unit_id -> (best_ploidy, read_ids, hap)
+    (None elsewhere).  One all_gather of sizes + one padded gather of the payload."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    unit_ids = np.asarray(unit_ids, dtype=np.int64)
+    read_ptr = np.asarray(read_ptr, dtype=np.int64)
+    head = np.concatenate([[len(unit_ids)], unit_ids, np.asarray(best_ploidy, dtype=np.int64), read_ptr]).astype(np.int64)
+    payload = np.concatenate([head.view(np.uint8), np.asarray(read_ids, np.uint32).view(np.uint8),
+                              np.asarray(hap, np.uint8)])
+    if world == 1:
+        bufs = [payload]
+    else:
+        n = torch.tensor([len(payload)], dtype=torch.int64, device=device)
+        sizes = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(sizes, n)
+        sizes = [int(s.item()) for s in sizes]
+        mx = max(sizes)
+        rec = torch.zeros(mx, dtype=torch.uint8, device=device)
+        rec[: len(payload)] = torch.from_numpy(payload).to(device)
+        out = [torch.zeros_like(rec) for _ in range(world)] if rank == dst else None
+        dist.gather(rec, out, dst=dst)
+        if rank != dst:
+            return None
+        bufs = [o[:s].cpu().numpy() for o, s in zip(out, sizes)]
+    res = {}
+    for b in bufs:
+        b = np.ascontiguousarray(b)
+        nu = int(b[:8].view(np.int64)[0])
+        off = 8
+        uids = b[off:off + 8 * nu].view(np.int64); off += 8 * nu
+        bp = b[off:off + 8 * nu].view(np.int64); off += 8 * nu
+        rp = b[off:off + 8 * (nu + 1)].view(np.int64); off += 8 * (nu + 1)
+        tot = int(rp[-1]) if nu else 0
+        rid = b[off:off + 4 * tot].view(np.uint32); off += 4 * tot
+        hp = b[off:off + tot]
+        for k in range(nu):
+            res[int(uids[k])] = (int(bp[k]), rid[rp[k]:rp[k + 1]].copy(), hp[rp[k]:rp[k + 1]].copy())
+    return res
