@@ -63,12 +63,12 @@ static int fb_run_beam(fb_ctx *ctx, Engine &e, const fb_params *prm, const BeamT
     double *d_best = nullptr;
     int rc;
     auto cleanup = [&]() {
-        cudaFree(d_scratch);
-        cudaFree(d_order);
-        cudaFree(d_counter);
-        cudaFree(d_cells);
-        cudaFree(d_tapn);
-        cudaFree(d_best);
+        fb_cache_free(d_scratch);
+        fb_cache_free(d_order);
+        fb_cache_free(d_counter);
+        fb_cache_free(d_cells);
+        fb_cache_free(d_tapn);
+        fb_cache_free(d_best);
     };
     if ((rc = fb_dalloc(ctx, &d_scratch, n_slots * slot_bytes)) || (rc = fb_upload(ctx, &d_order, order)) ||
         (rc = fb_dalloc(ctx, &d_counter, 1)) || (rc = fb_dalloc(ctx, &d_cells, (size_t)n_inst)) ||
@@ -136,7 +136,7 @@ static int fb_run_beam(fb_ctx *ctx, Engine &e, const fb_params *prm, const BeamT
     if (prof) {
         unsigned long long h[8];
         cudaMemcpy(h, d_prof, 64, cudaMemcpyDeviceToHost);
-        cudaFree(d_prof);
+        fb_cache_free(d_prof);
         double steps = (double)std::max<unsigned long long>(h[6], 1);
         fprintf(stderr, "[k_beam prof] %.3f ms, %d instances on %llu CTAs, %.0f steps; cycles/step: score %.0f  pvals %.0f  heap %.0f  copy %.0f  lists %.0f  (backtrack total %.0f)\n",
                 br.beam_ms, (int)order.size(), (unsigned long long)n_slots, steps, h[0] / steps, h[1] / steps, h[2] / steps, h[3] / steps,

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/floria_b200.h"
+#include "fb_cache.cuh"
 #include "fb_common.cuh"
 #include "fb_kernels.cuh"
 
@@ -78,7 +79,7 @@ template <class T>
 static int fb_dalloc(fb_ctx *ctx, T **p, size_t n) {
     *p = nullptr;
     if (n == 0) n = 1;
-    FB_CK(cudaMalloc((void **)p, n * sizeof(T)));
+    FB_CK(FbCache::get().alloc((void **)p, n * sizeof(T)));
     return FB_OK;
 }
 template <class T>
@@ -156,22 +157,22 @@ struct Engine {
 
     ~Engine() { release(); }
     void release() {
-        cudaFree(d_inst);
-        cudaFree(d_st);
-        cudaFree(d_assign_prefix);
-        cudaFree(d_tile_prefix);
-        cudaFree(d_hap_prefix);
-        cudaFree(d_moves_off);
-        cudaFree(d_moves_cap);
-        cudaFree(d_rinfo);
+        fb_cache_free(d_inst);
+        fb_cache_free(d_st);
+        fb_cache_free(d_assign_prefix);
+        fb_cache_free(d_tile_prefix);
+        fb_cache_free(d_hap_prefix);
+        fb_cache_free(d_moves_off);
+        fb_cache_free(d_moves_cap);
+        fb_cache_free(d_rinfo);
         for (int b = 0; b < 2; ++b) {
-            cudaFree(d_assign[b]);
-            cudaFree(d_cnt[b]);
-            cudaFree(d_masks[b]);
-            cudaFree(d_mec[b]);
+            fb_cache_free(d_assign[b]);
+            fb_cache_free(d_cnt[b]);
+            fb_cache_free(d_masks[b]);
+            fb_cache_free(d_mec[b]);
         }
-        cudaFree(d_gain);
-        cudaFree(d_moves);
+        fb_cache_free(d_gain);
+        fb_cache_free(d_moves);
         d_inst = nullptr;
         d_st = nullptr;
         d_assign_prefix = d_tile_prefix = d_hap_prefix = d_moves_off = nullptr;

@@ -81,6 +81,7 @@ void fb_destroy(fb_ctx *ctx) {
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     cudaFree(ctx->d_lut);
     cudaFree(ctx->d_n_active);
+    FbCache::get().trim(ctx->device);
     if (ctx->h_n_active) cudaFreeHost(ctx->h_n_active);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -176,10 +177,10 @@ int fb_frags_upload(fb_ctx *ctx, const fb_frags *fr, fb_dfrags **out) {
     uint32_t *d_pos = nullptr;
     uint8_t *d_al = nullptr, *d_q = nullptr;
     auto cleanup = [&]() {
-        cudaFree(d_row);
-        cudaFree(d_pos);
-        cudaFree(d_al);
-        cudaFree(d_q);
+        fb_cache_free(d_row);
+        fb_cache_free(d_pos);
+        fb_cache_free(d_al);
+        fb_cache_free(d_q);
     };
     if ((rc = fb_upload(ctx, &d_row, fr->row_ptr, R + 1)) || (rc = fb_upload(ctx, &d_pos, fr->pos, fr->nnz)) ||
         (rc = fb_upload(ctx, &d_al, fr->allele, fr->nnz)) || (rc = fb_upload(ctx, &d_q, fr->qual, fr->nnz)) ||
@@ -223,14 +224,14 @@ int fb_frags_upload(fb_ctx *ctx, const fb_frags *fr, fb_dfrags **out) {
 void fb_frags_free(fb_ctx *ctx, fb_dfrags *df) {
     if (!df) return;
     if (ctx) cudaSetDevice(ctx->device);
-    cudaFree(df->d_first);
-    cudaFree(df->d_last);
-    cudaFree(df->d_nnz);
-    cudaFree(df->d_gstart);
-    cudaFree(df->d_gptr);
-    cudaFree(df->d_qual);
-    cudaFree(df->d_allele);
-    cudaFree(df->d_present);
+    fb_cache_free(df->d_first);
+    fb_cache_free(df->d_last);
+    fb_cache_free(df->d_nnz);
+    fb_cache_free(df->d_gstart);
+    fb_cache_free(df->d_gptr);
+    fb_cache_free(df->d_qual);
+    fb_cache_free(df->d_allele);
+    fb_cache_free(df->d_present);
     delete df;
 }
 
@@ -384,11 +385,11 @@ int fb_score_reads(fb_ctx *ctx, const fb_frags *fr, uint64_t n_sel, const uint32
             rc = FB_ERR_CUDA;
         }
     }
-    cudaFree(d_same);
-    cudaFree(d_diff);
-    cudaFree(d_sq);
-    cudaFree(d_dq);
-    cudaFree(d_ne);
+    fb_cache_free(d_same);
+    fb_cache_free(d_diff);
+    fb_cache_free(d_sq);
+    fb_cache_free(d_dq);
+    fb_cache_free(d_ne);
     e.collect_timings();
     return rc;
 }
@@ -500,9 +501,9 @@ int fb_beam_search_phasing(fb_ctx *ctx, const fb_frags *fr, uint64_t n_sel, cons
         if (best_score) *best_score = br.best_score.empty() ? 0.0 : br.best_score[0];
         if (tap_n) *tap_n = br.tap_n.empty() ? 0 : br.tap_n[0];
     }
-    cudaFree(d_ts);
-    cudaFree(d_td);
-    cudaFree(d_tp);
+    fb_cache_free(d_ts);
+    fb_cache_free(d_td);
+    fb_cache_free(d_tp);
     e.collect_timings();
     return rc;
 }
@@ -796,10 +797,10 @@ int fb_process_reads_for_final_parts(fb_ctx *ctx, const fb_frags *fr, uint64_t n
         uint32_t *d_ids = nullptr, *d_cand = nullptr, *d_chosen = nullptr;
         uint64_t *d_cptr = nullptr;
         auto cleanup = [&]() {
-            cudaFree(d_ids);
-            cudaFree(d_cand);
-            cudaFree(d_chosen);
-            cudaFree(d_cptr);
+            fb_cache_free(d_ids);
+            fb_cache_free(d_cand);
+            fb_cache_free(d_chosen);
+            fb_cache_free(d_cptr);
         };
         if ((rc = fb_upload(ctx, &d_ids, read_ids)) || (rc = fb_upload(ctx, &d_cand, cand)) ||
             (rc = fb_upload(ctx, &d_cptr, cand_ptr)) || (rc = fb_dalloc(ctx, &d_chosen, read_ids.size()))) {
@@ -944,12 +945,12 @@ int fb_get_hapq(fb_ctx *ctx, const fb_frags *fr, uint64_t n_parts, const uint64_
     long long *d_ec = nullptr, *d_pd = nullptr;
     uint32_t *d_lo = nullptr, *d_hi = nullptr, *d_pi = nullptr, *d_pj = nullptr;
     auto cleanup = [&]() {
-        cudaFree(d_ec);
-        cudaFree(d_pd);
-        cudaFree(d_lo);
-        cudaFree(d_hi);
-        cudaFree(d_pi);
-        cudaFree(d_pj);
+        fb_cache_free(d_ec);
+        fb_cache_free(d_pd);
+        fb_cache_free(d_lo);
+        fb_cache_free(d_hi);
+        fb_cache_free(d_pi);
+        fb_cache_free(d_pj);
     };
     if ((rc = fb_dalloc(ctx, &d_ec, n_parts * 2)) || (rc = fb_dalloc(ctx, &d_pd, (size_t)n_pairs * 2)) ||
         (rc = fb_upload(ctx, &d_lo, range_lo, n_parts)) || (rc = fb_upload(ctx, &d_hi, range_hi, n_parts)) ||
