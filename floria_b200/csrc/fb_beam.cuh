@@ -24,7 +24,7 @@
 #include "fb_common.cuh"
 #include "fb_kernels.cuh"
 
-#define FB_BEAM_THREADS 256
+#define FB_BEAM_THREADS 512
 #define FB_BEAM_WARPS (FB_BEAM_THREADS / 32)
 
 struct BeamTapDev {
@@ -36,6 +36,7 @@ struct BeamParams {
     DFragsDev fr;
     const InstDev *inst;
     const RInfo *rinfo;
+    const RExtra *rextra;
     const uint32_t *lut;
     const int *order;  // instance indices to run, largest first
     int n_work;
@@ -59,7 +60,7 @@ struct BeamParams {
 struct BeamSmem {
     uint32_t off_nd_score, off_nd_err, off_nd_ref, off_st_hash, off_sc_same, off_sc_diff, off_st_hi, off_st_mark,
         off_free, off_live, off_ch_score, off_ch_parent, off_ch_part, off_ch_class, off_ch_diff, off_hp_score,
-        off_hp_item, off_lut, off_wscr, off_misc, off_job, off_addnew, off_plain, total;
+        off_hp_item, off_lut, off_wscr, off_misc, off_job, off_addnew, off_plain, off_sc_pv, off_ch_fold, off_ch_m, total;
     __host__ __device__ void layout(uint32_t P, uint32_t W, uint32_t NS) {
         uint32_t o = 0;
         auto take = [&](uint32_t bytes) {
@@ -87,9 +88,12 @@ struct BeamSmem {
         off_lut = take(256 * 4);
         off_wscr = take(FB_BEAM_WARPS * 16 * 4);
         off_misc = take(256);
-        off_job = take((W + 1) * 16);
+        off_job = take((W + 2) * 16);
         off_addnew = take(NS * 4);
         off_plain = take(NS * 4);
+        off_sc_pv = take(NS * 8);
+        off_ch_fold = take(W * P * 8);
+        off_ch_m = take(W * P * 4);
         total = o;
     }
 };
@@ -155,8 +159,12 @@ __device__ double fb_replay_diff_state(const DFragsDev &fr, uint32_t g0, uint32_
 }
 
 struct BeamJob {
-    uint32_t src, dst, inplace, _pad;
+    uint32_t src, dst;
+    int src_hi;      // st_hi of the source state before this step (groups beyond it are empty)
+    uint32_t _pad;
 };
+
+__device__ __forceinline__ void fb_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __global__ void __launch_bounds__(FB_BEAM_THREADS) k_beam(BeamParams bp) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -172,12 +180,14 @@ __global__ void __launch_bounds__(FB_BEAM_THREADS) k_beam(BeamParams bp) {
     unsigned long long *st_hash = reinterpret_cast<unsigned long long *>(smem + L.off_st_hash);
     double *sc_same = reinterpret_cast<double *>(smem + L.off_sc_same);
     double *sc_diff = reinterpret_cast<double *>(smem + L.off_sc_diff);
+    double *sc_pv = reinterpret_cast<double *>(smem + L.off_sc_pv);
     int *st_hi = reinterpret_cast<int *>(smem + L.off_st_hi);
     int *st_mark = reinterpret_cast<int *>(smem + L.off_st_mark);
     int *st_free = reinterpret_cast<int *>(smem + L.off_free);
     int *live = reinterpret_cast<int *>(smem + L.off_live);
     double *ch_score = reinterpret_cast<double *>(smem + L.off_ch_score);
-    double *ch_diff = reinterpret_cast<double *>(smem + L.off_ch_diff);
+    unsigned long long *ch_fold = reinterpret_cast<unsigned long long *>(smem + L.off_ch_fold);
+    int *ch_m = reinterpret_cast<int *>(smem + L.off_ch_m);
     uint16_t *ch_parent = reinterpret_cast<uint16_t *>(smem + L.off_ch_parent);
     uint16_t *ch_part = reinterpret_cast<uint16_t *>(smem + L.off_ch_part);
     uint16_t *ch_class = reinterpret_cast<uint16_t *>(smem + L.off_ch_class);
@@ -188,14 +198,10 @@ __global__ void __launch_bounds__(FB_BEAM_THREADS) k_beam(BeamParams bp) {
     BeamJob *jobs = reinterpret_cast<BeamJob *>(smem + L.off_job);
     int *addnew = reinterpret_cast<int *>(smem + L.off_addnew);
     int *plain = reinterpret_cast<int *>(smem + L.off_plain);
-    // misc scalars
     struct Misc {
         unsigned long long delta;
         int n_nodes[2];
-        int n_live, n_free, n_children, n_jobs_copy, n_jobs_inplace, hp_len;
-        RInfo ri;
-        uint32_t first0;  // block-local position0 of the read's first SNP
-        uint32_t nnz;
+        int n_live, n_free, n_jobs_copy, n_jobs_inplace;
     };
     Misc *ms = reinterpret_cast<Misc *>(smem + L.off_misc);
 
@@ -226,6 +232,8 @@ __global__ void __launch_bounds__(FB_BEAM_THREADS) k_beam(BeamParams bp) {
 #define ND_SCORE(g, n) nd_score[(g) * Wm + (n)]
 #define ND_ERR(g, n, h) nd_err[((g) * Wm + (n)) * Pm + (h)]
 #define ND_REF(g, n, h) nd_ref[((g) * Wm + (n)) * Pm + (h)]
+        const RInfo *__restrict__ rinfo = bp.rinfo + in.read_off;
+        const RExtra *__restrict__ rextra = bp.rextra + in.read_off;
 
         // ---- init: one root node over the empty state (global_clustering.rs:29-47) ---------------------------------
         for (uint32_t s = tid; s < NS; s += FB_BEAM_THREADS) {
@@ -247,7 +255,7 @@ __global__ void __launch_bounds__(FB_BEAM_THREADS) k_beam(BeamParams bp) {
                 ND_REF(0, 0, h) = 0;
             }
         }
-        long long pt[6] = {0, 0, 0, 0, 0, 0};
+        long long pt[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         long long tc = clock64();
 #define PROF(i)                         \
     if (bp.prof && tid == 0) {          \
@@ -259,66 +267,43 @@ __global__ void __launch_bounds__(FB_BEAM_THREADS) k_beam(BeamParams bp) {
         uint32_t prev_start = 0;  // block-local position0 from which the hashes are valid
         int gmax = -1;            // last block-local group touched so far
         unsigned long long cells = 0, tapn = 0;
+        RInfo ri_next = rinfo[0];
+        RExtra rx_next = rextra[0];
         __syncthreads();
 
         for (uint32_t step = 0; step < in.n_reads; ++step) {
             const uint32_t width = step < 25 ? Wmax : bp.B;  // global_clustering.rs:50-53
-            if (tid == 0) {
-                RInfo ri = bp.rinfo[in.read_off + step];
-                ms->ri = ri;
-                ms->first0 = (bp.fr.first[ri.rid] - 1u) - in.ag0 * 16u;
-                ms->nnz = bp.fr.nnz[ri.rid];
-                ms->delta = 0ULL;
+            const RInfo ri = ri_next;
+            const RExtra rx = rx_next;
+            if (step + 1 < in.n_reads) {  // prefetch the next read's descriptor (consumed next iteration)
+                ri_next = rinfo[step + 1];
+                rx_next = rextra[step + 1];
             }
-            __syncthreads();
-            const RInfo ri = ms->ri;
-            const uint32_t cur_start = ms->first0;
+            const uint32_t cur_start = rx.first0;
             const uint32_t g0 = ri.gbase + ri.lg0, g1 = ri.gbase + ri.lg1;  // global groups of the read
             const int n_nodes = ms->n_nodes[gen];
             const int n_live = ms->n_live;
             const int gmax_new = max(gmax, (int)ri.lg1 - 1);
             const uint32_t wend = (uint32_t)(gmax_new + 1) * 16u;  // one past the last live window position
 
-            // ---- P1: window advance: drop positions [prev_start, cur_start) from every live state's hash -----------
-            if (cur_start > prev_start) {
-                for (int li = warp; li < n_live; li += FB_BEAM_WARPS) {
-                    const int s = live[li];
-                    const int hi = st_hi[s];
+            // ---- phase 1 (all warps): per live state: window advance of the hash, score of the read, p-value --------
+            for (int li = warp; li < n_live; li += FB_BEAM_WARPS) {
+                const int s = live[li];
+                const int hi = st_hi[s];
+                if (cur_start > prev_start) {
+                    // drop positions [prev_start, cur_start) from the state's hash
                     unsigned long long sub = 0;
                     const uint32_t pend = min(cur_start, (uint32_t)(hi + 1) * 16u);
-                    const unsigned long long *c = ST_CNT(s);
-                    for (uint32_t x = prev_start * 4 + lane; x < pend * 4 && pend > prev_start; x += 32) {
-                        const uint32_t pos = x >> 2, a = x & 3;
-                        sub += fb_G(in.ag0 * 16u + pos, a) * (c[x] & FB_CNT_MASK);
+                    if (pend > prev_start) {
+                        const unsigned long long *c = ST_CNT(s);
+                        for (uint32_t x = prev_start * 4 + lane; x < pend * 4; x += 32) {
+                            const uint32_t pos = x >> 2, a = x & 3;
+                            sub += fb_G(in.ag0 * 16u + pos, a) * (c[x] & FB_CNT_MASK);
+                        }
                     }
                     sub = fb_warp_sum_u64(sub);
                     if (lane == 0) st_hash[s] -= sub;
                 }
-            }
-            // ---- delta(read) = sum over its cells of G(pos, allele) * weight ------------------------------------------
-            {
-                unsigned long long d = 0;
-                for (uint32_t x = tid; x < (ri.lg1 - ri.lg0) * 4; x += FB_BEAM_THREADS) {
-                    const uint32_t lg = ri.lg0 + (x >> 2), sub = x & 3;
-                    const uint32_t g = ri.gbase + lg;
-                    const uint32_t q = qual32[(uint64_t)g * 4 + sub];
-                    const uint32_t al = bp.fr.allele[g], pr = bp.fr.present[g];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t c = sub * 4 + k;
-                        if ((pr >> c) & 1u) {
-                            const uint32_t av = ((al >> c) & 1u) | (((al >> (16 + c)) & 1u) << 1);
-                            d += fb_G((in.ag0 + lg) * 16u + c, av) * (unsigned long long)lut_s[(q >> (8 * k)) & 0xFFu];
-                        }
-                    }
-                }
-                d = fb_warp_sum_u64(d);
-                if (lane == 0 && d) atomicAdd(&ms->delta, d);
-            }
-            // ---- P2: score the read against every live state (utils_frags.rs:32-75) --------------------------------------
-            for (int li = warp; li < n_live; li += FB_BEAM_WARPS) {
-                const int s = live[li];
-                const int hi = st_hi[s];
                 const uint2 *mk = ST_MASK(s);
                 unsigned long long total = 0, same = 0, emptyw = 0;
                 uint32_t ne_cnt = 0;
@@ -356,53 +341,86 @@ __global__ void __launch_bounds__(FB_BEAM_THREADS) k_beam(BeamParams bp) {
                 else
                     diff_f = fb_replay_diff_state(bp.fr, g0, g1, mk, ri.lg0, hi, lut_s, bp.eps, wscr);
                 if (lane == 0) {
-                    sc_same[s] = fb_q26_to_f64((long long)same);
+                    const double same_f = fb_q26_to_f64((long long)same);
+                    sc_same[s] = same_f;
                     sc_diff[s] = diff_f;
+                    // global_clustering.rs:81-88
+                    sc_pv[s] = 1.0 * fb_stable_binom_cdf_p_rev(fb_as_usize(same_f + diff_f), fb_as_usize(diff_f), bp.eps,
+                                                               bp.div_factor);
                 }
+            }
+            // delta(read) = sum over its cells of G(pos, allele) * weight, by the last warp (least loaded)
+            if (warp == FB_BEAM_WARPS - 1) {
+                unsigned long long d = 0;
+                for (uint32_t x = lane; x < (ri.lg1 - ri.lg0) * 4; x += 32) {
+                    const uint32_t lg = ri.lg0 + (x >> 2), sub = x & 3;
+                    const uint32_t g = ri.gbase + lg;
+                    const uint32_t q = qual32[(uint64_t)g * 4 + sub];
+                    const uint32_t al = bp.fr.allele[g], pr = bp.fr.present[g];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t c = sub * 4 + k;
+                        if ((pr >> c) & 1u) {
+                            const uint32_t av = ((al >> c) & 1u) | (((al >> (16 + c)) & 1u) << 1);
+                            d += fb_G((in.ag0 + lg) * 16u + c, av) * (unsigned long long)lut_s[(q >> (8 * k)) & 0xFFu];
+                        }
+                    }
+                }
+                d = fb_warp_sum_u64(d);
+                if (lane == 0) ms->delta = d;
             }
             __syncthreads();
             PROF(0)
 
-            // ---- P3: per node p-values, pruning, child scores (global_clustering.rs:71-115, 181-208) ----------------------
-            if (tid < n_nodes) {
-                const int n = tid;
-                double pv[FB_MAXP];
-                for (uint32_t j = 0; j < P; ++j) {
-                    const int s = ND_REF(gen, n, j);
-                    const double same = sc_same[s], diff = sc_diff[s];
-                    pv[j] = 1.0 * fb_stable_binom_cdf_p_rev(fb_as_usize(same + diff), fb_as_usize(diff), bp.eps,
-                                                            bp.div_factor);
-                    if (bp.tap.cap) {
-                        const unsigned long long o = tapn + (unsigned long long)n * P + j;
-                        if (o < bp.tap.cap) {
-                            if (bp.tap.same) bp.tap.same[o] = same;
-                            if (bp.tap.diff) bp.tap.diff[o] = diff;
-                            if (bp.tap.logp) bp.tap.logp[o] = pv[j];
+            // ---- phase 2 (warp 0): pruning, child scores, equality classes, exact BinaryHeap emulation, next generation;
+            //      the other warps prefetch the next read's groups into L2 ------------------------------------------------
+            if (warp != 0) {
+                if (step + 1 < in.n_reads) {
+                    const uint32_t ng0 = ri_next.gbase + ri_next.lg0, ng1 = ri_next.gbase + ri_next.lg1;
+                    for (uint32_t g = ng0 + (tid - 32) * 8; g < ng1; g += (FB_BEAM_THREADS - 32) * 8) {
+                        fb_prefetch_l2(bp.fr.qual + g);          // 8 groups = 128 B of quals
+                        if (((g - ng0) & 31) == 0) fb_prefetch_l2(bp.fr.allele + g);
+                        if (((g - ng0) & 63) == 0) fb_prefetch_l2(bp.fr.present + g);
+                    }
+                }
+            } else {
+                // (a) per node: log-sum-exp, pruning (global_clustering.rs:93-98), child score (:181-208)
+                for (int n0 = 0; n0 < n_nodes; n0 += 32) {
+                    const int n = n0 + (int)lane;
+                    if (n < n_nodes) {
+                        double pv[FB_MAXP];
+                        for (uint32_t j = 0; j < P; ++j) {
+                            const int s = ND_REF(gen, n, j);
+                            pv[j] = sc_pv[s];
+                            if (bp.tap.cap) {
+                                const unsigned long long o = tapn + (unsigned long long)n * P + j;
+                                if (o < bp.tap.cap) {
+                                    if (bp.tap.same) bp.tap.same[o] = sc_same[s];
+                                    if (bp.tap.diff) bp.tap.diff[o] = sc_diff[s];
+                                    if (bp.tap.logp) bp.tap.logp[o] = pv[j];
+                                }
+                            }
+                        }
+                        const double lse = fb_log_sum_exp(pv, (int)P);
+                        for (uint32_t j = 0; j < P; ++j) {
+                            double sc = -1.0;  // < 0 marks "pruned" (scores are sums of non-negative terms)
+                            if (pv[j] - lse > bp.cutoff) {
+                                double mec = 0.0;  // new_error_vec.iter().map(|x| x.1).sum()
+                                for (uint32_t h = 0; h < P; ++h) {
+                                    double e = ND_ERR(gen, n, h);
+                                    if (h == j) e = e + sc_diff[ND_REF(gen, n, j)];
+                                    mec += e;
+                                }
+                                sc = -(-1.0 * mec);  // new_node_score = -score, score = -1.0 * mec
+                            }
+                            ch_score[n * P + j] = sc;  // staging, compacted below
                         }
                     }
                 }
-                const double lse = fb_log_sum_exp(pv, (int)P);
-                for (uint32_t j = 0; j < P; ++j) {
-                    double sc = -1.0;  // < 0 marks "pruned" (scores are sums of non-negative terms)
-                    if (pv[j] - lse > bp.cutoff) {
-                        double mec = 0.0;  // new_error_vec.iter().map(|x| x.1).sum()
-                        for (uint32_t h = 0; h < P; ++h) {
-                            double e = ND_ERR(gen, n, h);
-                            if (h == j) e = e + sc_diff[ND_REF(gen, n, j)];
-                            mec += e;
-                        }
-                        sc = -(-1.0 * mec);  // new_node_score = -score, score = -1.0 * mec
-                    }
-                    ch_score[n * P + j] = sc;  // staging, compacted below
-                }
-            }
-            __syncthreads();
-            PROF(1)
-
-            // ---- P4 (warp 0): compaction, equality classes, exact BinaryHeap emulation -------------------------------------
-            if (warp == 0) {
-                // compaction in evaluation order (node in heap order, j ascending); staged scores are read before being
-                // overwritten because the compacted index never exceeds the staging index.
+                __syncwarp();
+                PROF(6)
+                // (b) compaction in evaluation order (node in heap order, j ascending); the compacted index never exceeds
+                //     the staging index, and every lane reads its staged value before anything of its chunk is written
                 int nc = 0;
                 for (int x0 = 0; x0 < n_nodes * (int)P; x0 += 32) {
                     const int x = x0 + (int)lane;
@@ -420,39 +438,56 @@ __global__ void __launch_bounds__(FB_BEAM_THREADS) k_beam(BeamParams bp) {
                     __syncwarp();
                 }
                 const unsigned long long delta = ms->delta;
-                // equality classes of the children's (virtual) blocks
-                int n_classes = 0;  // class representatives are children; ch_class[c] = index of the representative child
-                for (int c = 0; c < nc; ++c) {
-                    const int n1 = ch_parent[c], j1 = ch_part[c];
-                    int found = -1;
-                    for (int r0 = 0; r0 < c && found < 0; r0 += 32) {
-                        const int r = r0 + (int)lane;
-                        bool cand = false;
-                        if (r < c && ch_class[r] == r) {  // r is a representative
-                            const int n2 = ch_parent[r], j2 = ch_part[r];
-                            cand = true;
-                            for (uint32_t i = 0; i < P; ++i) {
-                                const unsigned long long ha =
-                                    st_hash[ND_REF(gen, n1, i)] + ((int)i == j1 ? delta : 0ULL);
-                                const unsigned long long hb =
-                                    st_hash[ND_REF(gen, n2, i)] + ((int)i == j2 ? delta : 0ULL);
-                                if (ha != hb) {
-                                    cand = false;
-                                    break;
-                                }
+                // (c) one 64-bit fold of each child's tuple of (virtual) state hashes
+                for (int c0 = 0; c0 < nc; c0 += 32) {
+                    const int c = c0 + (int)lane;
+                    if (c < nc) {
+                        const int n1 = ch_parent[c], j1 = ch_part[c];
+                        unsigned long long f = 0;
+                        for (uint32_t i = 0; i < P; ++i)
+                            f += fb_mix64(st_hash[ND_REF(gen, n1, i)] + ((int)i == j1 ? delta : 0ULL) +
+                                          0x632BE59BD9B4E019ULL * (i + 1));
+                        ch_fold[c] = f;
+                        ch_class[c] = (uint16_t)c;
+                    }
+                }
+                __syncwarp();
+                // (d) first earlier child with the same fold (candidate duplicate)
+                unsigned anydup = 0;
+                for (int c0 = 0; c0 < nc; c0 += 32) {
+                    const int c = c0 + (int)lane;
+                    int m = -1;
+                    if (c < nc) {
+                        const unsigned long long f = ch_fold[c];
+                        for (int r = 0; r < c; ++r)
+                            if (ch_fold[r] == f) {
+                                m = r;
+                                break;
                             }
-                        }
-                        unsigned bal = __ballot_sync(0xFFFFFFFFu, cand);
-                        while (bal && found < 0) {
-                            const int rr = r0 + __ffs(bal) - 1;
-                            bal &= bal - 1;
-                            // exact verification on the virtual states
-                            const int n2 = ch_parent[rr], j2 = ch_part[rr];
+                        ch_m[c] = m;
+                    }
+                    anydup |= __ballot_sync(0xFFFFFFFFu, m >= 0);
+                }
+                __syncwarp();
+                // (e) exact equality classes: only children with a fold match need the word-by-word verification
+                if (anydup) {
+                    for (int c = 0; c < nc; ++c) {
+                        if (ch_m[c] < 0) continue;
+                        const int n1 = ch_parent[c], j1 = ch_part[c];
+                        const unsigned long long f = ch_fold[c];
+                        int found = -1;
+                        for (int r = ch_m[c]; r < c && found < 0; ++r) {
+                            if (ch_fold[r] != f || ch_class[r] != r) continue;  // representatives with the same fold
+                            const int n2 = ch_parent[r], j2 = ch_part[r];
                             bool eq = true;
                             for (uint32_t i = 0; i < P && eq; ++i) {
                                 const int sA = ND_REF(gen, n1, i), sB = ND_REF(gen, n2, i);
                                 const bool addA = (int)i == j1, addB = (int)i == j2;
                                 if (sA == sB && addA == addB) continue;
+                                if (st_hash[sA] + (addA ? delta : 0ULL) != st_hash[sB] + (addB ? delta : 0ULL)) {
+                                    eq = false;
+                                    break;
+                                }
                                 const unsigned long long *cA = ST_CNT(sA), *cB = ST_CNT(sB);
                                 const int hiA = st_hi[sA], hiB = st_hi[sB];
                                 for (uint32_t p0 = cur_start; p0 < wend; p0 += 32) {
@@ -491,29 +526,30 @@ __global__ void __launch_bounds__(FB_BEAM_THREADS) k_beam(BeamParams bp) {
                                     }
                                 }
                             }
-                            if (eq) found = rr;
+                            if (eq) found = r;
                         }
+                        __syncwarp();
+                        if (lane == 0 && found >= 0) ch_class[c] = (uint16_t)found;
+                        __syncwarp();
                     }
-                    __syncwarp();
-                    if (lane == 0) ch_class[c] = (uint16_t)(found >= 0 ? found : c);
-                    if (found < 0) n_classes++;
-                    __syncwarp();
                 }
-                (void)n_classes;
-                // heap: global_clustering.rs:122-135
+                PROF(7)
+                // (f) heap: global_clustering.rs:122-135
                 HeapRef hp;
                 hp.score = hp_score;
                 hp.item = hp_item;
                 hp.len = 0;
                 for (int c = 0; c < nc; ++c) {
                     const double sc = ch_score[c];
-                    const int cls = ch_class[c];
                     bool exists = false;
-                    for (int e0 = 0; e0 < hp.len; e0 += 32) {
-                        const int e = e0 + (int)lane;
-                        bool hit = false;
-                        if (e < hp.len) hit = (ch_class[hp_item[e]] == cls) && (hp_score[e] >= sc);
-                        if (__any_sync(0xFFFFFFFFu, hit)) exists = true;
+                    if (anydup) {
+                        const int cls = ch_class[c];
+                        for (int e0 = 0; e0 < hp.len; e0 += 32) {
+                            const int e = e0 + (int)lane;
+                            bool hit = false;
+                            if (e < hp.len) hit = (ch_class[hp_item[e]] == cls) && (hp_score[e] >= sc);
+                            if (__any_sync(0xFFFFFFFFu, hit)) exists = true;
+                        }
                     }
                     if (!exists) {
                         if (lane == 0) {
@@ -521,53 +557,46 @@ __global__ void __launch_bounds__(FB_BEAM_THREADS) k_beam(BeamParams bp) {
                             if ((uint32_t)hp.len > width) hp.pop();
                         }
                         hp.len = __shfl_sync(0xFFFFFFFFu, hp.len, 0);
+                        __syncwarp();
                     }
-                    __syncwarp();
                 }
-                if (lane == 0) {
-                    ms->hp_len = hp.len;
-                    ms->n_children = nc;
-                }
-                // ---- which states does the next generation need? ---------------------------------------------------------
+                const int len = hp.len;
+                PROF(8)
+                if (bp.prof && tid == 0) { pt[10] += nc; pt[11] += len; }
+                // (g) which states does the next generation need?
                 for (uint32_t s = lane; s < NS; s += 32) {
                     plain[s] = 0;
                     addnew[s] = -1;
                     st_mark[s] = 0;
                 }
                 __syncwarp();
+                for (int x = (int)lane; x < len * (int)P; x += 32) {
+                    const int e = x / (int)P, i = x % (int)P;
+                    const int c = hp_item[e];
+                    if (i != (int)ch_part[c]) plain[ND_REF(gen, ch_parent[c], i)] = 1;
+                }
+                __syncwarp();
                 if (lane == 0) {
-                    const int len = hp.len;
-                    for (int e = 0; e < len; ++e) {
-                        const int c = hp_item[e];
-                        const int n = ch_parent[c], j = ch_part[c];
-                        for (uint32_t i = 0; i < P; ++i)
-                            if ((int)i != j) plain[ND_REF(gen, n, i)] = 1;
-                    }
                     int nj_copy = 0, nj_inpl = 0;
                     int nfree = ms->n_free;
                     // jobs: copies first [0, nj_copy), in-place ones stored from the back of the array
                     for (int e = 0; e < len; ++e) {
                         const int c = hp_item[e];
-                        const int n = ch_parent[c], j = ch_part[c];
-                        const int s = ND_REF(gen, n, j);
+                        const int s = ND_REF(gen, ch_parent[c], ch_part[c]);
                         if (addnew[s] < 0) {
+                            BeamJob jb;
+                            jb.src = (uint32_t)s;
+                            jb.src_hi = st_hi[s];
+                            jb._pad = 0;
                             if (!plain[s]) {
                                 addnew[s] = s;
-                                BeamJob jb;
-                                jb.src = s;
-                                jb.dst = s;
-                                jb.inplace = 1;
-                                jb._pad = 0;
-                                jobs[(int)Wm - nj_inpl] = jb;
+                                jb.dst = (uint32_t)s;
+                                jobs[(int)Wm + 1 - nj_inpl] = jb;
                                 nj_inpl++;
                             } else {
                                 const int d = st_free[--nfree];
                                 addnew[s] = d;
-                                BeamJob jb;
-                                jb.src = s;
-                                jb.dst = d;
-                                jb.inplace = 0;
-                                jb._pad = 0;
+                                jb.dst = (uint32_t)d;
                                 jobs[nj_copy++] = jb;
                             }
                         }
@@ -575,9 +604,14 @@ __global__ void __launch_bounds__(FB_BEAM_THREADS) k_beam(BeamParams bp) {
                     ms->n_free = nfree;
                     ms->n_jobs_copy = nj_copy;
                     ms->n_jobs_inplace = nj_inpl;
-                    // next generation's node tables + history
+                    ms->n_nodes[gen ^ 1] = len;
+                    if (bp.prof) pt[9] += nj_copy * 1000 + nj_inpl;
+                }
+                __syncwarp();
+                // next generation's node tables + history (one lane per entry)
+                {
                     const int ng2 = gen ^ 1;
-                    for (int e = 0; e < len; ++e) {
+                    for (int e = (int)lane; e < len; e += 32) {
                         const int c = hp_item[e];
                         const int n = ch_parent[c], j = ch_part[c];
                         ND_SCORE(ng2, e) = hp_score[e];
@@ -594,16 +628,50 @@ __global__ void __launch_bounds__(FB_BEAM_THREADS) k_beam(BeamParams bp) {
                         }
                         hist[(uint64_t)step * Wm + e] = (uint32_t)n | ((uint32_t)j << 16);
                     }
-                    ms->n_nodes[ng2] = len;
+                }
+                __syncwarp();
+                // per-state bookkeeping of the new states (each dst is written once; a copy's dst is never a src)
+                {
+                    const int nj_copy = ms->n_jobs_copy, njt = nj_copy + ms->n_jobs_inplace;
+                    for (int x = (int)lane; x < njt; x += 32) {
+                        const BeamJob jb = x < nj_copy ? jobs[x] : jobs[(int)Wm + 1 - (x - nj_copy)];
+                        const unsigned long long h = st_hash[jb.src] + delta;
+                        __syncwarp(__activemask());
+                        st_hash[jb.dst] = h;
+                        st_hi[jb.dst] = max(jb.src_hi, (int)ri.lg1 - 1);
+                    }
+                }
+                __syncwarp();
+                // free list + live list of the next generation (deterministic order)
+                {
+                    int nl = 0, nf = 0;
+                    for (uint32_t s0 = 0; s0 < NS; s0 += 32) {
+                        const uint32_t s = s0 + lane;
+                        const bool isl = s < NS && st_mark[s];
+                        const unsigned bal = __ballot_sync(0xFFFFFFFFu, isl);
+                        if (isl) live[nl + __popc(bal & ((1u << lane) - 1u))] = (int)s;
+                        nl += __popc(bal);
+                    }
+                    // free list: descending ids so that pops hand out ascending ids
+                    for (int s0 = (int)((NS + 31) / 32) * 32 - 32; s0 >= 0; s0 -= 32) {
+                        const int s = s0 + 31 - (int)lane;  // lane 0 sees the largest id of the chunk
+                        const bool isf = s >= 1 && s < (int)NS && !st_mark[s];
+                        const unsigned bal = __ballot_sync(0xFFFFFFFFu, isf);
+                        if (isf) st_free[nf + __popc(bal & ((1u << lane) - 1u))] = s;
+                        nf += __popc(bal);
+                    }
+                    if (lane == 0) {
+                        ms->n_live = nl;
+                        ms->n_free = nf;
+                    }
                 }
             }
             __syncthreads();
-            PROF(2)
+            PROF(1)
 
-            // ---- P5: materialise the new states (types_structs.rs:368-373 on the dense layout) ------------------------------
+            // ---- phase 3 (all warps): materialise the new states (types_structs.rs:368-373 on the dense layout) --------------
             {
                 const int nj_copy = ms->n_jobs_copy, nj_inpl = ms->n_jobs_inplace;
-                const unsigned long long delta = ms->delta;
                 const int gs = (int)(cur_start >> 4);
                 // copies: groups [gs, gmax_new]; in place: the read's groups only
                 for (int pass = 0; pass < 2; ++pass) {
@@ -619,17 +687,17 @@ __global__ void __launch_bounds__(FB_BEAM_THREADS) k_beam(BeamParams bp) {
                         int lg = 0;
                         uint32_t sub = 0;
                         BeamJob jb;
-                        jb.src = jb.dst = jb.inplace = jb._pad = 0;
+                        jb.src = jb.dst = jb._pad = 0;
+                        jb.src_hi = -1;
                         if (act) {
                             const int jn = idx / nq, qx = idx % nq;
-                            jb = pass == 0 ? jobs[jn] : jobs[(int)Wm - jn];
+                            jb = pass == 0 ? jobs[jn] : jobs[(int)Wm + 1 - jn];
                             lg = glo + (qx >> 2);
                             sub = (uint32_t)qx & 3u;
-                            const int hi_src = st_hi[jb.src];
                             unsigned long long wv[16];
                             const ulonglong2 *src =
                                 reinterpret_cast<const ulonglong2 *>(ST_CNT(jb.src) + ((uint64_t)lg * 16 + sub * 4) * 4);
-                            if (lg <= hi_src) {
+                            if (lg <= jb.src_hi) {
 #pragma unroll
                                 for (int x = 0; x < 8; ++x) {
                                     ulonglong2 v = src[x];
@@ -684,52 +752,14 @@ __global__ void __launch_bounds__(FB_BEAM_THREADS) k_beam(BeamParams bp) {
                             ST_MASK(jb.dst)[lg] = make_uint2(pl[0] | (pl[1] << 16), pl[2] | (pl[3] << 16));
                     }
                 }
-                __syncthreads();
-                PROF(3)
-                // per-state bookkeeping of the new states
-                const int njt = nj_copy + nj_inpl;
-                if (tid < njt) {
-                    const BeamJob jb = tid < nj_copy ? jobs[tid] : jobs[(int)Wm - (tid - nj_copy)];
-                    const unsigned long long h = st_hash[jb.src] + delta;
-                    const int hi = max(st_hi[jb.src], (int)ri.lg1 - 1);
-                    // (src may equal dst; each dst is written by exactly one thread, and src values of other jobs are
-                    //  never a dst of a copy job, so reading before the barrier below is race free for copies; in-place
-                    //  jobs read and write their own entry)
-                    st_hash[jb.dst] = h;
-                    st_hi[jb.dst] = hi;
-                }
-                __syncthreads();
             }
-            // ---- free list + live list of the next generation (warp 0, deterministic order) --------------------------------
-            if (warp == 0) {
-                int nl = 0, nf = 0;
-                for (uint32_t s0 = 0; s0 < NS; s0 += 32) {
-                    const uint32_t s = s0 + lane;
-                    const bool isl = s < NS && st_mark[s];
-                    const unsigned bal = __ballot_sync(0xFFFFFFFFu, isl);
-                    if (isl) live[nl + __popc(bal & ((1u << lane) - 1u))] = (int)s;
-                    nl += __popc(bal);
-                }
-                // free list: descending ids so that pops hand out ascending ids
-                for (int s0 = (int)((NS + 31) / 32) * 32 - 32; s0 >= 0; s0 -= 32) {
-                    const int s = s0 + 31 - (int)lane;  // lane 0 sees the largest id of the chunk
-                    const bool isf = s >= 1 && s < (int)NS && !st_mark[s];
-                    const unsigned bal = __ballot_sync(0xFFFFFFFFu, isf);
-                    if (isf) st_free[nf + __popc(bal & ((1u << lane) - 1u))] = s;
-                    nf += __popc(bal);
-                }
-                if (lane == 0) {
-                    ms->n_live = nl;
-                    ms->n_free = nf;
-                }
-            }
-            cells += (unsigned long long)n_nodes * ms->nnz;
+            cells += (unsigned long long)n_nodes * rx.nnz;
             tapn += (unsigned long long)n_nodes * P;
             gen ^= 1;
             prev_start = cur_start;
             gmax = gmax_new;
             __syncthreads();
-            PROF(4)
+            PROF(2)
         }
 
         // ---- global_clustering.rs:149-176: best = into_sorted_vec()[0]; walk the parent pointers ------------------------------
@@ -756,8 +786,8 @@ __global__ void __launch_bounds__(FB_BEAM_THREADS) k_beam(BeamParams bp) {
             bp.tapn_out[ii] = tapn;
             if (bp.prof) {
                 PROF(5)
-                for (int i = 0; i < 6; ++i) atomicAdd(bp.prof + i, (unsigned long long)pt[i]);
-                atomicAdd(bp.prof + 6, (unsigned long long)in.n_reads);
+                for (int i = 0; i < 12; ++i) atomicAdd(bp.prof + i, (unsigned long long)pt[i]);
+                atomicAdd(bp.prof + 12, (unsigned long long)in.n_reads);
             }
         }
 #undef PROF
@@ -768,4 +798,3 @@ __global__ void __launch_bounds__(FB_BEAM_THREADS) k_beam(BeamParams bp) {
 #undef ND_REF
     }
 }
-

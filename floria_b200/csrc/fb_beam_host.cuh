@@ -85,6 +85,7 @@ static int fb_run_beam(fb_ctx *ctx, Engine &e, const fb_params *prm, const BeamT
     bp.fr = e.df->dev();
     bp.inst = e.d_inst;
     bp.rinfo = e.d_rinfo;
+    bp.rextra = e.d_rextra;
     bp.lut = ctx->d_lut;
     bp.order = d_order;
     bp.n_work = (int)order.size();
@@ -108,11 +109,11 @@ static int fb_run_beam(fb_ctx *ctx, Engine &e, const fb_params *prm, const BeamT
     unsigned long long *d_prof = nullptr;
     const bool prof = getenv("FB_BEAM_PROF") != nullptr;
     if (prof) {
-        if ((rc = fb_dalloc(ctx, &d_prof, 8))) {
+        if ((rc = fb_dalloc(ctx, &d_prof, 16))) {
             cleanup();
             return rc;
         }
-        cudaMemsetAsync(d_prof, 0, 64, ctx->stream);
+        cudaMemsetAsync(d_prof, 0, 128, ctx->stream);
         bp.prof = d_prof;
     }
     cudaEvent_t e0 = fb_event(ctx);
@@ -134,13 +135,17 @@ static int fb_run_beam(fb_ctx *ctx, Engine &e, const fb_params *prm, const BeamT
     }
     cudaEventElapsedTime(&br.beam_ms, e0, e1);
     if (prof) {
-        unsigned long long h[8];
-        cudaMemcpy(h, d_prof, 64, cudaMemcpyDeviceToHost);
+        unsigned long long h[16];
+        cudaMemcpy(h, d_prof, 128, cudaMemcpyDeviceToHost);
         fb_cache_free(d_prof);
-        double steps = (double)std::max<unsigned long long>(h[6], 1);
-        fprintf(stderr, "[k_beam prof] %.3f ms, %d instances on %llu CTAs, %.0f steps; cycles/step: score %.0f  pvals %.0f  heap %.0f  copy %.0f  lists %.0f  (backtrack total %.0f)\n",
-                br.beam_ms, (int)order.size(), (unsigned long long)n_slots, steps, h[0] / steps, h[1] / steps, h[2] / steps, h[3] / steps,
-                h[4] / steps, (double)h[5]);
+        double steps = (double)std::max<unsigned long long>(h[12], 1);
+        fprintf(stderr,
+                "[k_beam prof] %.3f ms, %d instances on %llu CTAs, %.0f steps; cycles/step: phase1(score) %.0f | warp0: lse %.0f "
+                "compact+fold+dups+classes %.0f heap %.0f nextgen %.0f | phase3(copy) %.0f | children/step %.1f survivors/step %.1f "
+                "copyjobs/step %.2f inplace/step %.2f | backtrack total %.0f\n",
+                br.beam_ms, (int)order.size(), (unsigned long long)n_slots, steps, h[0] / steps, h[6] / steps, h[7] / steps,
+                h[8] / steps, h[1] / steps, h[2] / steps, h[10] / steps, h[11] / steps, (h[9] / 1000) / steps,
+                (h[9] % 1000) / steps, (double)h[5]);
     }
     cleanup();
     return FB_OK;

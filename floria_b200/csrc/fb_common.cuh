@@ -53,6 +53,12 @@ struct RInfo {
     uint32_t lg1;    // one past the last
 };
 
+// per (block, read) extras for the beam search
+struct RExtra {
+    uint32_t first0;  // block-local position0 of the read's first SNP
+    uint32_t nnz;     // stored cells of the read
+};
+
 struct InstState {
     int cur;       // which of the two count/mask/assign buffers holds the accepted partition
     int active;    // still iterating optimize_clustering

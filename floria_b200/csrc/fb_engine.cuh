@@ -139,6 +139,7 @@ struct Engine {
     std::vector<uint64_t> assign_prefix, tile_prefix, hap_prefix, moves_off;
     std::vector<uint32_t> moves_cap;
     std::vector<RInfo> rinfo;
+    std::vector<RExtra> rextra;
     uint64_t tot_assign = 0, tot_gain = 0, tot_cnt = 0, tot_mask = 0, tot_mec = 0, tot_moves = 0;
     // device
     InstDev *d_inst = nullptr;
@@ -146,6 +147,7 @@ struct Engine {
     uint64_t *d_assign_prefix = nullptr, *d_tile_prefix = nullptr, *d_hap_prefix = nullptr, *d_moves_off = nullptr;
     uint32_t *d_moves_cap = nullptr;
     RInfo *d_rinfo = nullptr;
+    RExtra *d_rextra = nullptr;
     uint8_t *d_assign[2] = {nullptr, nullptr};
     uint64_t *d_cnt[2] = {nullptr, nullptr};
     uint2 *d_masks[2] = {nullptr, nullptr};
@@ -165,6 +167,7 @@ struct Engine {
         fb_cache_free(d_moves_off);
         fb_cache_free(d_moves_cap);
         fb_cache_free(d_rinfo);
+        fb_cache_free(d_rextra);
         for (int b = 0; b < 2; ++b) {
             fb_cache_free(d_assign[b]);
             fb_cache_free(d_cnt[b]);
@@ -178,6 +181,7 @@ struct Engine {
         d_assign_prefix = d_tile_prefix = d_hap_prefix = d_moves_off = nullptr;
         d_moves_cap = nullptr;
         d_rinfo = nullptr;
+        d_rextra = nullptr;
         for (int b = 0; b < 2; ++b) {
             d_assign[b] = nullptr;
             d_cnt[b] = nullptr;
@@ -214,6 +218,10 @@ struct Engine {
             ri.lg1 = ri.lg0 + (df->h_gptr[r + 1] - df->h_gptr[r]);
             ri.gbase = df->h_gptr[r] - ri.lg0;
             rinfo.push_back(ri);
+            RExtra rx;
+            rx.first0 = (df->h_first[r] - 1u) - gmin * 16u;
+            rx.nnz = df->h_nnz[r];
+            rextra.push_back(rx);
         }
         blocks.push_back(std::move(b));
         return (int)blocks.size() - 1;
@@ -275,6 +283,7 @@ struct Engine {
         if ((rc = fb_upload(ctx, &d_moves_off, moves_off))) return rc;
         if ((rc = fb_upload(ctx, &d_moves_cap, moves_cap))) return rc;
         if ((rc = fb_upload(ctx, &d_rinfo, rinfo))) return rc;
+        if ((rc = fb_upload(ctx, &d_rextra, rextra))) return rc;
         for (int b = 0; b < 2; ++b) {
             if ((rc = fb_dalloc(ctx, &d_assign[b], tot_assign))) return rc;
             if ((rc = fb_dalloc(ctx, &d_cnt[b], tot_cnt))) return rc;
