@@ -98,66 +98,6 @@ struct BeamSmem {
     }
 };
 
-// exact left-to-right f64 sum of the diff/epsilon items of one read vs one state (canonical order); state planes
-// beyond `hi` are empty.  Warp-cooperative; returns the same value on every lane.
-__device__ double fb_replay_diff_state(const DFragsDev &fr, uint32_t g0, uint32_t g1, const uint2 *__restrict__ mh,
-                                       uint32_t lg0, int hi, const uint32_t *lut, double eps, uint32_t *wscratch) {
-    const uint32_t lane = fb_lane();
-    SeqSum ss;
-    ss.init();
-    for (uint32_t base = g0; base < g1; base += 32) {
-        uint32_t g = base + lane;
-        bool valid = g < g1;
-        uint32_t w[16];
-        uint32_t diffbits = 0, emptybits = 0;
-        if (valid) {
-            uint4 q = fr.qual[g];
-            uint32_t al = fr.allele[g];
-            uint32_t pr = fr.present[g];
-            fb_group_weights(q, pr, lut, w);
-            uint32_t lg = lg0 + (g - g0);
-            uint2 m = ((int)lg <= hi) ? mh[lg] : make_uint2(0u, 0u);
-            uint32_t same, ne;
-            fb_group_masks(al, m, same, ne);
-            diffbits = pr & ne & ~same;
-            emptybits = pr & ~ne & 0xFFFFu;
-        } else {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) w[k] = 0;
-        }
-        long long Wl = (long long)fb_masked_sum(w, diffbits);
-        unsigned anyE = __ballot_sync(0xFFFFFFFFu, emptybits != 0);
-        if (!anyE) {
-            long long tot = (long long)fb_warp_sum_u64((unsigned long long)Wl);
-            if (ss.add_dyadic_run(tot)) continue;
-        }
-        for (int l = 0; l < 32; ++l) {
-            long long Wl_l = __shfl_sync(0xFFFFFFFFu, Wl, l);
-            uint32_t eb = __shfl_sync(0xFFFFFFFFu, emptybits, l);
-            uint32_t db = __shfl_sync(0xFFFFFFFFu, diffbits, l);
-            if (eb == 0) {
-                if (ss.add_dyadic_run(Wl_l)) continue;
-            }
-            __syncwarp();
-            if (lane == l) {
-#pragma unroll
-                for (int k = 0; k < 16; ++k) wscratch[k] = w[k];
-            }
-            __syncwarp();
-            uint32_t bits = eb | db;
-            while (bits) {
-                int k = __ffs(bits) - 1;
-                bits &= bits - 1;
-                if ((eb >> k) & 1u)
-                    ss.add_eps(eps, 0);
-                else
-                    ss.add_dyadic((long long)wscratch[k]);
-            }
-        }
-    }
-    return ss.S;
-}
-
 struct BeamJob {
     uint32_t src, dst;
     int src_hi;      // st_hi of the source state before this step (groups beyond it are empty)
@@ -166,12 +106,10 @@ struct BeamJob {
 
 __device__ __forceinline__ void fb_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-__global__ void __launch_bounds__(FB_BEAM_THREADS) k_beam(BeamParams bp) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ int s_work;
+template <int P>
+__device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii, uint8_t *smem, uint8_t *slot) {
     const int tid = threadIdx.x;
     const uint32_t lane = tid & 31, warp = tid >> 5;
-
     BeamSmem L;
     L.layout(bp.maxP, bp.maxW, bp.maxNS);
     double *nd_score = reinterpret_cast<double *>(smem + L.off_nd_score);     // [2][W]
@@ -205,20 +143,10 @@ __global__ void __launch_bounds__(FB_BEAM_THREADS) k_beam(BeamParams bp) {
     };
     Misc *ms = reinterpret_cast<Misc *>(smem + L.off_misc);
 
-    for (int i = tid; i < 256; i += FB_BEAM_THREADS) lut_s[i] = bp.lut[i];
-    uint8_t *slot = bp.scratch + (uint64_t)blockIdx.x * bp.slot_bytes;
     uint32_t *hist = reinterpret_cast<uint32_t *>(slot + bp.hist_off);
     const uint32_t *__restrict__ qual32 = reinterpret_cast<const uint32_t *>(bp.fr.qual);
-
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_work = atomicAdd(bp.work_counter, 1);
-        __syncthreads();
-        const int wk = s_work;
-        if (wk >= bp.n_work) break;
-        const int ii = bp.order[wk];
+    {
         const InstDev in = bp.inst[ii];
-        const uint32_t P = in.ploidy;
         const uint32_t Wmax = P * bp.B;
         const uint32_t NS = P * bp.B * (P + 1) + 1;
         const uint32_t npos = in.ng * 16;
@@ -339,14 +267,31 @@ __global__ void __launch_bounds__(FB_BEAM_THREADS) k_beam(BeamParams bp) {
                 else if (bp.eps_safe)
                     diff_f = fb_q26_to_f64(diff_q + (long long)ne_cnt * (long long)(bp.eps * FB_Q26));
                 else
-                    diff_f = fb_replay_diff_state(bp.fr, g0, g1, mk, ri.lg0, hi, lut_s, bp.eps, wscr);
-                if (lane == 0) {
+                    diff_f = fb_replay_diff(bp.fr, g0, g1, mk, ri.lg0, hi, lut_s, bp.eps, wscr);
+                {
+                    // stable_binom_cdf_p_rev (utils_frags.rs:211-248) with its two log terms evaluated on two lanes; the
+                    // operations and their order are those of fb_stable_binom_cdf_p_rev (global_clustering.rs:81-88).
                     const double same_f = fb_q26_to_f64((long long)same);
-                    sc_same[s] = same_f;
-                    sc_diff[s] = diff_f;
-                    // global_clustering.rs:81-88
-                    sc_pv[s] = 1.0 * fb_stable_binom_cdf_p_rev(fb_as_usize(same_f + diff_f), fb_as_usize(diff_f), bp.eps,
-                                                               bp.div_factor);
+                    const unsigned long long nn = fb_as_usize(same_f + diff_f), kk = fb_as_usize(diff_f);
+                    double pvs = 0.0;
+                    if (nn != 0) {
+                        const double n64 = (double)nn, k64 = (double)kk;
+                        double a = k64 / n64;
+                        if (a == 1.0) a = 0.9999999;
+                        if (a == 0.0) a = 0.0000001;
+                        const double x = lane == 0 ? a : (1.0 - a);
+                        const double y = lane == 0 ? bp.eps : (1.0 - bp.eps);
+                        const double t = x * log(x / y);
+                        const double t1 = __shfl_sync(0xFFFFFFFFu, t, 1);
+                        double rel_ent = t + t1;
+                        if (a < bp.eps) rel_ent = -rel_ent;
+                        pvs = -1.0 * n64 / bp.div_factor * rel_ent;
+                    }
+                    if (lane == 0) {
+                        sc_same[s] = same_f;
+                        sc_diff[s] = diff_f;
+                        sc_pv[s] = 1.0 * pvs;
+                    }
                 }
             }
             // delta(read) = sum over its cells of G(pos, allele) * weight, by the last warp (least loaded)
@@ -384,36 +329,55 @@ __global__ void __launch_bounds__(FB_BEAM_THREADS) k_beam(BeamParams bp) {
                     }
                 }
             } else {
-                // (a) per node: log-sum-exp, pruning (global_clustering.rs:93-98), child score (:181-208)
+                // (a) per node: log-sum-exp, pruning (global_clustering.rs:93-98), child score (:181-208).
+                //     Register arrays with static indexing (guards on j < P) keep the loads independent.
                 for (int n0 = 0; n0 < n_nodes; n0 += 32) {
                     const int n = n0 + (int)lane;
                     if (n < n_nodes) {
-                        double pv[FB_MAXP];
-                        for (uint32_t j = 0; j < P; ++j) {
-                            const int s = ND_REF(gen, n, j);
-                            pv[j] = sc_pv[s];
-                            if (bp.tap.cap) {
-                                const unsigned long long o = tapn + (unsigned long long)n * P + j;
-                                if (o < bp.tap.cap) {
-                                    if (bp.tap.same) bp.tap.same[o] = sc_same[s];
-                                    if (bp.tap.diff) bp.tap.diff[o] = sc_diff[s];
-                                    if (bp.tap.logp) bp.tap.logp[o] = pv[j];
+                        double pv[P], er[P], df[P];
+#pragma unroll
+                        for (int j = 0; j < P; ++j) {
+                            {
+                                const int s = ND_REF(gen, n, j);
+                                pv[j] = sc_pv[s];
+                                df[j] = sc_diff[s];
+                                er[j] = ND_ERR(gen, n, j);
+                                if (bp.tap.cap) {
+                                    const unsigned long long o = tapn + (unsigned long long)n * P + j;
+                                    if (o < bp.tap.cap) {
+                                        if (bp.tap.same) bp.tap.same[o] = sc_same[s];
+                                        if (bp.tap.diff) bp.tap.diff[o] = df[j];
+                                        if (bp.tap.logp) bp.tap.logp[o] = pv[j];
+                                    }
                                 }
                             }
                         }
-                        const double lse = fb_log_sum_exp(pv, (int)P);
-                        for (uint32_t j = 0; j < P; ++j) {
-                            double sc = -1.0;  // < 0 marks "pruned" (scores are sums of non-negative terms)
-                            if (pv[j] - lse > bp.cutoff) {
-                                double mec = 0.0;  // new_error_vec.iter().map(|x| x.1).sum()
-                                for (uint32_t h = 0; h < P; ++h) {
-                                    double e = ND_ERR(gen, n, h);
-                                    if (h == j) e = e + sc_diff[ND_REF(gen, n, j)];
-                                    mec += e;
+                        // utils_frags.rs:250-258 log_sum_exp
+                        double mx = pv[0];
+#pragma unroll
+                        for (int j = 1; j < P; ++j) mx = pv[j] > mx ? pv[j] : mx;
+                        double sum = 0.0;
+#pragma unroll
+                        for (int j = 0; j < P; ++j) sum += exp(pv[j] - mx);
+                        const double lse = mx + log(sum);
+#pragma unroll
+                        for (int j = 0; j < P; ++j) {
+                            {
+                                double sc = -1.0;  // < 0 marks "pruned" (scores are sums of non-negative terms)
+                                if (pv[j] - lse > bp.cutoff) {
+                                    double mec = 0.0;  // new_error_vec.iter().map(|x| x.1).sum()
+#pragma unroll
+                                    for (int h = 0; h < P; ++h) {
+                                        {
+                                            double e = er[h];
+                                            if (h == j) e = e + df[j];
+                                            mec += e;
+                                        }
+                                    }
+                                    sc = -(-1.0 * mec);  // new_node_score = -score, score = -1.0 * mec
                                 }
-                                sc = -(-1.0 * mec);  // new_node_score = -score, score = -1.0 * mec
+                                ch_score[n * P + j] = sc;  // staging, compacted below
                             }
-                            ch_score[n * P + j] = sc;  // staging, compacted below
                         }
                     }
                 }
@@ -796,5 +760,36 @@ __global__ void __launch_bounds__(FB_BEAM_THREADS) k_beam(BeamParams bp) {
 #undef ND_SCORE
 #undef ND_ERR
 #undef ND_REF
+    }
+}
+
+__global__ void __launch_bounds__(FB_BEAM_THREADS, 1) k_beam(BeamParams bp) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ int s_work;
+    const int tid = threadIdx.x;
+    {
+        BeamSmem L;
+        L.layout(bp.maxP, bp.maxW, bp.maxNS);
+        uint32_t *lut_s = reinterpret_cast<uint32_t *>(smem + L.off_lut);
+        for (int i = tid; i < 256; i += FB_BEAM_THREADS) lut_s[i] = bp.lut[i];
+    }
+    uint8_t *slot = bp.scratch + (uint64_t)blockIdx.x * bp.slot_bytes;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_work = atomicAdd(bp.work_counter, 1);
+        __syncthreads();
+        const int wk = s_work;
+        if (wk >= bp.n_work) break;
+        const int ii = bp.order[wk];
+        switch (bp.inst[ii].ploidy) {
+            case 2: fb_beam_instance<2>(bp, ii, smem, slot); break;
+            case 3: fb_beam_instance<3>(bp, ii, smem, slot); break;
+            case 4: fb_beam_instance<4>(bp, ii, smem, slot); break;
+            case 5: fb_beam_instance<5>(bp, ii, smem, slot); break;
+            case 6: fb_beam_instance<6>(bp, ii, smem, slot); break;
+            case 7: fb_beam_instance<7>(bp, ii, smem, slot); break;
+            case 8: fb_beam_instance<8>(bp, ii, smem, slot); break;
+            default: break;
+        }
     }
 }

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(FB_FINAL_THREADS) k_final_assign(FinalArgs a) 
                 else if (a.eps_safe)
                     diff_f = fb_q26_to_f64(diff_q + (long long)ne_cnt * (long long)(a.eps * FB_Q26));
                 else
-                    diff_f = fb_replay_diff_state(a.fr, g0, g1, mk, lg0, hi, lut_s, a.eps, wscr[warp]);
+                    diff_f = fb_replay_diff(a.fr, g0, g1, mk, lg0, hi, lut_s, a.eps, wscr[warp]);
                 if (lane == 0) {
                     s_same[k] = fb_q26_to_f64((long long)same);
                     s_diff[k] = diff_f;

@@ -64,9 +64,13 @@ struct SweepArgs {
     uint32_t *o_nempty;
 };
 
-// exact left-to-right f64 sum of the diff/epsilon items of one read vs one haplotype (canonical order)
+// Exact left-to-right f64 sum of the diff/epsilon items of one read vs one haplotype table (canonical position order),
+// i.e. the `diff` accumulator of utils_frags.rs:33-72.  Warp-cooperative; every lane returns the same value.
+// Planes of groups beyond `hi` are empty.  Per chunk of 32 groups the lanes are split by ballot into runs of
+// epsilon-free lanes (added as ONE exact integer lump when SeqSum proves that identical to item-by-item addition)
+// and lanes holding epsilon items (replayed item by item).
 __device__ double fb_replay_diff(const DFragsDev &fr, uint32_t g0, uint32_t g1, const uint2 *__restrict__ mh,
-                                 uint32_t lg0, const uint32_t *lut, double eps, uint32_t *wscratch /*16 per warp*/) {
+                                 uint32_t lg0, int hi, const uint32_t *lut, double eps, uint32_t *wscratch /*16 per warp*/) {
     const uint32_t lane = fb_lane();
     SeqSum ss;
     ss.init();
@@ -80,7 +84,8 @@ __device__ double fb_replay_diff(const DFragsDev &fr, uint32_t g0, uint32_t g1, 
             uint32_t al = fr.allele[g];
             uint32_t pr = fr.present[g];
             fb_group_weights(q, pr, lut, w);
-            uint2 m = mh[lg0 + (g - g0)];
+            const uint32_t lg = lg0 + (g - g0);
+            uint2 m = ((int)lg <= hi) ? mh[lg] : make_uint2(0u, 0u);
             uint32_t same, ne;
             fb_group_masks(al, m, same, ne);
             diffbits = pr & ne & ~same;
@@ -89,34 +94,65 @@ __device__ double fb_replay_diff(const DFragsDev &fr, uint32_t g0, uint32_t g1, 
 #pragma unroll
             for (int k = 0; k < 16; ++k) w[k] = 0;
         }
-        long long Wl = (long long)fb_masked_sum(w, diffbits);
-        unsigned anyE = __ballot_sync(0xFFFFFFFFu, emptybits != 0);
-        if (!anyE) {
-            long long tot = (long long)fb_warp_sum_u64((unsigned long long)Wl);
-            if (ss.add_dyadic_run(tot)) continue;
-        }
-        for (int l = 0; l < 32; ++l) {
-            long long Wl_l = __shfl_sync(0xFFFFFFFFu, Wl, l);
-            uint32_t eb = __shfl_sync(0xFFFFFFFFu, emptybits, l);
-            uint32_t db = __shfl_sync(0xFFFFFFFFu, diffbits, l);
-            if (eb == 0) {
-                if (ss.add_dyadic_run(Wl_l)) continue;
-            }
-            __syncwarp();
-            if (lane == l) {
+        const long long Wl = (long long)fb_masked_sum(w, diffbits);
+        const unsigned E = __ballot_sync(0xFFFFFFFFu, emptybits != 0);
+        // inclusive prefix sums of the per-lane dyadic sums
+        long long pre = Wl;
 #pragma unroll
-                for (int k = 0; k < 16; ++k) wscratch[k] = w[k];
+        for (int o = 1; o < 32; o <<= 1) {
+            long long v = __shfl_up_sync(0xFFFFFFFFu, pre, o);
+            if ((int)lane >= o) pre += v;
+        }
+        int cur = 0;
+        while (cur < 32) {
+            const unsigned rest = E >> cur;
+            const int e = rest ? cur + __ffs(rest) - 1 : 32;  // next lane holding epsilon items
+            if (e > cur) {
+                const long long hi_sum = __shfl_sync(0xFFFFFFFFu, pre, e - 1);
+                const long long lo_sum = cur ? __shfl_sync(0xFFFFFFFFu, pre, cur - 1) : 0;
+                if (!ss.add_dyadic_run(hi_sum - lo_sum)) {
+                    for (int l = cur; l < e; ++l) {
+                        const long long Wl_l = __shfl_sync(0xFFFFFFFFu, Wl, l);
+                        if (ss.add_dyadic_run(Wl_l)) continue;
+                        const uint32_t db = __shfl_sync(0xFFFFFFFFu, diffbits, l);
+                        __syncwarp();
+                        if ((int)lane == l) {
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) wscratch[k] = w[k];
+                        }
+                        __syncwarp();
+                        uint32_t bits = db;
+                        while (bits) {
+                            const int k = __ffs(bits) - 1;
+                            bits &= bits - 1;
+                            ss.add_dyadic((long long)wscratch[k]);
+                        }
+                    }
+                }
             }
-            __syncwarp();
-            uint32_t bits = eb | db;
-            while (bits) {
-                int k = __ffs(bits) - 1;
-                bits &= bits - 1;
-                if ((eb >> k) & 1u)
-                    ss.add_eps(eps, 0);
-                else
-                    ss.add_dyadic((long long)wscratch[k]);
+            if (e == 32) break;
+            const uint32_t eb = __shfl_sync(0xFFFFFFFFu, emptybits, e);
+            const uint32_t db = __shfl_sync(0xFFFFFFFFu, diffbits, e);
+            if (db == 0) {
+                for (int n = __popc(eb); n > 0; --n) ss.add_eps(eps, 0);  // an all-epsilon lane needs no weights
+            } else {
+                __syncwarp();
+                if ((int)lane == e) {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) wscratch[k] = w[k];
+                }
+                __syncwarp();
+                uint32_t bits = eb | db;
+                while (bits) {
+                    const int k = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    if ((eb >> k) & 1u)
+                        ss.add_eps(eps, 0);
+                    else
+                        ss.add_dyadic((long long)wscratch[k]);
+                }
             }
+            cur = e + 1;
         }
     }
     return ss.S;
@@ -180,7 +216,7 @@ __device__ void fb_sweep_body(const SweepArgs &a, const InstDev &in, int ii, uin
             // every term is a multiple of 2^-26: the sum is exact in any order
             diff_f[h] = fb_q26_to_f64(diff_q[h] + (long long)ne_cnt[h] * (long long)(a.eps * FB_Q26));
         } else {
-            diff_f[h] = fb_replay_diff(a.fr, g0, g1, masks + (uint32_t)h * in.ng, ri.lg0, lut_s, a.eps, wscratch);
+            diff_f[h] = fb_replay_diff(a.fr, g0, g1, masks + (uint32_t)h * in.ng, ri.lg0, 0x7FFFFFFF, lut_s, a.eps, wscratch);
         }
     }
     if (lane != 0) return;
