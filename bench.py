@@ -107,6 +107,26 @@ def make_workload(rank):
     return c, prm, lo, hi, desc
 
 
+def c3_roofline(ctx, peak, n_reads=100000, n_snps=50000, ploidy=4, iters=5):
+    """BASELINE.json configs[2]: the 100k x 50k full-span block (5e9 cells, 6.9 GB packed, >> L2), ploidy 4.
+    Times the two bandwidth-bound kernels of one optimize_clustering round: k_sweep (every read x every haplotype)
+    and k_hist (hap_block_from_partition).  achieved = stored cells x 1.375 B / CUDA-event time per launch."""
+    from floria_b200 import default_params
+
+    d = ctx.bench_synth_dense(n_reads, n_snps, ploidy, 3)
+    prm = default_params(epsilon=0.04)
+    sw, hs, cells = ctx.bench_sweep_hist(d, ploidy, d.src, prm, iters)
+    out = {"workload": f"configs[2]: {n_reads} full-span frags x {n_snps} SNPs, ploidy {ploidy}, eps 0.04",
+           "stored_cells": cells, "packed_bytes": d.nbytes, "iters": iters, "bytes_per_cell": BYTES_PER_CELL}
+    for name, t in (("k_sweep", sw), ("k_hist", hs)):
+        ms = float(np.median(t))
+        gbs = cells * BYTES_PER_CELL / 1e9 / (ms / 1e3)
+        out[name] = {"ms_per_launch": ms, "cells_per_s": cells / (ms / 1e3), "achieved_GBps": gbs, "peak_GBps": peak,
+                     "frac": gbs / peak}
+    d.free()
+    return out
+
+
 def cpu_sample(c, prm, lo, hi, threads):
     """bounded sample of the same workload for the CPU arm: the first `threads` blocks (one per worker)."""
     n = int(min(len(lo), max(1, threads)))
@@ -282,6 +302,8 @@ def run_ours(args):
                         "ms_per_step": ms_total2 / K},
                 "roofline": roofline, "cells_per_step": cells_all,
                 "cells_breakdown": {"sweep": res.cells_sweep, "hist": res.cells_hist, "beam": res.cells_beam}}
+        if world == 1 and not args.no_c3:
+            line["roofline_c3"] = c3_roofline(ctx, peak)
         if world == 1 and not args.no_cpu:
             import oracle
 
@@ -312,6 +334,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--no-c3", action="store_true", help="skip the configs[2] sweep/hist roofline leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -94,6 +94,12 @@ def load_library():
                               C.POINTER(FbParams), u8p, f64p, f64p]
     L.fb_update_hap_graph.argtypes = [C.c_void_p, C.POINTER(FbFrags), C.c_uint64, u64p, u64p, u32p, u32p, u32p,
                                       C.POINTER(FbParams), f64p]
+    # measurement helpers (include/floria_b200_bench.h)
+    L.fb_bench_synth_dense.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_double,
+                                       C.c_double, u8p, u8p, u8p, C.POINTER(C.c_void_p)]
+    L.fb_bench_sweep_hist.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, u8p, C.POINTER(FbParams), C.c_uint32,
+                                      C.POINTER(C.c_float), C.POINTER(C.c_float), u64p]
+    L.fb_bench_download_planes.argtypes = [C.c_void_p, C.c_void_p, u64p, u8p, u32p, C.POINTER(C.c_uint16)]
     _lib = L
     return L
 
@@ -183,6 +189,47 @@ class Context:
         out = C.c_void_p()
         self._chk(self.L.fb_frags_upload(self.h, C.byref(fs), C.byref(out)))
         return DeviceFrags(self, out, frags)
+
+    # ---- measurement helpers (include/floria_b200_bench.h) ----
+    def bench_synth_dense(self, n_reads, n_snps, ploidy, config_seed, present=0.98, flip=0.04):
+        """configs[2]-style full-span block generated in HBM; same cells as synth.make_contig(.., full_span=True)."""
+        from . import synth
+
+        seed = synth.SEED_BASE + config_seed
+        truth, nall = synth.make_truth(seed, ploidy, n_snps)
+        rid = np.arange(n_reads, dtype=np.uint64)
+        w = 1.0 / np.arange(1, ploidy + 1)
+        cdf = np.cumsum(w / w.sum())
+        src = np.searchsorted(cdf, synth.rng_u01(seed, 100, rid), side="right").clip(0, ploidy - 1).astype(np.uint8)
+        truth = np.ascontiguousarray(truth, np.uint8)
+        nall8 = np.ascontiguousarray(nall, np.uint8)
+        out = C.c_void_p()
+        self._chk(self.L.fb_bench_synth_dense(self.h, n_reads, n_snps, ploidy, seed, present, flip, ptr(truth, u8p),
+                                              ptr(nall8, u8p), ptr(src, u8p), C.byref(out)))
+        d = DeviceFrags(self, out, None)
+        d.src = src
+        return d
+
+    def bench_sweep_hist(self, dfrags, ploidy, hap, params, iters):
+        hap = np.ascontiguousarray(hap, np.uint8)
+        sw = np.zeros(iters, np.float32)
+        hs = np.zeros(iters, np.float32)
+        cells = C.c_uint64(0)
+        self._chk(self.L.fb_bench_sweep_hist(self.h, dfrags.handle, ploidy, ptr(hap, u8p), C.byref(params), iters,
+                                             sw.ctypes.data_as(C.POINTER(C.c_float)),
+                                             hs.ctypes.data_as(C.POINTER(C.c_float)), C.byref(cells)))
+        return sw, hs, int(cells.value)
+
+    def download_planes(self, dfrags):
+        ng = C.c_uint64(0)
+        self._chk(self.L.fb_bench_download_planes(self.h, dfrags.handle, C.byref(ng), None, None, None))
+        n = int(ng.value)
+        q = np.zeros(n * 16, np.uint8)
+        a = np.zeros(n, np.uint32)
+        p = np.zeros(n, np.uint16)
+        self._chk(self.L.fb_bench_download_planes(self.h, dfrags.handle, C.byref(ng), ptr(q, u8p), ptr(a, u32p),
+                                                  p.ctypes.data_as(C.POINTER(C.c_uint16))))
+        return q.reshape(n, 16), a, p
 
     # ---- batched hot path ----
     def phase_blocks(self, frags, blk_lo, blk_hi, params):

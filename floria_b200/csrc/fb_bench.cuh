@@ -1,0 +1,157 @@
+// fb_bench.cuh — measurement helpers (include/floria_b200_bench.h): device-side synthetic dense block + timed
+// sweep/hist loop.  Not part of the reference-facing boundary.
+#pragma once
+#include "../../include/floria_b200_bench.h"
+#include "fb_engine.cuh"
+
+// counter-based PRNG of floria_b200/synth.py
+__device__ __forceinline__ uint64_t fbs_mix(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ uint64_t fbs_u64(uint64_t seed, uint64_t stream, uint64_t idx) {
+    return fbs_mix(seed + stream * 0xD1B54A32D192ED03ULL + (idx + 1) * 0x9E3779B97F4A7C15ULL);
+}
+__device__ __forceinline__ double fbs_u01(uint64_t seed, uint64_t stream, uint64_t idx) {
+    return (double)(fbs_u64(seed, stream, idx) >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// one thread per (read, group)
+__global__ void k_synth_dense(uint64_t n_reads, uint32_t n_snps, uint32_t ng_per_read, uint64_t seed, double present,
+                              double flip, const uint8_t *__restrict__ truth, const uint8_t *__restrict__ nall,
+                              const uint8_t *__restrict__ src, uint4 *__restrict__ qual, uint32_t *__restrict__ allele,
+                              uint16_t *__restrict__ pres, uint32_t *__restrict__ nnz) {
+    const uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n_reads * ng_per_read) return;
+    const uint64_t r = x / ng_per_read;
+    const uint32_t gl = (uint32_t)(x % ng_per_read);
+    const uint32_t h = src[r];
+    uint32_t qq[4] = {0, 0, 0, 0};
+    uint32_t al = 0, pr = 0;
+    for (uint32_t k = 0; k < 16; ++k) {
+        const uint32_t off = gl * 16 + k;  // position0 == offset inside the (full-span) read
+        if (off >= n_snps) break;
+        const uint64_t key = r * (1ULL << 20) + off;
+        bool keep = fbs_u01(seed, 200, key) < present;
+        keep |= (off == 0) | (off == n_snps - 1);
+        if (!keep) continue;
+        const uint32_t t = truth[(uint64_t)h * n_snps + off];
+        const uint32_t na = nall[off];
+        const bool do_flip = fbs_u01(seed, 201, key) < flip;
+        const uint32_t shift = 1 + (uint32_t)(fbs_u64(seed, 202, key) % (uint64_t)(na - 1));
+        const uint32_t a = do_flip ? (t + shift) % na : t;
+        const uint32_t q = 5 + (uint32_t)(fbs_u64(seed, 203, key) % 36ULL);
+        pr |= 1u << k;
+        al |= ((a & 1u) << k) | (((a >> 1) & 1u) << (16 + k));
+        qq[k >> 2] |= q << (8 * (k & 3));
+    }
+    qual[x] = make_uint4(qq[0], qq[1], qq[2], qq[3]);
+    allele[x] = al;
+    pres[x] = (uint16_t)pr;
+    atomicAdd(&nnz[r], (uint32_t)__popc(pr));
+}
+
+extern "C" {
+
+int fb_bench_synth_dense(fb_ctx *ctx, uint64_t n_reads, uint32_t n_snps, uint32_t ploidy, uint64_t seed, double present,
+                         double flip, const uint8_t *truth, const uint8_t *nall, const uint8_t *src, fb_dfrags **out) {
+    if (!ctx) return FB_ERR_ARG;
+    if (!out || !truth || !nall || !src || n_reads == 0 || n_snps == 0 || n_snps >= (1u << 20))
+        FB_FAIL(FB_ERR_ARG, "bad argument");
+    *out = nullptr;
+    FB_CK(cudaSetDevice(ctx->device));
+    const uint32_t ngr = (n_snps + 15) / 16;
+    const uint64_t ng = n_reads * (uint64_t)ngr;
+    if (ng >= (1ull << 32) - 64) FB_FAIL(FB_ERR_LIMIT, "more than 2^32 groups");
+    fb_dfrags *df = new fb_dfrags();
+    df->ctx = ctx;
+    df->n_reads = n_reads;
+    df->n_groups = ng;
+    df->h_first.assign(n_reads, 1);
+    df->h_last.assign(n_reads, n_snps);
+    df->h_gstart.assign(n_reads, 0);
+    df->h_gptr.resize(n_reads + 1);
+    df->h_prefmax_last.assign(n_reads, n_snps);
+    df->h_nnz.resize(n_reads);
+    for (uint64_t i = 0; i <= n_reads; ++i) df->h_gptr[i] = (uint32_t)(i * ngr);
+    uint8_t *d_truth = nullptr, *d_nall = nullptr, *d_src = nullptr;
+    int rc;
+    if ((rc = fb_upload(ctx, &df->d_first, df->h_first)) || (rc = fb_upload(ctx, &df->d_last, df->h_last)) ||
+        (rc = fb_upload(ctx, &df->d_gstart, df->h_gstart)) || (rc = fb_upload(ctx, &df->d_gptr, df->h_gptr)) ||
+        (rc = fb_dalloc(ctx, &df->d_nnz, n_reads)) || (rc = fb_dalloc(ctx, &df->d_qual, ng + 1)) ||
+        (rc = fb_dalloc(ctx, &df->d_allele, ng + 1)) || (rc = fb_dalloc(ctx, &df->d_present, ng + 2)) ||
+        (rc = fb_upload(ctx, &d_truth, truth, (size_t)ploidy * n_snps)) || (rc = fb_upload(ctx, &d_nall, nall, n_snps)) ||
+        (rc = fb_upload(ctx, &d_src, src, n_reads))) {
+        fb_frags_free(ctx, df);
+        return rc;
+    }
+    cudaMemsetAsync(df->d_nnz, 0, n_reads * 4, ctx->stream);
+    k_synth_dense<<<(unsigned)((ng + 255) / 256), 256, 0, ctx->stream>>>(n_reads, n_snps, ngr, seed, present, flip, d_truth,
+                                                                          d_nall, d_src, df->d_qual, df->d_allele,
+                                                                          df->d_present, df->d_nnz);
+    cudaMemcpyAsync(df->h_nnz.data(), df->d_nnz, n_reads * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+    if (ce == cudaSuccess) ce = cudaGetLastError();
+    fb_cache_free(d_truth);
+    fb_cache_free(d_nall);
+    fb_cache_free(d_src);
+    if (ce != cudaSuccess) {
+        ctx->err = std::string("fb_bench_synth_dense: ") + cudaGetErrorString(ce);
+        fb_frags_free(ctx, df);
+        return FB_ERR_CUDA;
+    }
+    uint64_t nnz = 0;
+    for (uint64_t i = 0; i < n_reads; ++i) nnz += df->h_nnz[i];
+    df->nnz = nnz;
+    df->bytes = ng * 22;
+    *out = df;
+    return FB_OK;
+}
+
+int fb_bench_sweep_hist(fb_ctx *ctx, const fb_dfrags *df, uint32_t ploidy, const uint8_t *hap, const fb_params *prm,
+                        uint32_t iters, float *sweep_ms, float *hist_ms, uint64_t *cells) {
+    if (!ctx) return FB_ERR_ARG;
+    if (!df || !hap || !prm) FB_FAIL(FB_ERR_ARG, "null argument");
+    FB_CK(cudaSetDevice(ctx->device));
+    ctx->ev_used = 0;
+    int rc = fb_check_params(ctx, prm, ploidy);
+    if (rc) return rc;
+    Engine e;
+    e.ctx = ctx;
+    e.df = df;
+    std::vector<uint32_t> reads(df->n_reads);
+    for (uint64_t i = 0; i < df->n_reads; ++i) reads[i] = (uint32_t)i;
+    int b = e.add_block(reads);
+    e.add_instance(b, ploidy);
+    if ((rc = e.finalize_and_upload(prm->epsilon))) return rc;
+    FB_CK(cudaMemcpyAsync(e.d_assign[0], hap, df->n_reads, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = e.launch_sizes(0))) return rc;
+    if ((rc = e.launch_hist(0, 1, 0))) return rc;  // warm-up + the table the sweep reads
+    e.hist_ev.clear();
+    for (uint32_t it = 0; it < iters; ++it) {
+        if ((rc = e.launch_sweep(e.sweep_args(FB_SWEEP_MOVES)))) return rc;
+        if ((rc = e.launch_hist(0, 1, 0))) return rc;
+    }
+    FB_CK(cudaStreamSynchronize(ctx->stream));
+    FB_CK(cudaGetLastError());
+    for (uint32_t it = 0; it < iters; ++it) {
+        cudaEventElapsedTime(&sweep_ms[it], e.sweep_ev[it].first, e.sweep_ev[it].second);
+        cudaEventElapsedTime(&hist_ms[it], e.hist_ev[it].first, e.hist_ev[it].second);
+    }
+    if (cells) *cells = e.blocks[0].nnz;
+    return FB_OK;
+}
+
+int fb_bench_download_planes(fb_ctx *ctx, const fb_dfrags *df, uint64_t *n_groups, uint8_t *qual, uint32_t *allele,
+                             uint16_t *present) {
+    if (!ctx) return FB_ERR_ARG;
+    if (!df) FB_FAIL(FB_ERR_ARG, "null argument");
+    FB_CK(cudaSetDevice(ctx->device));
+    if (n_groups) *n_groups = df->n_groups;
+    if (qual) FB_CK(cudaMemcpy(qual, df->d_qual, df->n_groups * 16, cudaMemcpyDeviceToHost));
+    if (allele) FB_CK(cudaMemcpy(allele, df->d_allele, df->n_groups * 4, cudaMemcpyDeviceToHost));
+    if (present) FB_CK(cudaMemcpy(present, df->d_present, df->n_groups * 2, cudaMemcpyDeviceToHost));
+    return FB_OK;
+}
+}

@@ -1034,3 +1034,5 @@ int fb_update_hap_graph(fb_ctx *ctx, const fb_frags *, uint64_t, const uint64_t 
 }
 
 }  // extern "C"
+
+#include "fb_bench.cuh"

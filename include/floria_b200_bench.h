@@ -1,0 +1,33 @@
+/*
+ * floria_b200_bench.h — measurement helpers of libfloria_b200.so.  NOT part of the reference-facing boundary
+ * (include/floria_b200.h): these exist so bench.py / tests can build the 100k x 50k "roofline" block of
+ * BASELINE.json configs[2] directly in HBM (5e9 cells do not fit a host CSR round trip) and time the
+ * bandwidth-bound kernels on it.
+ */
+#ifndef FLORIA_B200_BENCH_H
+#define FLORIA_B200_BENCH_H
+#include "floria_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Full-span synthetic reads (first = 1, last = n_snps) generated on the device with the counter-based PRNG of
+ * floria_b200/synth.py (make_contig(..., full_span=True, qual_mode="long")): identical cells for identical
+ * (seed, truth, nall, src).  truth: [ploidy*n_snps] alleles, nall: [n_snps] alleles per column (2 or 3),
+ * src: [n_reads] source haplotype of each read. */
+int fb_bench_synth_dense(fb_ctx *, uint64_t n_reads, uint32_t n_snps, uint32_t ploidy, uint64_t seed, double present,
+                         double flip, const uint8_t *truth, const uint8_t *nall, const uint8_t *src, fb_dfrags **out);
+
+/* One block made of ALL reads of `df`, partition `hap`: builds the haplotype table (k_hist), then `iters` times
+ * runs the scoring sweep of opt_iterate (k_sweep, every read x every haplotype) and a histogram rebuild (k_hist),
+ * timing each launch with CUDA events.  cells = stored cells streamed by one launch. */
+int fb_bench_sweep_hist(fb_ctx *, const fb_dfrags *df, uint32_t ploidy, const uint8_t *hap, const fb_params *,
+                        uint32_t iters, float *sweep_ms, float *hist_ms, uint64_t *cells);
+
+/* Debug/test: copy the packed planes of a resident contig back to the host (any pointer may be NULL). */
+int fb_bench_download_planes(fb_ctx *, const fb_dfrags *df, uint64_t *n_groups, uint8_t *qual /*[16*ng]*/,
+                             uint32_t *allele /*[ng]*/, uint16_t *present /*[ng]*/);
+#ifdef __cplusplus
+}
+#endif
+#endif
