@@ -136,7 +136,12 @@ struct Engine {
     std::vector<BlockPlan> blocks;
     std::vector<InstDev> inst;
     std::vector<InstState> st;
-    std::vector<uint64_t> assign_prefix, tile_prefix, hap_prefix, moves_off;
+    std::vector<uint64_t> assign_prefix, tile_prefix, hap_prefix, moves_off, done_off;
+    std::vector<uint32_t> hist_splits;
+    uint64_t tot_done = 0;
+    uint32_t *d_hist_splits = nullptr, *d_done = nullptr;
+    uint64_t *d_done_off = nullptr;
+    bool any_split = false;
     std::vector<uint32_t> moves_cap;
     std::vector<RInfo> rinfo;
     std::vector<RExtra> rextra;
@@ -167,6 +172,9 @@ struct Engine {
         fb_cache_free(d_moves_off);
         fb_cache_free(d_moves_cap);
         fb_cache_free(d_rinfo);
+        fb_cache_free(d_hist_splits);
+        fb_cache_free(d_done_off);
+        fb_cache_free(d_done);
         fb_cache_free(d_rextra);
         for (int b = 0; b < 2; ++b) {
             fb_cache_free(d_assign[b]);
@@ -181,6 +189,9 @@ struct Engine {
         d_assign_prefix = d_tile_prefix = d_hap_prefix = d_moves_off = nullptr;
         d_moves_cap = nullptr;
         d_rinfo = nullptr;
+        d_hist_splits = nullptr;
+        d_done_off = nullptr;
+        d_done = nullptr;
         d_rextra = nullptr;
         for (int b = 0; b < 2; ++b) {
             d_assign[b] = nullptr;
@@ -249,7 +260,13 @@ struct Engine {
         tot_cnt += (uint64_t)ploidy * b.ng * 64;
         tot_mask += (uint64_t)ploidy * b.ng;
         tot_mec += ploidy;
-        tile_counts.push_back((uint64_t)tiles * ploidy);
+        // read splits per (tile, haplotype): enough CTAs to saturate HBM on big blocks, 1 (no atomics) on small ones
+        uint32_t splits = std::min<uint32_t>(16, std::max<uint32_t>(1, in.n_reads / 4096));
+        if (splits > 1) any_split = true;
+        hist_splits.push_back(splits);
+        done_off.push_back(tot_done);
+        tot_done += (uint64_t)tiles * ploidy;
+        tile_counts.push_back((uint64_t)tiles * ploidy * splits);
         uint64_t maxm = (uint64_t)in.n_reads * (ploidy > 1 ? ploidy - 1 : 1);
         uint32_t cap = 1;
         while (cap < maxm) cap <<= 1;
@@ -283,6 +300,9 @@ struct Engine {
         if ((rc = fb_upload(ctx, &d_moves_off, moves_off))) return rc;
         if ((rc = fb_upload(ctx, &d_moves_cap, moves_cap))) return rc;
         if ((rc = fb_upload(ctx, &d_rinfo, rinfo))) return rc;
+        if ((rc = fb_upload(ctx, &d_hist_splits, hist_splits))) return rc;
+        if ((rc = fb_upload(ctx, &d_done_off, done_off))) return rc;
+        if ((rc = fb_dalloc(ctx, &d_done, tot_done))) return rc;
         if ((rc = fb_upload(ctx, &d_rextra, rextra))) return rc;
         for (int b = 0; b < 2; ++b) {
             if ((rc = fb_dalloc(ctx, &d_assign[b], tot_assign))) return rc;
@@ -316,6 +336,9 @@ struct Engine {
         a.st = d_st;
         a.n_inst = n;
         a.tile_prefix = d_tile_prefix;
+        a.splits = d_hist_splits;
+        a.done_off = d_done_off;
+        a.done = d_done;
         a.rinfo = d_rinfo;
         a.assign[0] = d_assign[0];
         a.assign[1] = d_assign[1];
@@ -330,6 +353,11 @@ struct Engine {
         a.only_active = only_active;
         a.assign_cur = assign_cur;
         cudaEvent_t e0 = fb_event(ctx);
+        if (any_split) {
+            cudaMemsetAsync(d_done, 0, std::max<uint64_t>(tot_done, 1) * 4, ctx->stream);
+            k_hist_zero<<<dim3(64, (unsigned)n), 256, 0, ctx->stream>>>(a);
+            ctx->tim.n_launches++;
+        }
         k_hist<<<(unsigned)ctas, FB_HIST_THREADS, 0, ctx->stream>>>(a);
         cudaEvent_t e1 = fb_event(ctx);
         hist_ev.push_back(std::make_pair(e0, e1));

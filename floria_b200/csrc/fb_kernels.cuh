@@ -279,20 +279,31 @@ __global__ void __launch_bounds__(FB_SWEEP_WARPS * 32) k_sweep(SweepArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// K2 hap_histogram.  One CTA per (instance, tile of 1024 positions, haplotype); every thread owns 4 consecutive
-// positions x 4 alleles of exact 64-bit counters (thread-private columns of shared memory: no atomics) and the CTA
-// streams the block's reads assigned to that haplotype.  Reproduces utils_frags.rs:160-184 set_to_seq_dict /
-// hap_block_from_partition; the epilogue derives the is-max planes the sweep consumes (consensus of utils_frags.rs:53-69).
+// K2 hap_histogram.  One CTA per (instance, tile of 1024 positions, haplotype, read split).  Every thread owns 4
+// consecutive positions; all threads of the CTA process the same read at the same time (each its own columns), so the
+// counters live in REGISTERS with static indexing and no atomics: per position total weight T and the sums C1 (allele
+// bit 0 set), C2 (allele bit 1 set), C3 (both), from which n3 = C3, n1 = C1-C3, n2 = C2-C3, n0 = T-C1-C2+C3.  32-bit
+// partial sums are flushed to 64 bit every 28 reads (28 * 2^26 < 2^32).  Reads of the wanted haplotype that overlap the
+// tile are compacted into shared memory 256 at a time and streamed in batches of 4 independent loads.
+// With several read splits per (tile, haplotype) the partial tables are merged with 64-bit global atomics (exact integer
+// adds: deterministic) and the last CTA to finish derives the is-max planes.
+// Reproduces utils_frags.rs:160-184 set_to_seq_dict / hap_block_from_partition; the planes are the consensus test of
+// utils_frags.rs:53-69.
 // ---------------------------------------------------------------------------------------------------------------------
 #define FB_HIST_THREADS 256
 #define FB_HIST_TILE_GROUPS 64  // 1024 positions
+#define FB_HIST_LIST 256
+#define FB_HIST_BATCH 4
 
 struct HistArgs {
     DFragsDev fr;
     const InstDev *inst;
     const InstState *st;
     int n_inst;
-    const uint64_t *tile_prefix;  // [n_inst+1] prefix of tiles(i) * ploidy(i)
+    const uint64_t *tile_prefix;  // [n_inst+1] prefix of tiles(i) * ploidy(i) * splits(i)
+    const uint32_t *splits;       // [n_inst] read splits per (tile, haplotype)
+    const uint64_t *done_off;     // [n_inst] offset into done[] ([tiles][ploidy] counters)
+    uint32_t *done;               // zeroed before the launch
     const RInfo *rinfo;
     const uint8_t *assign[2];
     uint64_t *cnt[2];
@@ -305,70 +316,185 @@ struct HistArgs {
     int assign_cur;   // 1: read the partition from the CURRENT buffer whatever buffer the table is written to
 };
 
+// zero the count tables of the instances that merge with atomics
+__global__ void k_hist_zero(HistArgs a) {
+    const int ii = blockIdx.y;
+    if (a.splits[ii] <= 1) return;
+    if (a.only_active && !a.st[ii].active) return;
+    const InstDev in = a.inst[ii];
+    const int cur = a.st[ii].cur;
+    const int buf = a.which == 0 ? cur : (a.which == 1 ? (cur ^ 1) : a.buf);
+    ulonglong2 *p = reinterpret_cast<ulonglong2 *>(a.cnt[buf] + in.cnt_off);
+    const uint64_t n2 = (uint64_t)in.ploidy * in.ng * 32;  // 64 words per group = 32 ulonglong2
+    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n2; x += (uint64_t)gridDim.x * blockDim.x)
+        p[x] = make_ulonglong2(0ULL, 0ULL);
+}
+
 __global__ void __launch_bounds__(FB_HIST_THREADS) k_hist(HistArgs a) {
-    __shared__ unsigned long long cnt_s[16 * FB_HIST_THREADS];  // [k*4 + allele][thread]
     __shared__ uint32_t lut_s[256];
+    __shared__ uint4 s_list[FB_HIST_LIST];
+    __shared__ int s_n;
+    __shared__ int s_last;
     const int t = threadIdx.x;
     for (int i = t; i < 256; i += FB_HIST_THREADS) lut_s[i] = a.use_phred ? a.lut[i] : (1u << 26);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) cnt_s[i * FB_HIST_THREADS + t] = 0ULL;
+    if (t == 0) s_n = 0;
     const uint64_t cta = blockIdx.x;
     const int ii = fb_upper_seg(a.tile_prefix, a.n_inst, cta);
     const InstDev in = a.inst[ii];
     if (a.only_active && !a.st[ii].active) return;
-    const uint32_t rel = (uint32_t)(cta - a.tile_prefix[ii]);
-    const uint32_t tile = rel / in.ploidy, h = rel % in.ploidy;
+    const uint32_t S = a.splits[ii];
+    uint32_t rel = (uint32_t)(cta - a.tile_prefix[ii]);
+    const uint32_t split = rel % S;
+    rel /= S;
+    const uint32_t h = rel % in.ploidy, tile = rel / in.ploidy;
     const int cur = a.st[ii].cur;
     const int buf = a.which == 0 ? cur : (a.which == 1 ? (cur ^ 1) : a.buf);
     const uint8_t *__restrict__ assign = a.assign[a.assign_cur ? cur : buf] + in.assign_off;
     const RInfo *__restrict__ rinfo = a.rinfo + in.read_off;
-    const uint32_t tg0 = tile * FB_HIST_TILE_GROUPS;       // first block-local group of the tile
-    const uint32_t G = tg0 + (t >> 2);                     // this thread's block-local group
-    const uint32_t sub = t & 3;                            // which 4 cells of the group
-    __syncthreads();
+    const uint32_t tg0 = tile * FB_HIST_TILE_GROUPS;  // first block-local group of the tile
+    const uint32_t G = tg0 + (t >> 2);                // this thread's block-local group
+    const uint32_t sub = t & 3;                       // which 4 cells of the group
+    const uint32_t r_begin = (uint32_t)((uint64_t)in.n_reads * split / S);
+    const uint32_t r_end = (uint32_t)((uint64_t)in.n_reads * (split + 1) / S);
     const uint32_t *__restrict__ qual32 = reinterpret_cast<const uint32_t *>(a.fr.qual);
-    for (uint32_t rl = 0; rl < in.n_reads; ++rl) {
-        const RInfo ri = rinfo[rl];
-        if (ri.lg0 >= tg0 + FB_HIST_TILE_GROUPS) break;  // reads are sorted by first position
-        if (ri.lg1 <= tg0) continue;
-        if (assign[rl] != h) continue;
-        if (G < ri.lg0 || G >= ri.lg1) continue;
-        const uint32_t g = ri.gbase + G;
-        const uint32_t q = qual32[(uint64_t)g * 4 + sub];
-        const uint32_t al = a.fr.allele[g];
-        const uint32_t pr = a.fr.present[g];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t c = sub * 4 + k;
-            if ((pr >> c) & 1u) {
-                const uint32_t w = lut_s[(q >> (8 * k)) & 0xFFu];
-                const uint32_t av = ((al >> c) & 1u) | (((al >> (16 + c)) & 1u) << 1);
-                unsigned long long *p = &cnt_s[(k * 4 + av) * FB_HIST_THREADS + t];
-                *p = (*p + w) | FB_PRESENT;
+    uint32_t t32[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0}, c2[4] = {0, 0, 0, 0}, c3[4] = {0, 0, 0, 0};
+    unsigned long long T[4] = {0, 0, 0, 0}, C1[4] = {0, 0, 0, 0}, C2[4] = {0, 0, 0, 0}, C3[4] = {0, 0, 0, 0};
+    uint32_t zf = 0;  // bit k*4+allele: a zero-weight cell inserted that allele key
+    int since_flush = 0;
+    __syncthreads();
+    for (uint32_t base = r_begin; base < r_end; base += FB_HIST_LIST) {
+        // reads are sorted by first position: once a chunk starts right of the tile, nothing later overlaps it
+        if (rinfo[base].lg0 >= tg0 + FB_HIST_TILE_GROUPS) break;
+        const uint32_t rl = base + t;
+        if (rl < r_end) {
+            const RInfo ri = rinfo[rl];
+            if (assign[rl] == h && ri.lg1 > tg0 && ri.lg0 < tg0 + FB_HIST_TILE_GROUPS) {
+                const int o = atomicAdd(&s_n, 1);  // order is irrelevant: integer adds commute
+                s_list[o] = make_uint4(ri.gbase, ri.lg0, ri.lg1, 0u);
             }
         }
+        __syncthreads();
+        const int n = s_n;
+        for (int e0 = 0; e0 < n; e0 += FB_HIST_BATCH) {
+            uint32_t q[FB_HIST_BATCH], al[FB_HIST_BATCH], pr[FB_HIST_BATCH];
+#pragma unroll
+            for (int b = 0; b < FB_HIST_BATCH; ++b) {
+                q[b] = 0;
+                al[b] = 0;
+                pr[b] = 0;
+                if (e0 + b < n) {
+                    const uint4 en = s_list[e0 + b];
+                    if (G >= en.y && G < en.z) {
+                        const uint32_t g = en.x + G;
+                        q[b] = qual32[(uint64_t)g * 4 + sub];
+                        al[b] = a.fr.allele[g];
+                        pr[b] = a.fr.present[g];
+                    }
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < FB_HIST_BATCH; ++b) {
+                const uint32_t P4 = (pr[b] >> (sub * 4)) & 0xFu;
+                const uint32_t A0 = (al[b] >> (sub * 4)) & P4;
+                const uint32_t A1 = (al[b] >> (16 + sub * 4)) & P4;
+                const uint32_t A3 = A0 & A1;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t w = lut_s[(q[b] >> (8 * k)) & 0xFFu];
+                    if (P4 & (1u << k)) {
+                        t32[k] += w;
+                        if (w == 0) zf |= 1u << (k * 4 + (((A0 >> k) & 1u) | (((A1 >> k) & 1u) << 1)));
+                    }
+                    if (A0 & (1u << k)) c1[k] += w;
+                    if (A1 & (1u << k)) c2[k] += w;
+                    if (A3 & (1u << k)) c3[k] += w;
+                }
+            }
+            since_flush += FB_HIST_BATCH;
+            if (since_flush >= 28) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    T[k] += t32[k];
+                    C1[k] += c1[k];
+                    C2[k] += c2[k];
+                    C3[k] += c3[k];
+                    t32[k] = c1[k] = c2[k] = c3[k] = 0;
+                }
+                since_flush = 0;
+            }
+        }
+        __syncthreads();
+        if (t == 0) s_n = 0;
+        __syncthreads();
     }
-    // epilogue: counts -> global [h][pos][4]; is-max planes -> global [h][group]
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        T[k] += t32[k];
+        C1[k] += c1[k];
+        C2[k] += c2[k];
+        C3[k] += c3[k];
+    }
+    // epilogue
     const bool in_range = G < in.ng;
+    unsigned long long *out = reinterpret_cast<unsigned long long *>(a.cnt[buf] + in.cnt_off) +
+                              (((uint64_t)h * in.ng + G) * 16 + sub * 4) * 4;
+    unsigned long long c4[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        c4[k][3] = C3[k];
+        c4[k][1] = C1[k] - C3[k];
+        c4[k][2] = C2[k] - C3[k];
+        c4[k][0] = T[k] - C1[k] - C2[k] + C3[k];
+    }
+    if (S > 1) {
+        if (in_range) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int av = 0; av < 4; ++av) {
+                    if (c4[k][av]) atomicAdd(out + k * 4 + av, c4[k][av]);
+                    if (zf & (1u << (k * 4 + av))) atomicOr(out + k * 4 + av, FB_PRESENT);
+                }
+        }
+        __threadfence();
+        __syncthreads();
+        if (t == 0) {
+            const uint32_t prev = atomicAdd(a.done + a.done_off[ii] + (uint64_t)tile * in.ploidy + h, 1u);
+            s_last = prev == S - 1;
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        if (in_range) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const ulonglong2 x = __ldcg(reinterpret_cast<const ulonglong2 *>(out + k * 4));
+                const ulonglong2 y = __ldcg(reinterpret_cast<const ulonglong2 *>(out + k * 4) + 1);
+                c4[k][0] = x.x;
+                c4[k][1] = x.y;
+                c4[k][2] = y.x;
+                c4[k][3] = y.y;
+            }
+        }
+        zf = 0;  // presence of zero-weight keys already sits in bit 62
+    }
     uint32_t pl[4] = {0, 0, 0, 0};
     if (in_range) {
-        uint64_t *out = a.cnt[buf] + in.cnt_off + (((uint64_t)h * in.ng + G) * 16 + sub * 4) * 4;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            unsigned long long c4[4];
             unsigned long long mx = 0;
 #pragma unroll
             for (int av = 0; av < 4; ++av) {
-                c4[av] = cnt_s[(k * 4 + av) * FB_HIST_THREADS + t];
-                unsigned long long v = c4[av] & FB_CNT_MASK;
+                unsigned long long v = c4[k][av] & FB_CNT_MASK;
+                if (v > 0 || (zf & (1u << (k * 4 + av)))) c4[k][av] |= FB_PRESENT;
                 mx = v > mx ? v : mx;
             }
-            reinterpret_cast<ulonglong2 *>(out + k * 4)[0] = make_ulonglong2(c4[0], c4[1]);
-            reinterpret_cast<ulonglong2 *>(out + k * 4)[1] = make_ulonglong2(c4[2], c4[3]);
+            reinterpret_cast<ulonglong2 *>(out + k * 4)[0] = make_ulonglong2(c4[k][0], c4[k][1]);
+            reinterpret_cast<ulonglong2 *>(out + k * 4)[1] = make_ulonglong2(c4[k][2], c4[k][3]);
             if (mx > 0) {
 #pragma unroll
                 for (int av = 0; av < 4; ++av)
-                    if ((c4[av] & FB_CNT_MASK) == mx) pl[av] |= 1u << (sub * 4 + k);
+                    if ((c4[k][av] & FB_CNT_MASK) == mx) pl[av] |= 1u << (sub * 4 + k);
             }
         }
     }
