@@ -100,6 +100,29 @@ __device__ __forceinline__ uint32_t fb_masked_sum(const uint32_t (&w)[16], uint3
     return s;
 }
 
+// s + w computed as a multiply-add by an opaque 1 (a kernel parameter), so the add issues on the FMA pipe (IMAD)
+// instead of the ALU pipe that already carries the bit tests: ncu showed the scoring kernels ALU-pipe bound with the
+// FMA pipe idle (profiles/r01_*).
+__device__ __forceinline__ uint32_t fb_add_fma(uint32_t s, uint32_t w, uint32_t one) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(one), "r"(s));
+    return r;
+}
+__device__ __forceinline__ uint32_t fb_masked_sum_fma(const uint32_t (&w)[16], uint32_t bits, uint32_t one) {
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        if (bits & (1u << k)) s = fb_add_fma(s, w[k], one);
+    return s;
+}
+
+// LUT weights of the 16 cells of a group WITHOUT zeroing absent cells (callers mask their bit sets with `present`)
+__device__ __forceinline__ void fb_group_weights_raw(uint4 q, const uint32_t *__restrict__ lut, uint32_t (&w)[16]) {
+    const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) w[k] = lut[__byte_perm(qq[k >> 2], 0, 0x4440 | (k & 3))];
+}
+
 __device__ __forceinline__ unsigned long long fb_warp_sum_u64(unsigned long long v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);

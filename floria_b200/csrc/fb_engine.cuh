@@ -352,6 +352,7 @@ struct Engine {
         a.buf = buf;
         a.only_active = only_active;
         a.assign_cur = assign_cur;
+        a.one = 1u;
         cudaEvent_t e0 = fb_event(ctx);
         if (any_split) {
             cudaMemsetAsync(d_done, 0, std::max<uint64_t>(tot_done, 1) * 4, ctx->stream);
@@ -409,13 +410,22 @@ struct Engine {
         a.eps = eps;
         a.eps_safe = eps_safe;
         a.mode = mode;
+        a.one = 1u;
         a.gain = d_gain;
         return a;
     }
     int launch_sweep(const SweepArgs &a) {
         if (!tot_assign) return FB_OK;
         cudaEvent_t e0 = fb_event(ctx);
-        k_sweep<<<(unsigned)((tot_assign + FB_SWEEP_WARPS - 1) / FB_SWEEP_WARPS), FB_SWEEP_WARPS * 32, 0, ctx->stream>>>(a);
+        uint32_t pmax = 1;
+        for (const InstDev &in : inst) pmax = std::max(pmax, in.ploidy);
+        const unsigned grid = (unsigned)((tot_assign + FB_SWEEP_WARPS - 1) / FB_SWEEP_WARPS);
+        if (pmax <= 2)
+            k_sweep<2><<<grid, FB_SWEEP_WARPS * 32, 0, ctx->stream>>>(a);
+        else if (pmax <= 4)
+            k_sweep<4><<<grid, FB_SWEEP_WARPS * 32, 0, ctx->stream>>>(a);
+        else
+            k_sweep<8><<<grid, FB_SWEEP_WARPS * 32, 0, ctx->stream>>>(a);
         cudaEvent_t e1 = fb_event(ctx);
         sweep_ev.push_back(std::make_pair(e0, e1));
         ctx->tim.n_launches++;

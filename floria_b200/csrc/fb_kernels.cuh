@@ -56,6 +56,7 @@ struct SweepArgs {
     double eps;
     int eps_safe;
     int mode;
+    uint32_t one;  // == 1, opaque to the compiler (see fb_add_fma)
     // MOVES
     double *gain;
     // SCORE (any may be null)
@@ -158,55 +159,102 @@ __device__ double fb_replay_diff(const DFragsDev &fr, uint32_t g0, uint32_t g1, 
     return ss.S;
 }
 
-template <int P>
+template <int P, int MODE>
 __device__ void fb_sweep_body(const SweepArgs &a, const InstDev &in, int ii, uint64_t slot, const RInfo ri,
                               const uint32_t *lut_s, uint32_t *wscratch) {
     const uint32_t lane = fb_lane();
     const int cur = a.st[ii].cur;
     const uint2 *__restrict__ masks = a.masks[cur] + in.mask_off;
     const uint32_t g0 = a.fr.gptr[ri.rid], g1 = a.fr.gptr[ri.rid + 1];
-    unsigned long long total = 0, same[P], emptyw[P];
+    const uint32_t one = a.one;
+    // MOVES needs only `diff` per haplotype (opt_iterate); SCORE also reports `same`
+    unsigned long long acc[P], emptyw[P], total = 0;  // acc = diff (MOVES) or same (SCORE) weight sums
     uint32_t ne_cnt[P];
 #pragma unroll
     for (int h = 0; h < P; ++h) {
-        same[h] = 0;
+        acc[h] = 0;
         emptyw[h] = 0;
         ne_cnt[h] = 0;
     }
-    for (uint32_t g = g0 + lane; g < g1; g += 32) {
-        uint4 q = a.fr.qual[g];
-        uint32_t al = a.fr.allele[g];
-        uint32_t pr = a.fr.present[g];
-        uint32_t w[16];
-        fb_group_weights(q, pr, lut_s, w);
-        uint32_t t = 0;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) t += w[k];
-        total += t;
+    // software pipeline: the next group's loads are in flight while the current one is scored
+    uint32_t g = g0 + lane;
+    uint4 q_n = make_uint4(0, 0, 0, 0);
+    uint32_t al_n = 0, pr_n = 0;
+    if (g < g1) {
+        q_n = a.fr.qual[g];
+        al_n = a.fr.allele[g];
+        pr_n = a.fr.present[g];
+    }
+    for (; g < g1; g += 32) {
+        const uint4 q = q_n;
+        const uint32_t al = al_n, pr = pr_n;
+        if (g + 32 < g1) {
+            q_n = a.fr.qual[g + 32];
+            al_n = a.fr.allele[g + 32];
+            pr_n = a.fr.present[g + 32];
+        }
         const uint32_t lg = ri.lg0 + (g - g0);
+        // bit sets first (cells outer / haplotypes inner below keeps only one weight live: fewer registers, more warps)
+        uint32_t sel[P], ebs[P];
+        uint32_t any_e = 0;
 #pragma unroll
         for (int h = 0; h < P; ++h) {
-            uint2 m = masks[(uint32_t)h * in.ng + lg];
+            const uint2 m = masks[(uint32_t)h * in.ng + lg];
             uint32_t sb, ne;
             fb_group_masks(al, m, sb, ne);
-            same[h] += fb_masked_sum(w, sb);
-            uint32_t eb = pr & ~ne & 0xFFFFu;
-            if (eb) {
-                emptyw[h] += fb_masked_sum(w, eb);
-                ne_cnt[h] += __popc(eb);
+            sel[h] = MODE == FB_SWEEP_SCORE ? (sb & pr) : (pr & ne & ~sb);
+            ebs[h] = pr & ~ne & 0xFFFFu;
+            any_e |= ebs[h];
+            ne_cnt[h] += __popc(ebs[h]);
+        }
+        uint32_t a32[P], e32[P], t32 = 0;
+#pragma unroll
+        for (int h = 0; h < P; ++h) {
+            a32[h] = 0;
+            e32[h] = 0;
+        }
+        const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const uint32_t w = lut_s[__byte_perm(qq[k >> 2], 0, 0x4440 | (k & 3))];
+            if (MODE == FB_SWEEP_SCORE) {
+                if (pr & (1u << k)) t32 = fb_add_fma(t32, w, one);
+            }
+#pragma unroll
+            for (int h = 0; h < P; ++h)
+                if (sel[h] & (1u << k)) a32[h] = fb_add_fma(a32[h], w, one);
+        }
+        if (MODE == FB_SWEEP_SCORE && any_e) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const uint32_t w = lut_s[__byte_perm(qq[k >> 2], 0, 0x4440 | (k & 3))];
+#pragma unroll
+                for (int h = 0; h < P; ++h)
+                    if (ebs[h] & (1u << k)) e32[h] += w;
             }
         }
+        total += t32;
+#pragma unroll
+        for (int h = 0; h < P; ++h) {
+            acc[h] += a32[h];
+            emptyw[h] += e32[h];
+        }
     }
-    total = fb_warp_sum_u64(total);
     double diff_f[P];
     long long same_q[P], diff_q[P];
+    if (MODE == FB_SWEEP_SCORE) total = fb_warp_sum_u64(total);
 #pragma unroll
     for (int h = 0; h < P; ++h) {
-        same[h] = fb_warp_sum_u64(same[h]);
-        emptyw[h] = fb_warp_sum_u64(emptyw[h]);
+        acc[h] = fb_warp_sum_u64(acc[h]);
         ne_cnt[h] = fb_warp_sum_u32(ne_cnt[h]);
-        same_q[h] = (long long)same[h];
-        diff_q[h] = (long long)(total - same[h] - emptyw[h]);
+        if (MODE == FB_SWEEP_SCORE) {
+            emptyw[h] = fb_warp_sum_u64(emptyw[h]);
+            same_q[h] = (long long)acc[h];
+            diff_q[h] = (long long)(total - acc[h] - emptyw[h]);
+        } else {
+            same_q[h] = 0;
+            diff_q[h] = (long long)acc[h];
+        }
     }
 #pragma unroll
     for (int h = 0; h < P; ++h) {
@@ -220,7 +268,7 @@ __device__ void fb_sweep_body(const SweepArgs &a, const InstDev &in, int ii, uin
         }
     }
     if (lane != 0) return;
-    if (a.mode == FB_SWEEP_SCORE) {
+    if (MODE == FB_SWEEP_SCORE) {
 #pragma unroll
         for (int h = 0; h < P; ++h) {
             uint64_t o = slot * P + h;
@@ -236,22 +284,34 @@ __device__ void fb_sweep_body(const SweepArgs &a, const InstDev &in, int ii, uin
         const int i = a.assign[cur][slot];
         double *gout = a.gain + in.gain_off + (uint64_t)r_local * P;
         const bool skip = (i >= P) || a.st[ii].sizes[cur][i] <= 1;  // `if partition[i].len() <= 1 { continue; }`
+        double errors_read = 0.0;
+#pragma unroll
+        for (int h = 0; h < P; ++h)
+            if (h == i) errors_read = diff_f[h];
 #pragma unroll
         for (int j = 0; j < P; ++j) {
-            double g = 0.0;
+            double gn = 0.0;
             if (!skip && j != i) {
-                double errors_read = 0.0;
-#pragma unroll
-                for (int h = 0; h < P; ++h)
-                    if (h == i) errors_read = diff_f[h];
-                double diff_score = errors_read - diff_f[j];
-                if (diff_score > 0.0) g = diff_score;
+                const double diff_score = errors_read - diff_f[j];
+                if (diff_score > 0.0) gn = diff_score;
             }
-            gout[j] = g;
+            gout[j] = gn;
         }
     }
 }
 
+template <int P>
+__device__ __forceinline__ void fb_sweep_dispatch(const SweepArgs &a, const InstDev &in, int ii, uint64_t slot,
+                                                  const RInfo ri, const uint32_t *lut_s, uint32_t *ws) {
+    if (a.mode == FB_SWEEP_SCORE)
+        fb_sweep_body<P, FB_SWEEP_SCORE>(a, in, ii, slot, ri, lut_s, ws);
+    else
+        fb_sweep_body<P, FB_SWEEP_MOVES>(a, in, ii, slot, ri, lut_s, ws);
+}
+
+// PMAX = largest ploidy this instantiation handles: the register budget of a kernel is that of its widest path, so the
+// host launches the narrowest variant that covers the batch (2, 4 or 8).
+template <int PMAX>
 __global__ void __launch_bounds__(FB_SWEEP_WARPS * 32) k_sweep(SweepArgs a) {
     __shared__ uint32_t lut_s[256];
     __shared__ uint32_t wscr[FB_SWEEP_WARPS][16];
@@ -266,14 +326,14 @@ __global__ void __launch_bounds__(FB_SWEEP_WARPS * 32) k_sweep(SweepArgs a) {
     const RInfo ri = a.rinfo[in.read_off + (uint32_t)(slot - in.assign_off)];
     uint32_t *ws = wscr[threadIdx.x >> 5];
     switch (in.ploidy) {
-        case 1: fb_sweep_body<1>(a, in, ii, slot, ri, lut_s, ws); break;
-        case 2: fb_sweep_body<2>(a, in, ii, slot, ri, lut_s, ws); break;
-        case 3: fb_sweep_body<3>(a, in, ii, slot, ri, lut_s, ws); break;
-        case 4: fb_sweep_body<4>(a, in, ii, slot, ri, lut_s, ws); break;
-        case 5: fb_sweep_body<5>(a, in, ii, slot, ri, lut_s, ws); break;
-        case 6: fb_sweep_body<6>(a, in, ii, slot, ri, lut_s, ws); break;
-        case 7: fb_sweep_body<7>(a, in, ii, slot, ri, lut_s, ws); break;
-        case 8: fb_sweep_body<8>(a, in, ii, slot, ri, lut_s, ws); break;
+        case 1: fb_sweep_dispatch<1>(a, in, ii, slot, ri, lut_s, ws); break;
+        case 2: fb_sweep_dispatch<2>(a, in, ii, slot, ri, lut_s, ws); break;
+        case 3: if (PMAX >= 3) fb_sweep_dispatch<(PMAX >= 3 ? 3 : 1)>(a, in, ii, slot, ri, lut_s, ws); break;
+        case 4: if (PMAX >= 4) fb_sweep_dispatch<(PMAX >= 4 ? 4 : 1)>(a, in, ii, slot, ri, lut_s, ws); break;
+        case 5: if (PMAX >= 5) fb_sweep_dispatch<(PMAX >= 5 ? 5 : 1)>(a, in, ii, slot, ri, lut_s, ws); break;
+        case 6: if (PMAX >= 6) fb_sweep_dispatch<(PMAX >= 6 ? 6 : 1)>(a, in, ii, slot, ri, lut_s, ws); break;
+        case 7: if (PMAX >= 7) fb_sweep_dispatch<(PMAX >= 7 ? 7 : 1)>(a, in, ii, slot, ri, lut_s, ws); break;
+        case 8: if (PMAX >= 8) fb_sweep_dispatch<(PMAX >= 8 ? 8 : 1)>(a, in, ii, slot, ri, lut_s, ws); break;
         default: break;
     }
 }
@@ -314,6 +374,7 @@ struct HistArgs {
     int buf;
     int only_active;  // skip instances whose optimize loop has finished
     int assign_cur;   // 1: read the partition from the CURRENT buffer whatever buffer the table is written to
+    uint32_t one;     // == 1, opaque to the compiler (see fb_add_fma)
 };
 
 // zero the count tables of the instances that merge with atomics
@@ -360,6 +421,7 @@ __global__ void __launch_bounds__(FB_HIST_THREADS) k_hist(HistArgs a) {
     uint32_t t32[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0}, c2[4] = {0, 0, 0, 0}, c3[4] = {0, 0, 0, 0};
     unsigned long long T[4] = {0, 0, 0, 0}, C1[4] = {0, 0, 0, 0}, C2[4] = {0, 0, 0, 0}, C3[4] = {0, 0, 0, 0};
     uint32_t zf = 0;  // bit k*4+allele: a zero-weight cell inserted that allele key
+    const uint32_t one = a.one;
     int since_flush = 0;
     __syncthreads();
     for (uint32_t base = r_begin; base < r_end; base += FB_HIST_LIST) {
@@ -397,17 +459,27 @@ __global__ void __launch_bounds__(FB_HIST_THREADS) k_hist(HistArgs a) {
                 const uint32_t P4 = (pr[b] >> (sub * 4)) & 0xFu;
                 const uint32_t A0 = (al[b] >> (sub * 4)) & P4;
                 const uint32_t A1 = (al[b] >> (16 + sub * 4)) & P4;
-                const uint32_t A3 = A0 & A1;
+                uint32_t w[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) w[k] = lut_s[__byte_perm(q[b], 0, 0x4440 | k)];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint32_t w = lut_s[(q[b] >> (8 * k)) & 0xFFu];
-                    if (P4 & (1u << k)) {
-                        t32[k] += w;
-                        if (w == 0) zf |= 1u << (k * 4 + (((A0 >> k) & 1u) | (((A1 >> k) & 1u) << 1)));
+                    if (P4 & (1u << k)) t32[k] = fb_add_fma(t32[k], w[k], one);
+                    if (A0 & (1u << k)) c1[k] = fb_add_fma(c1[k], w[k], one);
+                }
+                if (A1) {  // alleles 2/3 are rare: keep their bookkeeping off the common path
+                    const uint32_t A3 = A0 & A1;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (A1 & (1u << k)) c2[k] += w[k];
+                        if (A3 & (1u << k)) c3[k] += w[k];
                     }
-                    if (A0 & (1u << k)) c1[k] += w;
-                    if (A1 & (1u << k)) c2[k] += w;
-                    if (A3 & (1u << k)) c3[k] += w;
+                }
+                if (P4 && (w[0] == 0 || w[1] == 0 || w[2] == 0 || w[3] == 0)) {  // zero-weight keys (q = 0)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if ((P4 & (1u << k)) && w[k] == 0)
+                            zf |= 1u << (k * 4 + (((A0 >> k) & 1u) | (((A1 >> k) & 1u) << 1)));
                 }
             }
             since_flush += FB_HIST_BATCH;
