@@ -39,6 +39,7 @@ struct InstDev {
     uint32_t read_off;                    // into blk_reads / blk_rinfo
     uint32_t mec_off;                     // into mec arrays: [ploidy] pairs
     uint32_t _pad;
+    uint32_t flt_lo, flt_hi;              // block-local position0 range counted by k_hist (HapNode::new endpoints)
     uint64_t assign_off;  // into assign_cur/new; prefix over instances of n_reads
     uint64_t gain_off;    // into gain slots [n_reads][ploidy]
     uint64_t cnt_off;     // into count buffers, words: [ploidy][ng*16][4]

@@ -248,6 +248,8 @@ struct Engine {
         in.ag0 = b.ag0;
         in.read_off = b.read_off;
         in.mec_off = (uint32_t)tot_mec;
+        in.flt_lo = 0;
+        in.flt_hi = 0xFFFFFFFFu;
         in.assign_off = tot_assign;
         in.gain_off = tot_gain;
         in.cnt_off = tot_cnt;

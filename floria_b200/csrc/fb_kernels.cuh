@@ -422,6 +422,15 @@ __global__ void __launch_bounds__(FB_HIST_THREADS) k_hist(HistArgs a) {
     unsigned long long T[4] = {0, 0, 0, 0}, C1[4] = {0, 0, 0, 0}, C2[4] = {0, 0, 0, 0}, C3[4] = {0, 0, 0, 0};
     uint32_t zf = 0;  // bit k*4+allele: a zero-weight cell inserted that allele key
     const uint32_t one = a.one;
+    // optional position filter (types_structs.rs:173: HapNode::new keeps positions inside snp_endpoints only)
+    uint32_t flt4 = 0xFu;
+    if (in.flt_lo != 0 || in.flt_hi != 0xFFFFFFFFu) {
+        flt4 = 0;
+        for (uint32_t k = 0; k < 4; ++k) {
+            const uint32_t pos = G * 16 + sub * 4 + k;
+            if (pos >= in.flt_lo && pos <= in.flt_hi) flt4 |= 1u << k;
+        }
+    }
     int since_flush = 0;
     __syncthreads();
     for (uint32_t base = r_begin; base < r_end; base += FB_HIST_LIST) {
@@ -456,7 +465,7 @@ __global__ void __launch_bounds__(FB_HIST_THREADS) k_hist(HistArgs a) {
             }
 #pragma unroll
             for (int b = 0; b < FB_HIST_BATCH; ++b) {
-                const uint32_t P4 = (pr[b] >> (sub * 4)) & 0xFu;
+                const uint32_t P4 = (pr[b] >> (sub * 4)) & flt4;
                 const uint32_t A0 = (al[b] >> (sub * 4)) & P4;
                 const uint32_t A1 = (al[b] >> (16 + sub * 4)) & P4;
                 uint32_t w[4];

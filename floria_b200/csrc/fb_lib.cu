@@ -7,6 +7,7 @@
 #include "fb_engine.cuh"
 #include "fb_beam_host.cuh"
 #include "fb_final.cuh"
+#include "fb_graph.cuh"
 
 // ======================================================================================================================
 // context
@@ -1027,10 +1028,124 @@ int fb_get_hapq(fb_ctx *ctx, const fb_frags *fr, uint64_t n_parts, const uint64_
     return FB_OK;
 }
 
-int fb_update_hap_graph(fb_ctx *ctx, const fb_frags *, uint64_t, const uint64_t *, const uint64_t *, const uint32_t *,
-                        const uint32_t *, const uint32_t *, const fb_params *, double *) {
+int fb_update_hap_graph(fb_ctx *ctx, const fb_frags *fr, uint64_t n_cols, const uint64_t *col_ptr,
+                        const uint64_t *node_ptr, const uint32_t *node_reads, const uint32_t *node_lo,
+                        const uint32_t *node_hi, const fb_params *prm, double *out_weights) {
     if (!ctx) return FB_ERR_ARG;
-    FB_FAIL(FB_ERR_ARG, "fb_update_hap_graph: not implemented yet");
+    if (!fr || !col_ptr || !node_ptr || !node_lo || !node_hi || !out_weights) FB_FAIL(FB_ERR_ARG, "null argument");
+    FB_CK(cudaSetDevice(ctx->device));
+    ctx->ev_used = 0;
+    int rc = fb_check_params(ctx, prm, 1);
+    if (rc) return rc;
+    const uint64_t n_nodes = col_ptr[n_cols];
+    Single s;
+    s.ctx = ctx;
+    if ((rc = fb_frags_upload(ctx, fr, &s.df))) return rc;
+    s.own_df = true;
+    Engine &e = s.eng;
+    e.ctx = ctx;
+    e.df = s.df;
+    std::vector<std::vector<uint32_t>> nodes;
+    if ((rc = fb_parts_engine(ctx, e, s.df, n_nodes, node_ptr, node_reads, nodes))) return rc;
+    // HapNode::new keeps only positions inside snp_endpoints (types_structs.rs:173)
+    for (uint64_t v = 0; v < n_nodes; ++v) {
+        InstDev &in = e.inst[v];
+        const long long base0 = (long long)in.ag0 * 16;  // position0 of table row 0
+        long long lo = (long long)node_lo[v] - 1 - base0, hi = (long long)node_hi[v] - 1 - base0;
+        if (hi < 0 || lo > (long long)in.ng * 16) {  // nothing inside: an empty filter range
+            in.flt_lo = 1;
+            in.flt_hi = 0;
+        } else {
+            in.flt_lo = (uint32_t)std::max<long long>(lo, 0);
+            in.flt_hi = (uint32_t)std::min<long long>(hi, 0xFFFFFFFELL);
+        }
+    }
+    if ((rc = e.finalize_and_upload(prm->epsilon))) return rc;
+    std::vector<uint64_t> out_off(n_nodes, 0), gprefix(n_nodes + 1, 0);
+    std::vector<uint32_t> next_first(n_nodes, 0xFFFFFFFFu), next_count(n_nodes, 0), item_node, item_read;
+    uint64_t tot_out = 0;
+    for (uint64_t i = 0; i + 1 < n_cols; ++i)
+        for (uint64_t v = col_ptr[i]; v < col_ptr[i + 1]; ++v) {
+            next_first[v] = (uint32_t)col_ptr[i + 1];
+            next_count[v] = (uint32_t)(col_ptr[i + 2] - col_ptr[i + 1]);
+            out_off[v] = tot_out;
+            tot_out += next_count[v];
+            for (uint32_t r : nodes[v]) {
+                item_node.push_back((uint32_t)v);
+                item_read.push_back(r);
+            }
+        }
+    for (uint64_t v = 0; v < n_nodes; ++v) gprefix[v + 1] = gprefix[v] + e.inst[v].ng;
+    // sorted, de-duplicated node read lists for the membership test
+    std::vector<uint64_t> nptr(n_nodes + 1, 0);
+    std::vector<uint32_t> nreads;
+    for (uint64_t v = 0; v < n_nodes; ++v) {
+        nreads.insert(nreads.end(), nodes[v].begin(), nodes[v].end());
+        nptr[v + 1] = nreads.size();
+    }
+    for (uint64_t k = 0; k < tot_out; ++k) out_weights[k] = 0.0;
+    if (n_nodes == 0 || item_node.empty() || tot_out == 0) return FB_OK;
+    if ((rc = e.launch_hist(2, 1, 0, 0))) return rc;  // phred-weighted hap_map of every node -> buffer 0
+    uint64_t *d_gprefix = nullptr, *d_nptr = nullptr, *d_out_off = nullptr;
+    uint32_t *d_next_first = nullptr, *d_next_count = nullptr, *d_item_node = nullptr, *d_item_read = nullptr,
+             *d_nreads = nullptr;
+    unsigned int *d_out = nullptr;
+    uint4 *d_planes = nullptr;
+    auto cleanup = [&]() {
+        fb_cache_free(d_gprefix);
+        fb_cache_free(d_nptr);
+        fb_cache_free(d_out_off);
+        fb_cache_free(d_next_first);
+        fb_cache_free(d_next_count);
+        fb_cache_free(d_item_node);
+        fb_cache_free(d_item_read);
+        fb_cache_free(d_nreads);
+        fb_cache_free(d_out);
+        fb_cache_free(d_planes);
+    };
+    if ((rc = fb_upload(ctx, &d_gprefix, gprefix)) || (rc = fb_upload(ctx, &d_nptr, nptr)) ||
+        (rc = fb_upload(ctx, &d_out_off, out_off)) || (rc = fb_upload(ctx, &d_next_first, next_first)) ||
+        (rc = fb_upload(ctx, &d_next_count, next_count)) || (rc = fb_upload(ctx, &d_item_node, item_node)) ||
+        (rc = fb_upload(ctx, &d_item_read, item_read)) || (rc = fb_upload(ctx, &d_nreads, nreads)) ||
+        (rc = fb_dalloc(ctx, &d_out, tot_out)) || (rc = fb_dalloc(ctx, &d_planes, gprefix[n_nodes]))) {
+        cleanup();
+        return rc;
+    }
+    cudaMemsetAsync(d_out, 0, tot_out * 4, ctx->stream);
+    if (gprefix[n_nodes]) {
+        k_planes_a4<<<(unsigned)((gprefix[n_nodes] + 127) / 128), 128, 0, ctx->stream>>>(e.d_inst, (int)n_nodes, d_gprefix,
+                                                                                       e.d_cnt[0], d_planes);
+        ctx->tim.n_launches++;
+    }
+    EdgeArgs a;
+    a.fr = s.df->dev();
+    a.inst = e.d_inst;
+    a.group_prefix = d_gprefix;
+    a.planes = d_planes;
+    a.lut = ctx->d_lut;
+    a.n_items = item_node.size();
+    a.item_node = d_item_node;
+    a.item_read = d_item_read;
+    a.next_first = d_next_first;
+    a.next_count = d_next_count;
+    a.node_ptr = d_nptr;
+    a.node_reads = d_nreads;
+    a.out_off = d_out_off;
+    a.out = d_out;
+    k_edge_score<<<(unsigned)((a.n_items + 7) / 8), 256, 0, ctx->stream>>>(a);
+    ctx->tim.n_launches++;
+    std::vector<unsigned int> h_out(tot_out);
+    cudaMemcpyAsync(h_out.data(), d_out, tot_out * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+    if (ce == cudaSuccess) ce = cudaGetLastError();
+    cleanup();
+    if (ce != cudaSuccess) {
+        ctx->err = std::string("fb_update_hap_graph: ") + cudaGetErrorString(ce);
+        return FB_ERR_CUDA;
+    }
+    for (uint64_t k = 0; k < tot_out; ++k) out_weights[k] = (double)h_out[k];
+    e.collect_timings();
+    return FB_OK;
 }
 
 }  // extern "C"
