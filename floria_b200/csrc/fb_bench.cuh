@@ -18,7 +18,8 @@ __device__ __forceinline__ double fbs_u01(uint64_t seed, uint64_t stream, uint64
 }
 
 // one thread per (read, group)
-__global__ void k_synth_dense(uint64_t n_reads, uint32_t n_snps, uint32_t ng_per_read, uint64_t seed, double present,
+__global__ void k_synth_dense(uint64_t n_reads, uint32_t n_snps, uint32_t ng_per_read, uint32_t stride, uint64_t seed,
+                              double present,
                               double flip, const uint8_t *__restrict__ truth, const uint8_t *__restrict__ nall,
                               const uint8_t *__restrict__ src, uint4 *__restrict__ qual, uint32_t *__restrict__ allele,
                               uint16_t *__restrict__ pres, uint32_t *__restrict__ nnz) {
@@ -46,9 +47,10 @@ __global__ void k_synth_dense(uint64_t n_reads, uint32_t n_snps, uint32_t ng_per
         al |= ((a & 1u) << k) | (((a >> 1) & 1u) << (16 + k));
         qq[k >> 2] |= q << (8 * (k & 3));
     }
-    qual[x] = make_uint4(qq[0], qq[1], qq[2], qq[3]);
-    allele[x] = al;
-    pres[x] = (uint16_t)pr;
+    const uint64_t go = r * stride + gl;
+    qual[go] = make_uint4(qq[0], qq[1], qq[2], qq[3]);
+    allele[go] = al;
+    pres[go] = (uint16_t)pr;
     atomicAdd(&nnz[r], (uint32_t)__popc(pr));
 }
 
@@ -62,7 +64,8 @@ int fb_bench_synth_dense(fb_ctx *ctx, uint64_t n_reads, uint32_t n_snps, uint32_
     *out = nullptr;
     FB_CK(cudaSetDevice(ctx->device));
     const uint32_t ngr = (n_snps + 15) / 16;
-    const uint64_t ng = n_reads * (uint64_t)ngr;
+    const uint32_t stride = (ngr + 7) & ~7u;  // reads start on 8-group boundaries (16-byte aligned planes)
+    const uint64_t ng = n_reads * (uint64_t)stride;
     if (ng >= (1ull << 32) - 64) FB_FAIL(FB_ERR_LIMIT, "more than 2^32 groups");
     fb_dfrags *df = new fb_dfrags();
     df->ctx = ctx;
@@ -74,12 +77,13 @@ int fb_bench_synth_dense(fb_ctx *ctx, uint64_t n_reads, uint32_t n_snps, uint32_
     df->h_gptr.resize(n_reads + 1);
     df->h_prefmax_last.assign(n_reads, n_snps);
     df->h_nnz.resize(n_reads);
-    for (uint64_t i = 0; i <= n_reads; ++i) df->h_gptr[i] = (uint32_t)(i * ngr);
+    for (uint64_t i = 0; i <= n_reads; ++i) df->h_gptr[i] = (uint32_t)(i * stride);
+    df->h_gnum.assign(n_reads, ngr);
     uint8_t *d_truth = nullptr, *d_nall = nullptr, *d_src = nullptr;
     int rc;
     if ((rc = fb_upload(ctx, &df->d_first, df->h_first)) || (rc = fb_upload(ctx, &df->d_last, df->h_last)) ||
         (rc = fb_upload(ctx, &df->d_gstart, df->h_gstart)) || (rc = fb_upload(ctx, &df->d_gptr, df->h_gptr)) ||
-        (rc = fb_dalloc(ctx, &df->d_nnz, n_reads)) || (rc = fb_dalloc(ctx, &df->d_qual, ng + 1)) ||
+        (rc = fb_upload(ctx, &df->d_gnum, df->h_gnum)) || (rc = fb_dalloc(ctx, &df->d_nnz, n_reads)) || (rc = fb_dalloc(ctx, &df->d_qual, ng + 1)) ||
         (rc = fb_dalloc(ctx, &df->d_allele, ng + 1)) || (rc = fb_dalloc(ctx, &df->d_present, ng + 2)) ||
         (rc = fb_upload(ctx, &d_truth, truth, (size_t)ploidy * n_snps)) || (rc = fb_upload(ctx, &d_nall, nall, n_snps)) ||
         (rc = fb_upload(ctx, &d_src, src, n_reads))) {
@@ -87,7 +91,10 @@ int fb_bench_synth_dense(fb_ctx *ctx, uint64_t n_reads, uint32_t n_snps, uint32_
         return rc;
     }
     cudaMemsetAsync(df->d_nnz, 0, n_reads * 4, ctx->stream);
-    k_synth_dense<<<(unsigned)((ng + 255) / 256), 256, 0, ctx->stream>>>(n_reads, n_snps, ngr, seed, present, flip, d_truth,
+    cudaMemsetAsync(df->d_qual, 0, (ng + 1) * sizeof(uint4), ctx->stream);
+    cudaMemsetAsync(df->d_allele, 0, (ng + 1) * sizeof(uint32_t), ctx->stream);
+    cudaMemsetAsync(df->d_present, 0, (ng + 2) * sizeof(uint16_t), ctx->stream);
+    k_synth_dense<<<(unsigned)((n_reads * (uint64_t)ngr + 255) / 256), 256, 0, ctx->stream>>>(n_reads, n_snps, ngr, stride, seed, present, flip, d_truth,
                                                                           d_nall, d_src, df->d_qual, df->d_allele,
                                                                           df->d_present, df->d_nnz);
     cudaMemcpyAsync(df->h_nnz.data(), df->d_nnz, n_reads * 4, cudaMemcpyDeviceToHost, ctx->stream);

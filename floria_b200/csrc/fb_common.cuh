@@ -7,7 +7,9 @@
 //     qual    uint4    16 x 8-bit phred bytes (cell c in byte c)
 //     allele  uint32   2-bit alleles, planar: bit c = allele bit 0 of cell c, bit 16+c = allele bit 1
 //     present uint16   bit c = the read has a cell at that position
-//   gptr[r]..gptr[r+1] are the groups of read r; gstart[r] is the absolute index of its first group.
+//   gptr[r] is the first group of read r (aligned to 8 groups so that every plane of a read starts on a 16-byte
+//   boundary: the 1-D TMA bulk copies of the sweep need that), gnum[r] its number of groups, gstart[r] the absolute
+//   index of its first group.
 //
 // Haplotype tables (replace Haplotype = FxHashMap<pos, FxHashMap<allele, f64>>, types_structs.rs:15):
 //   counts  uint64 [ploidy][n_pos][4]   weight sums in units of 2^-26 (exact), bit 62 = allele key present
@@ -26,7 +28,7 @@
 
 struct DFragsDev {
     uint64_t n_reads;
-    const uint32_t *first, *last, *nnz, *gstart, *gptr;
+    const uint32_t *first, *last, *nnz, *gstart, *gptr, *gnum;
     const uint4 *qual;
     const uint32_t *allele;
     const uint16_t *present;
@@ -70,6 +72,35 @@ struct InstState {
 };
 
 __device__ __forceinline__ uint32_t fb_lane() { return threadIdx.x & 31; }
+
+// ---- 1-D TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers --------------------------------------------------
+__device__ __forceinline__ uint32_t fb_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fb_mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fb_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fb_mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fb_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fb_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     fb_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(fb_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fb_mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(fb_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
 
 // isSame / nonEmpty bit words of one group for one haplotype (16 low bits significant)
 __device__ __forceinline__ void fb_group_masks(uint32_t al, uint2 m, uint32_t &same, uint32_t &nonempty) {

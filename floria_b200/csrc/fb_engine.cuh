@@ -4,6 +4,7 @@
 #pragma once
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -34,11 +35,12 @@ struct fb_ctx {
 struct fb_dfrags {
     fb_ctx *ctx = nullptr;
     uint64_t n_reads = 0, nnz = 0, n_groups = 0, bytes = 0;
-    uint32_t *d_first = nullptr, *d_last = nullptr, *d_nnz = nullptr, *d_gstart = nullptr, *d_gptr = nullptr;
+    uint32_t *d_first = nullptr, *d_last = nullptr, *d_nnz = nullptr, *d_gstart = nullptr, *d_gptr = nullptr,
+             *d_gnum = nullptr;
     uint4 *d_qual = nullptr;
     uint32_t *d_allele = nullptr;
     uint16_t *d_present = nullptr;
-    std::vector<uint32_t> h_first, h_last, h_nnz, h_gstart, h_gptr, h_prefmax_last;
+    std::vector<uint32_t> h_first, h_last, h_nnz, h_gstart, h_gptr, h_gnum, h_prefmax_last;
     DFragsDev dev() const {
         DFragsDev d;
         d.n_reads = n_reads;
@@ -47,6 +49,7 @@ struct fb_dfrags {
         d.nnz = d_nnz;
         d.gstart = d_gstart;
         d.gptr = d_gptr;
+        d.gnum = d_gnum;
         d.qual = d_qual;
         d.allele = d_allele;
         d.present = d_present;
@@ -210,7 +213,7 @@ struct Engine {
         uint32_t gmin = 0xFFFFFFFFu, gmax = 0;
         for (uint32_t r : reads) {
             uint32_t g0 = df->h_gstart[r];
-            uint32_t g1 = g0 + (df->h_gptr[r + 1] - df->h_gptr[r]);
+            uint32_t g1 = g0 + df->h_gnum[r];
             gmin = std::min(gmin, g0);
             gmax = std::max(gmax, g1);
             b.nnz += df->h_nnz[r];
@@ -226,7 +229,7 @@ struct Engine {
             RInfo ri;
             ri.rid = r;
             ri.lg0 = df->h_gstart[r] - gmin;
-            ri.lg1 = ri.lg0 + (df->h_gptr[r + 1] - df->h_gptr[r]);
+            ri.lg1 = ri.lg0 + df->h_gnum[r];
             ri.gbase = df->h_gptr[r] - ri.lg0;
             rinfo.push_back(ri);
             RExtra rx;
@@ -422,12 +425,25 @@ struct Engine {
         uint32_t pmax = 1;
         for (const InstDev &in : inst) pmax = std::max(pmax, in.ploidy);
         const unsigned grid = (unsigned)((tot_assign + FB_SWEEP_WARPS - 1) / FB_SWEEP_WARPS);
-        if (pmax <= 2)
-            k_sweep<2><<<grid, FB_SWEEP_WARPS * 32, 0, ctx->stream>>>(a);
-        else if (pmax <= 4)
-            k_sweep<4><<<grid, FB_SWEEP_WARPS * 32, 0, ctx->stream>>>(a);
-        else
-            k_sweep<8><<<grid, FB_SWEEP_WARPS * 32, 0, ctx->stream>>>(a);
+        // FB_SWEEP_TMA=1 selects the cp.async.bulk (1-D TMA) staged variant.  Measured on configs[2] (profiles/): the sweep
+        // is instruction-issue bound, so the staging does not pay (p=4: 5.0 vs 4.7 ms, p=2: 3.0 vs 2.5 ms); default off.
+        static const bool use_tma = getenv("FB_SWEEP_TMA") && atoi(getenv("FB_SWEEP_TMA")) != 0;
+        const unsigned blk = FB_SWEEP_WARPS * 32;
+        if (use_tma) {
+            if (pmax <= 2)
+                k_sweep<2, true><<<grid, blk, 0, ctx->stream>>>(a);
+            else if (pmax <= 4)
+                k_sweep<4, true><<<grid, blk, 0, ctx->stream>>>(a);
+            else
+                k_sweep<8, true><<<grid, blk, 0, ctx->stream>>>(a);
+        } else {
+            if (pmax <= 2)
+                k_sweep<2, false><<<grid, blk, 0, ctx->stream>>>(a);
+            else if (pmax <= 4)
+                k_sweep<4, false><<<grid, blk, 0, ctx->stream>>>(a);
+            else
+                k_sweep<8, false><<<grid, blk, 0, ctx->stream>>>(a);
+        }
         cudaEvent_t e1 = fb_event(ctx);
         sweep_ev.push_back(std::make_pair(e0, e1));
         ctx->tim.n_launches++;

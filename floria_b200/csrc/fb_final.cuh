@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(FB_FINAL_THREADS) k_final_assign(FinalArgs a) 
         const uint32_t rid = a.read_ids[x];
         const uint64_t c0 = a.cand_ptr[x], c1 = a.cand_ptr[x + 1];
         const uint32_t nc = (uint32_t)(c1 - c0);
-        const uint32_t g0 = a.fr.gptr[rid], g1 = a.fr.gptr[rid + 1];
+        const uint32_t g0 = a.fr.gptr[rid], g1 = g0 + a.fr.gnum[rid];
         const uint32_t gs = a.fr.gstart[rid];
         uint32_t best = a.cand[c0];
         if (nc > 1) {

@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256) k_edge_score(EdgeArgs a) {
     const uint32_t v1 = a.item_node[item], rid = a.item_read[item];
     const uint32_t b0 = a.next_first[v1], nb = a.next_count[v1];
     if (b0 == 0xFFFFFFFFu || nb == 0) return;
-    const uint32_t g0 = a.fr.gptr[rid], g1 = a.fr.gptr[rid + 1], gs = a.fr.gstart[rid];
+    const uint32_t g0 = a.fr.gptr[rid], g1 = g0 + a.fr.gnum[rid], gs = a.fr.gstart[rid];
     unsigned long long best = ~0ULL, second = ~0ULL;  // two smallest rounded diffs (read_to_hap_sim.sort(), :43-45)
     uint32_t hap_id_in = 0xFFFFFFFFu;
     for (uint32_t l = 0; l < nb; ++l) {

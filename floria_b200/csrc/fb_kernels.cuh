@@ -42,6 +42,15 @@ __global__ void k_pack(uint64_t nnz, uint64_t n_reads, const uint64_t *__restric
 #define FB_SWEEP_MOVES 0
 #define FB_SWEEP_SCORE 1
 #define FB_SWEEP_WARPS 8
+#define FB_SWEEP_STAGES 4
+
+// one pipeline stage of a warp: 32 groups of a read, staged by three 1-D TMA bulk copies
+struct __align__(128) SweepStage {
+    uint4 qual[32];       // 512 B
+    uint32_t allele[32];  // 128 B
+    uint16_t present[32]; //  64 B
+    uint8_t _pad[64];
+};
 
 struct SweepArgs {
     DFragsDev fr;
@@ -159,13 +168,13 @@ __device__ double fb_replay_diff(const DFragsDev &fr, uint32_t g0, uint32_t g1, 
     return ss.S;
 }
 
-template <int P, int MODE>
+template <int P, int MODE, bool TMA>
 __device__ void fb_sweep_body(const SweepArgs &a, const InstDev &in, int ii, uint64_t slot, const RInfo ri,
-                              const uint32_t *lut_s, uint32_t *wscratch) {
+                              const uint32_t *lut_s, uint32_t *wscratch, SweepStage *stg, uint64_t *bars) {
     const uint32_t lane = fb_lane();
     const int cur = a.st[ii].cur;
     const uint2 *__restrict__ masks = a.masks[cur] + in.mask_off;
-    const uint32_t g0 = a.fr.gptr[ri.rid], g1 = a.fr.gptr[ri.rid + 1];
+    const uint32_t g0 = a.fr.gptr[ri.rid], g1 = g0 + (ri.lg1 - ri.lg0);
     const uint32_t one = a.one;
     // MOVES needs only `diff` per haplotype (opt_iterate); SCORE also reports `same`
     unsigned long long acc[P], emptyw[P], total = 0;  // acc = diff (MOVES) or same (SCORE) weight sums
@@ -176,68 +185,104 @@ __device__ void fb_sweep_body(const SweepArgs &a, const InstDev &in, int ii, uin
         emptyw[h] = 0;
         ne_cnt[h] = 0;
     }
-    // software pipeline: the next group's loads are in flight while the current one is scored
-    uint32_t g = g0 + lane;
-    uint4 q_n = make_uint4(0, 0, 0, 0);
-    uint32_t al_n = 0, pr_n = 0;
-    if (g < g1) {
-        q_n = a.fr.qual[g];
-        al_n = a.fr.allele[g];
-        pr_n = a.fr.present[g];
-    }
-    for (; g < g1; g += 32) {
-        const uint4 q = q_n;
-        const uint32_t al = al_n, pr = pr_n;
-        if (g + 32 < g1) {
-            q_n = a.fr.qual[g + 32];
-            al_n = a.fr.allele[g + 32];
-            pr_n = a.fr.present[g + 32];
-        }
-        const uint32_t lg = ri.lg0 + (g - g0);
-        // bit sets first (cells outer / haplotypes inner below keeps only one weight live: fewer registers, more warps)
-        uint32_t sel[P], ebs[P];
-        uint32_t any_e = 0;
+    // scoring of one 16-cell group against every haplotype
+    auto score_group = [&](const uint4 q, const uint32_t al, const uint32_t pr, const uint32_t g) {
+            const uint32_t lg = ri.lg0 + (g - g0);
+            // bit sets first (cells outer / haplotypes inner below keeps only one weight live: fewer registers, more warps)
+            uint32_t sel[P], ebs[P];
+            uint32_t any_e = 0;
 #pragma unroll
-        for (int h = 0; h < P; ++h) {
-            const uint2 m = masks[(uint32_t)h * in.ng + lg];
-            uint32_t sb, ne;
-            fb_group_masks(al, m, sb, ne);
-            sel[h] = MODE == FB_SWEEP_SCORE ? (sb & pr) : (pr & ne & ~sb);
-            ebs[h] = pr & ~ne & 0xFFFFu;
-            any_e |= ebs[h];
-            ne_cnt[h] += __popc(ebs[h]);
-        }
-        uint32_t a32[P], e32[P], t32 = 0;
-#pragma unroll
-        for (int h = 0; h < P; ++h) {
-            a32[h] = 0;
-            e32[h] = 0;
-        }
-        const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const uint32_t w = lut_s[__byte_perm(qq[k >> 2], 0, 0x4440 | (k & 3))];
-            if (MODE == FB_SWEEP_SCORE) {
-                if (pr & (1u << k)) t32 = fb_add_fma(t32, w, one);
+            for (int h = 0; h < P; ++h) {
+                const uint2 m = masks[(uint32_t)h * in.ng + lg];
+                uint32_t sb, ne;
+                fb_group_masks(al, m, sb, ne);
+                sel[h] = MODE == FB_SWEEP_SCORE ? (sb & pr) : (pr & ne & ~sb);
+                ebs[h] = pr & ~ne & 0xFFFFu;
+                any_e |= ebs[h];
+                ne_cnt[h] += __popc(ebs[h]);
             }
+            uint32_t a32[P], e32[P], t32 = 0;
 #pragma unroll
-            for (int h = 0; h < P; ++h)
-                if (sel[h] & (1u << k)) a32[h] = fb_add_fma(a32[h], w, one);
-        }
-        if (MODE == FB_SWEEP_SCORE && any_e) {
+            for (int h = 0; h < P; ++h) {
+                a32[h] = 0;
+                e32[h] = 0;
+            }
+            const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 const uint32_t w = lut_s[__byte_perm(qq[k >> 2], 0, 0x4440 | (k & 3))];
+                if (MODE == FB_SWEEP_SCORE) {
+                    if (pr & (1u << k)) t32 = fb_add_fma(t32, w, one);
+                }
 #pragma unroll
                 for (int h = 0; h < P; ++h)
-                    if (ebs[h] & (1u << k)) e32[h] += w;
+                    if (sel[h] & (1u << k)) a32[h] = fb_add_fma(a32[h], w, one);
             }
-        }
-        total += t32;
+            if (MODE == FB_SWEEP_SCORE && any_e) {
 #pragma unroll
-        for (int h = 0; h < P; ++h) {
-            acc[h] += a32[h];
-            emptyw[h] += e32[h];
+                for (int k = 0; k < 16; ++k) {
+                    const uint32_t w = lut_s[__byte_perm(qq[k >> 2], 0, 0x4440 | (k & 3))];
+#pragma unroll
+                    for (int h = 0; h < P; ++h)
+                        if (ebs[h] & (1u << k)) e32[h] += w;
+                }
+            }
+            total += t32;
+#pragma unroll
+            for (int h = 0; h < P; ++h) {
+                acc[h] += a32[h];
+                emptyw[h] += e32[h];
+            }
+    };
+    if (TMA) {
+        // TMA pipeline: lane 0 keeps FB_SWEEP_STAGES chunks of 32 groups in flight (three cp.async.bulk per chunk,
+        // completion on the stage's mbarrier); every lane then scores one group out of shared memory.  Reads start on
+        // 8-group boundaries and their planes are padded to 8 groups, so every copy is 16-byte aligned and a multiple
+        // of 16 bytes.
+        const uint32_t ng_pad = (g1 - g0 + 7u) & ~7u;
+        const uint32_t n_chunks = (g1 - g0 + 31u) >> 5;
+        auto issue = [&](uint32_t c) {
+            const uint32_t st = c % FB_SWEEP_STAGES;
+            const uint32_t n = min(32u, ng_pad - c * 32u);
+            const uint32_t gsrc = g0 + c * 32u;
+            fb_mbar_expect_tx(&bars[st], n * 22u);
+            fb_bulk_g2s(stg[st].qual, a.fr.qual + gsrc, n * 16u, &bars[st]);
+            fb_bulk_g2s(stg[st].allele, a.fr.allele + gsrc, n * 4u, &bars[st]);
+            fb_bulk_g2s(stg[st].present, a.fr.present + gsrc, n * 2u, &bars[st]);
+        };
+        if (lane == 0)
+            for (uint32_t c = 0; c < min(n_chunks, (uint32_t)FB_SWEEP_STAGES); ++c) issue(c);
+        for (uint32_t c = 0; c < n_chunks; ++c) {
+            const uint32_t st = c % FB_SWEEP_STAGES;
+            fb_mbar_wait(&bars[st], (c / FB_SWEEP_STAGES) & 1u);
+            const uint32_t g = g0 + c * 32u + lane;
+            const bool live = g < g1;
+            const uint4 q = stg[st].qual[lane];
+            const uint32_t al = stg[st].allele[lane];
+            const uint32_t pr = live ? (uint32_t)stg[st].present[lane] : 0u;
+            __syncwarp();
+            if (lane == 0 && c + FB_SWEEP_STAGES < n_chunks) issue(c + FB_SWEEP_STAGES);
+            if (live) score_group(q, al, pr, g);
+        }
+    } else {
+        // register pipeline: the next group's loads are in flight while the current one is scored
+        uint32_t g = g0 + lane;
+        uint4 q_n = make_uint4(0, 0, 0, 0);
+        uint32_t al_n = 0, pr_n = 0;
+        if (g < g1) {
+            q_n = a.fr.qual[g];
+            al_n = a.fr.allele[g];
+            pr_n = a.fr.present[g];
+        }
+        for (; g < g1; g += 32) {
+            const uint4 q = q_n;
+            const uint32_t al = al_n, pr = pr_n;
+            if (g + 32 < g1) {
+                q_n = a.fr.qual[g + 32];
+                al_n = a.fr.allele[g + 32];
+                pr_n = a.fr.present[g + 32];
+            }
+            score_group(q, al, pr, g);
         }
     }
     double diff_f[P];
@@ -300,23 +345,32 @@ __device__ void fb_sweep_body(const SweepArgs &a, const InstDev &in, int ii, uin
     }
 }
 
-template <int P>
+template <int P, bool TMA>
 __device__ __forceinline__ void fb_sweep_dispatch(const SweepArgs &a, const InstDev &in, int ii, uint64_t slot,
-                                                  const RInfo ri, const uint32_t *lut_s, uint32_t *ws) {
+                                                  const RInfo ri, const uint32_t *lut_s, uint32_t *ws, SweepStage *stg,
+                                                  uint64_t *bars) {
     if (a.mode == FB_SWEEP_SCORE)
-        fb_sweep_body<P, FB_SWEEP_SCORE>(a, in, ii, slot, ri, lut_s, ws);
+        fb_sweep_body<P, FB_SWEEP_SCORE, TMA>(a, in, ii, slot, ri, lut_s, ws, stg, bars);
     else
-        fb_sweep_body<P, FB_SWEEP_MOVES>(a, in, ii, slot, ri, lut_s, ws);
+        fb_sweep_body<P, FB_SWEEP_MOVES, TMA>(a, in, ii, slot, ri, lut_s, ws, stg, bars);
 }
 
 // PMAX = largest ploidy this instantiation handles: the register budget of a kernel is that of its widest path, so the
 // host launches the narrowest variant that covers the batch (2, 4 or 8).
-template <int PMAX>
+template <int PMAX, bool TMA>
 __global__ void __launch_bounds__(FB_SWEEP_WARPS * 32) k_sweep(SweepArgs a) {
     __shared__ uint32_t lut_s[256];
     __shared__ uint32_t wscr[FB_SWEEP_WARPS][16];
+    __shared__ SweepStage stages[TMA ? FB_SWEEP_WARPS : 1][TMA ? FB_SWEEP_STAGES : 1];
+    __shared__ __align__(8) uint64_t mbars[TMA ? FB_SWEEP_WARPS : 1][FB_SWEEP_STAGES];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut_s[i] = a.lut[i];
+    if (TMA && (threadIdx.x & 31) == 0) {
+        for (int s2 = 0; s2 < FB_SWEEP_STAGES; ++s2) fb_mbar_init(&mbars[threadIdx.x >> 5][s2], 1);
+        fb_mbar_fence_init();
+    }
     __syncthreads();
+    SweepStage *stg = stages[TMA ? (threadIdx.x >> 5) : 0];
+    uint64_t *bars = mbars[TMA ? (threadIdx.x >> 5) : 0];
     const uint64_t total = a.assign_prefix[a.n_inst];
     const uint64_t slot = (uint64_t)blockIdx.x * FB_SWEEP_WARPS + (threadIdx.x >> 5);
     if (slot >= total) return;
@@ -326,14 +380,14 @@ __global__ void __launch_bounds__(FB_SWEEP_WARPS * 32) k_sweep(SweepArgs a) {
     const RInfo ri = a.rinfo[in.read_off + (uint32_t)(slot - in.assign_off)];
     uint32_t *ws = wscr[threadIdx.x >> 5];
     switch (in.ploidy) {
-        case 1: fb_sweep_dispatch<1>(a, in, ii, slot, ri, lut_s, ws); break;
-        case 2: fb_sweep_dispatch<2>(a, in, ii, slot, ri, lut_s, ws); break;
-        case 3: if (PMAX >= 3) fb_sweep_dispatch<(PMAX >= 3 ? 3 : 1)>(a, in, ii, slot, ri, lut_s, ws); break;
-        case 4: if (PMAX >= 4) fb_sweep_dispatch<(PMAX >= 4 ? 4 : 1)>(a, in, ii, slot, ri, lut_s, ws); break;
-        case 5: if (PMAX >= 5) fb_sweep_dispatch<(PMAX >= 5 ? 5 : 1)>(a, in, ii, slot, ri, lut_s, ws); break;
-        case 6: if (PMAX >= 6) fb_sweep_dispatch<(PMAX >= 6 ? 6 : 1)>(a, in, ii, slot, ri, lut_s, ws); break;
-        case 7: if (PMAX >= 7) fb_sweep_dispatch<(PMAX >= 7 ? 7 : 1)>(a, in, ii, slot, ri, lut_s, ws); break;
-        case 8: if (PMAX >= 8) fb_sweep_dispatch<(PMAX >= 8 ? 8 : 1)>(a, in, ii, slot, ri, lut_s, ws); break;
+        case 1: fb_sweep_dispatch<1, TMA>(a, in, ii, slot, ri, lut_s, ws, stg, bars); break;
+        case 2: fb_sweep_dispatch<2, TMA>(a, in, ii, slot, ri, lut_s, ws, stg, bars); break;
+        case 3: if (PMAX >= 3) fb_sweep_dispatch<(PMAX >= 3 ? 3 : 1), TMA>(a, in, ii, slot, ri, lut_s, ws, stg, bars); break;
+        case 4: if (PMAX >= 4) fb_sweep_dispatch<(PMAX >= 4 ? 4 : 1), TMA>(a, in, ii, slot, ri, lut_s, ws, stg, bars); break;
+        case 5: if (PMAX >= 5) fb_sweep_dispatch<(PMAX >= 5 ? 5 : 1), TMA>(a, in, ii, slot, ri, lut_s, ws, stg, bars); break;
+        case 6: if (PMAX >= 6) fb_sweep_dispatch<(PMAX >= 6 ? 6 : 1), TMA>(a, in, ii, slot, ri, lut_s, ws, stg, bars); break;
+        case 7: if (PMAX >= 7) fb_sweep_dispatch<(PMAX >= 7 ? 7 : 1), TMA>(a, in, ii, slot, ri, lut_s, ws, stg, bars); break;
+        case 8: if (PMAX >= 8) fb_sweep_dispatch<(PMAX >= 8 ? 8 : 1), TMA>(a, in, ii, slot, ri, lut_s, ws, stg, bars); break;
         default: break;
     }
 }
@@ -396,9 +450,22 @@ __global__ void __launch_bounds__(FB_HIST_THREADS) k_hist(HistArgs a) {
     __shared__ uint4 s_list[FB_HIST_LIST];
     __shared__ int s_n;
     __shared__ int s_last;
+    __shared__ int s_zero_any, s_zero_other;
     const int t = threadIdx.x;
-    for (int i = t; i < 256; i += FB_HIST_THREADS) lut_s[i] = a.use_phred ? a.lut[i] : (1u << 26);
-    if (t == 0) s_n = 0;
+    if (t == 0) {
+        s_n = 0;
+        s_zero_any = 0;
+        s_zero_other = 0;
+    }
+    __syncthreads();
+    for (int i = t; i < 256; i += FB_HIST_THREADS) {
+        const uint32_t v = a.use_phred ? a.lut[i] : (1u << 26);
+        lut_s[i] = v;
+        if (v == 0) {
+            s_zero_any = 1;
+            if (i != 0) s_zero_other = 1;
+        }
+    }
     const uint64_t cta = blockIdx.x;
     const int ii = fb_upper_seg(a.tile_prefix, a.n_inst, cta);
     const InstDev in = a.inst[ii];
@@ -433,6 +500,7 @@ __global__ void __launch_bounds__(FB_HIST_THREADS) k_hist(HistArgs a) {
     }
     int since_flush = 0;
     __syncthreads();
+    const bool lut_zero = s_zero_any != 0, lut_zero_only_q0 = s_zero_other == 0;
     for (uint32_t base = r_begin; base < r_end; base += FB_HIST_LIST) {
         // reads are sorted by first position: once a chunk starts right of the tile, nothing later overlaps it
         if (rinfo[base].lg0 >= tg0 + FB_HIST_TILE_GROUPS) break;
@@ -446,26 +514,40 @@ __global__ void __launch_bounds__(FB_HIST_THREADS) k_hist(HistArgs a) {
         }
         __syncthreads();
         const int n = s_n;
-        for (int e0 = 0; e0 < n; e0 += FB_HIST_BATCH) {
-            uint32_t q[FB_HIST_BATCH], al[FB_HIST_BATCH], pr[FB_HIST_BATCH];
+        // double-buffered batches: the loads of batch e0+4 are in flight while batch e0 is accumulated
+        uint32_t q[FB_HIST_BATCH], al[FB_HIST_BATCH], pr[FB_HIST_BATCH];
+        uint32_t qn[FB_HIST_BATCH], aln[FB_HIST_BATCH], prn[FB_HIST_BATCH];
+        auto load_batch = [&](int e0, uint32_t(&qq)[FB_HIST_BATCH], uint32_t(&aa)[FB_HIST_BATCH],
+                              uint32_t(&pp)[FB_HIST_BATCH]) {
 #pragma unroll
             for (int b = 0; b < FB_HIST_BATCH; ++b) {
-                q[b] = 0;
-                al[b] = 0;
-                pr[b] = 0;
+                qq[b] = 0;
+                aa[b] = 0;
+                pp[b] = 0;
                 if (e0 + b < n) {
                     const uint4 en = s_list[e0 + b];
                     if (G >= en.y && G < en.z) {
                         const uint32_t g = en.x + G;
-                        q[b] = qual32[(uint64_t)g * 4 + sub];
-                        al[b] = a.fr.allele[g];
-                        pr[b] = a.fr.present[g];
+                        qq[b] = qual32[(uint64_t)g * 4 + sub];
+                        aa[b] = a.fr.allele[g];
+                        pp[b] = a.fr.present[g];
                     }
                 }
             }
+        };
+        load_batch(0, qn, aln, prn);
+        for (int e0 = 0; e0 < n; e0 += FB_HIST_BATCH) {
+#pragma unroll
+            for (int b = 0; b < FB_HIST_BATCH; ++b) {
+                q[b] = qn[b];
+                al[b] = aln[b];
+                pr[b] = prn[b];
+            }
+            if (e0 + FB_HIST_BATCH < n) load_batch(e0 + FB_HIST_BATCH, qn, aln, prn);
 #pragma unroll
             for (int b = 0; b < FB_HIST_BATCH; ++b) {
                 const uint32_t P4 = (pr[b] >> (sub * 4)) & flt4;
+                if (P4 == 0) continue;  // this thread's four positions are not covered by the read
                 const uint32_t A0 = (al[b] >> (sub * 4)) & P4;
                 const uint32_t A1 = (al[b] >> (16 + sub * 4)) & P4;
                 uint32_t w[4];
@@ -484,7 +566,8 @@ __global__ void __launch_bounds__(FB_HIST_THREADS) k_hist(HistArgs a) {
                         if (A3 & (1u << k)) c3[k] += w[k];
                     }
                 }
-                if (P4 && (w[0] == 0 || w[1] == 0 || w[2] == 0 || w[3] == 0)) {  // zero-weight keys (q = 0)
+                // zero-weight keys: a cell whose weight is 0 still inserts its allele key (utils_frags.rs:165-166)
+                if (lut_zero && (lut_zero_only_q0 ? ((q[b] - 0x01010101u) & ~q[b] & 0x80808080u) != 0u : true)) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         if ((P4 & (1u << k)) && w[k] == 0)

@@ -134,6 +134,7 @@ int fb_frags_upload(fb_ctx *ctx, const fb_frags *fr, fb_dfrags **out) {
     df->h_nnz.resize(R);
     df->h_gstart.resize(R);
     df->h_gptr.resize(R + 1);
+    df->h_gnum.resize(R);
     df->h_prefmax_last.resize(R);
     uint64_t ng = 0;
     uint32_t pm = 0;
@@ -163,12 +164,15 @@ int fb_frags_upload(fb_ctx *ctx, const fb_frags *fr, fb_dfrags **out) {
         df->h_nnz[i] = (uint32_t)(b - a);
         uint32_t g0 = (f - 1) >> 4, g1 = (l - 1) >> 4;
         df->h_gstart[i] = g0;
+        ng = (ng + 7) & ~7ULL;  // every read starts on an 8-group boundary (16-byte aligned planes)
         df->h_gptr[i] = (uint32_t)ng;
+        df->h_gnum[i] = g1 - g0 + 1;
         ng += (uint64_t)(g1 - g0 + 1);
         if (ng >= (1ull << 32) - 64) FB_FAIL(FB_ERR_LIMIT, "more than 2^32 groups");
         pm = std::max(pm, l);
         df->h_prefmax_last[i] = pm;
     }
+    ng = (ng + 7) & ~7ULL;
     df->h_gptr[R] = (uint32_t)ng;
     df->n_groups = ng;
     int rc;
@@ -187,7 +191,8 @@ int fb_frags_upload(fb_ctx *ctx, const fb_frags *fr, fb_dfrags **out) {
         (rc = fb_upload(ctx, &d_al, fr->allele, fr->nnz)) || (rc = fb_upload(ctx, &d_q, fr->qual, fr->nnz)) ||
         (rc = fb_upload(ctx, &df->d_first, df->h_first)) || (rc = fb_upload(ctx, &df->d_last, df->h_last)) ||
         (rc = fb_upload(ctx, &df->d_nnz, df->h_nnz)) || (rc = fb_upload(ctx, &df->d_gstart, df->h_gstart)) ||
-        (rc = fb_upload(ctx, &df->d_gptr, df->h_gptr)) || (rc = fb_dalloc(ctx, &df->d_qual, ng + 1)) ||
+        (rc = fb_upload(ctx, &df->d_gptr, df->h_gptr)) || (rc = fb_upload(ctx, &df->d_gnum, df->h_gnum)) ||
+        (rc = fb_dalloc(ctx, &df->d_qual, ng + 1)) ||
         (rc = fb_dalloc(ctx, &df->d_allele, ng + 1)) || (rc = fb_dalloc(ctx, &df->d_present, ng + 2))) {
         cleanup();
         fb_frags_free(ctx, df.release());
@@ -230,6 +235,7 @@ void fb_frags_free(fb_ctx *ctx, fb_dfrags *df) {
     fb_cache_free(df->d_nnz);
     fb_cache_free(df->d_gstart);
     fb_cache_free(df->d_gptr);
+    fb_cache_free(df->d_gnum);
     fb_cache_free(df->d_qual);
     fb_cache_free(df->d_allele);
     fb_cache_free(df->d_present);
