@@ -165,6 +165,21 @@ def test_beam_search_matches_oracle(ctx, case, eps, ploidy):
     assert_f64_identical([gsc], [osc], "best score")
 
 
+@pytest.mark.parametrize("ploidy", [6, 8])
+def test_beam_search_high_ploidy_short_reads(ctx, ploidy):
+    """many duplicate blocks (short windows) and the widest instantiations of the kernel"""
+    fr = CASES["short"]()
+    prm = default_params(epsilon=0.01, max_number_solns=4)
+    sel = np.arange(90, dtype=np.uint32)
+    oh, osc, (os_, od, ol, on) = oracle.beam_search_phasing(fr, sel, ploidy, prm, tap_cap=400000)
+    gh, gsc, (gs, gd, gl, gn) = ctx.beam_search_phasing(fr, sel, ploidy, prm, tap_cap=400000)
+    assert gn == on
+    assert_f64_identical(gs, os_, "tap same")
+    assert_f64_identical(gd, od, "tap diff")
+    assert np.array_equal(gh, oh)
+    assert_f64_identical([gsc], [osc], "best score")
+
+
 def test_beam_search_small_beam_and_single_read(ctx):
     fr = CASES["edge"]()
     for B in (1, 3):
