@@ -9,8 +9,10 @@
 __global__ void k_pack(uint64_t nnz, uint64_t n_reads, const uint64_t *__restrict__ row_ptr,
                        const uint32_t *__restrict__ pos, const uint8_t *__restrict__ allele,
                        const uint8_t *__restrict__ qual, const uint32_t *__restrict__ gstart,
-                       const uint32_t *__restrict__ gptr, uint8_t *__restrict__ qual_out,
-                       uint32_t *__restrict__ allele_out, uint32_t *__restrict__ present_out32) {
+                       const uint32_t *__restrict__ gptr, const uint32_t *__restrict__ first,
+                       const uint32_t *__restrict__ last, uint8_t *__restrict__ qual_out,
+                       uint32_t *__restrict__ allele_out, uint32_t *__restrict__ present_out32,
+                       unsigned long long *__restrict__ err /* first bad cell + 1, 0 = none */) {
     uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nnz) return;
     // read of this cell: last r with row_ptr[r] <= c
@@ -22,10 +24,21 @@ __global__ void k_pack(uint64_t nnz, uint64_t n_reads, const uint64_t *__restric
         else
             hi = mid;
     }
-    uint32_t p0 = pos[c] - 1u;
+    const uint32_t p = pos[c];
+    const uint32_t a = allele[c];
+    // per-cell validation (the per-read checks are done on the host): allele index fits 2 bits, positions strictly
+    // ascending inside [first, last] with the end points present
+    bool bad = a > 3 || p < first[lo] || p > last[lo];
+    if (c > row_ptr[lo] && pos[c - 1] >= p) bad = true;
+    if (c == row_ptr[lo] && p != first[lo]) bad = true;
+    if (c + 1 == row_ptr[lo + 1] && p != last[lo]) bad = true;
+    if (bad) {
+        atomicMin(err, c + 1);
+        return;
+    }
+    uint32_t p0 = p - 1u;
     uint32_t g = gptr[lo] + ((p0 >> 4) - gstart[lo]);
     uint32_t k = p0 & 15u;
-    uint32_t a = allele[c];
     atomicOr(&allele_out[g], ((a & 1u) << k) | (((a >> 1) & 1u) << (16 + k)));
     atomicOr(&present_out32[g >> 1], 1u << (k + 16u * (g & 1u)));
     qual_out[(uint64_t)g * 16 + k] = qual[c];

@@ -145,16 +145,7 @@ int fb_frags_upload(fb_ctx *ctx, const fb_frags *fr, fb_dfrags **out) {
         if (b <= a) FB_FAIL(FB_ERR_ARG, "read %llu has no cells", (unsigned long long)i);
         uint32_t f = fr->first[i], l = fr->last[i];
         if (f < 1 || l < f) FB_FAIL(FB_ERR_ARG, "read %llu: bad first/last", (unsigned long long)i);
-        if (fr->pos[a] != f || fr->pos[b - 1] != l)
-            FB_FAIL(FB_ERR_ARG, "read %llu: first/last_position must be the min/max of its positions",
-                    (unsigned long long)i);
-        for (uint64_t c = a; c < b; ++c) {
-            if (c > a && fr->pos[c] <= fr->pos[c - 1])
-                FB_FAIL(FB_ERR_ARG, "read %llu: positions must be strictly ascending", (unsigned long long)i);
-            if (fr->allele[c] > 3)
-                FB_FAIL(FB_ERR_ARG, "read %llu: allele %u > 3 (packed layout holds 2-bit alleles)",
-                        (unsigned long long)i, (unsigned)fr->allele[c]);
-        }
+        // per-cell checks (strictly ascending positions inside [first, last], allele <= 3) run in k_pack on the device
         if (i > 0) {
             // Frag::cmp (types_structs.rs:87-93): first asc, last desc, counter_id asc
             uint32_t pf = fr->first[i - 1], pl = fr->last[i - 1];
@@ -181,7 +172,10 @@ int fb_frags_upload(fb_ctx *ctx, const fb_frags *fr, fb_dfrags **out) {
     uint64_t *d_row = nullptr;
     uint32_t *d_pos = nullptr;
     uint8_t *d_al = nullptr, *d_q = nullptr;
+    unsigned long long *d_err = nullptr;
+    unsigned long long h_err = 0;
     auto cleanup = [&]() {
+        fb_cache_free(d_err);
         fb_cache_free(d_row);
         fb_cache_free(d_pos);
         fb_cache_free(d_al);
@@ -193,7 +187,8 @@ int fb_frags_upload(fb_ctx *ctx, const fb_frags *fr, fb_dfrags **out) {
         (rc = fb_upload(ctx, &df->d_nnz, df->h_nnz)) || (rc = fb_upload(ctx, &df->d_gstart, df->h_gstart)) ||
         (rc = fb_upload(ctx, &df->d_gptr, df->h_gptr)) || (rc = fb_upload(ctx, &df->d_gnum, df->h_gnum)) ||
         (rc = fb_dalloc(ctx, &df->d_qual, ng + 1)) ||
-        (rc = fb_dalloc(ctx, &df->d_allele, ng + 1)) || (rc = fb_dalloc(ctx, &df->d_present, ng + 2))) {
+        (rc = fb_dalloc(ctx, &df->d_allele, ng + 1)) || (rc = fb_dalloc(ctx, &df->d_present, ng + 2)) ||
+        (rc = fb_dalloc(ctx, &d_err, 1))) {
         cleanup();
         fb_frags_free(ctx, df.release());
         return rc;
@@ -202,12 +197,14 @@ int fb_frags_upload(fb_ctx *ctx, const fb_frags *fr, fb_dfrags **out) {
     cudaMemsetAsync(df->d_qual, 0, (ng + 1) * sizeof(uint4), ctx->stream);
     cudaMemsetAsync(df->d_allele, 0, (ng + 1) * sizeof(uint32_t), ctx->stream);
     cudaMemsetAsync(df->d_present, 0, (ng + 2) * sizeof(uint16_t), ctx->stream);
+    cudaMemsetAsync(d_err, 0xFF, sizeof(unsigned long long), ctx->stream);
     if (fr->nnz) {
         k_pack<<<(unsigned)((fr->nnz + 255) / 256), 256, 0, ctx->stream>>>(
-            fr->nnz, R, d_row, d_pos, d_al, d_q, df->d_gstart, df->d_gptr, reinterpret_cast<uint8_t *>(df->d_qual),
-            df->d_allele, reinterpret_cast<uint32_t *>(df->d_present));
+            fr->nnz, R, d_row, d_pos, d_al, d_q, df->d_gstart, df->d_gptr, df->d_first, df->d_last,
+            reinterpret_cast<uint8_t *>(df->d_qual), df->d_allele, reinterpret_cast<uint32_t *>(df->d_present), d_err);
         ctx->tim.n_launches++;
     }
+    cudaMemcpyAsync(&h_err, d_err, sizeof(h_err), cudaMemcpyDeviceToHost, ctx->stream);
     cudaEvent_t e2 = fb_event(ctx);
     cudaError_t ce = cudaStreamSynchronize(ctx->stream);
     if (ce == cudaSuccess) ce = cudaGetLastError();
@@ -216,6 +213,18 @@ int fb_frags_upload(fb_ctx *ctx, const fb_frags *fr, fb_dfrags **out) {
         ctx->err = std::string("fb_frags_upload: ") + cudaGetErrorString(ce);
         fb_frags_free(ctx, df.release());
         return FB_ERR_CUDA;
+    }
+    if (h_err != ~0ULL) {
+        const uint64_t c = h_err - 1;
+        uint64_t r = std::upper_bound(fr->row_ptr, fr->row_ptr + R + 1, c) - fr->row_ptr - 1;
+        char b_[256];
+        snprintf(b_, sizeof(b_),
+                 "read %llu: invalid cell (allele %u at position %u): alleles must be 0..3 and positions strictly "
+                 "ascending with first/last_position their min/max",
+                 (unsigned long long)r, (unsigned)fr->allele[c], fr->pos[c]);
+        ctx->err = b_;
+        fb_frags_free(ctx, df.release());
+        return FB_ERR_ARG;
     }
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
