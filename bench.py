@@ -283,8 +283,15 @@ def run_ours(args):
             k["frac_of_peak"] = k["GB/s"] / peak
             k["share_of_step"] = k["ms"] / max(d["total_ms"], 1e-9)
         dom = max(kern, key=lambda n: kern[n]["ms"])
+        # DRAM traffic per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/)
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            traffic = tj.get(dom, {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
         roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["GB/s"], "peak": peak, "unit": "GB/s",
-                    "frac": kern[dom]["frac_of_peak"], "traffic": None, "peak_source": peak_src,
+                    "frac": kern[dom]["frac_of_peak"], "traffic": traffic, "peak_source": peak_src,
                     "avg_launch_ms": kern[dom]["ms"] / max(kern[dom]["launches"], 1),
                     "algorithmic_bytes_per_cell": BYTES_PER_CELL, "kernels": kern,
                     "note": "k_beam is dependency-bound (one sequential step per read); the HBM-bound kernels are "

@@ -24,7 +24,7 @@
 #include "fb_common.cuh"
 #include "fb_kernels.cuh"
 
-#define FB_BEAM_THREADS 512
+#define FB_BEAM_THREADS 256
 #define FB_BEAM_WARPS (FB_BEAM_THREADS / 32)
 
 struct BeamTapDev {

@@ -28,7 +28,7 @@ __global__ void k_synth_dense(uint64_t n_reads, uint32_t n_snps, uint32_t ng_per
     const uint64_t r = x / ng_per_read;
     const uint32_t gl = (uint32_t)(x % ng_per_read);
     const uint32_t h = src[r];
-    uint32_t qq[4] = {0, 0, 0, 0};
+    uint32_t qq[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};  // absent cells: 0xFF
     uint32_t al = 0, pr = 0;
     for (uint32_t k = 0; k < 16; ++k) {
         const uint32_t off = gl * 16 + k;  // position0 == offset inside the (full-span) read
@@ -45,7 +45,7 @@ __global__ void k_synth_dense(uint64_t n_reads, uint32_t n_snps, uint32_t ng_per
         const uint32_t q = 5 + (uint32_t)(fbs_u64(seed, 203, key) % 36ULL);
         pr |= 1u << k;
         al |= ((a & 1u) << k) | (((a >> 1) & 1u) << (16 + k));
-        qq[k >> 2] |= q << (8 * (k & 3));
+        qq[k >> 2] = (qq[k >> 2] & ~(0xFFu << (8 * (k & 3)))) | (q << (8 * (k & 3)));
     }
     const uint64_t go = r * stride + gl;
     qual[go] = make_uint4(qq[0], qq[1], qq[2], qq[3]);
@@ -91,7 +91,7 @@ int fb_bench_synth_dense(fb_ctx *ctx, uint64_t n_reads, uint32_t n_snps, uint32_
         return rc;
     }
     cudaMemsetAsync(df->d_nnz, 0, n_reads * 4, ctx->stream);
-    cudaMemsetAsync(df->d_qual, 0, (ng + 1) * sizeof(uint4), ctx->stream);
+    cudaMemsetAsync(df->d_qual, 0xFF, (ng + 1) * sizeof(uint4), ctx->stream);
     cudaMemsetAsync(df->d_allele, 0, (ng + 1) * sizeof(uint32_t), ctx->stream);
     cudaMemsetAsync(df->d_present, 0, (ng + 2) * sizeof(uint16_t), ctx->stream);
     k_synth_dense<<<(unsigned)((n_reads * (uint64_t)ngr + 255) / 256), 256, 0, ctx->stream>>>(n_reads, n_snps, ngr, stride, seed, present, flip, d_truth,

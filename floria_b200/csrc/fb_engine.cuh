@@ -266,7 +266,7 @@ struct Engine {
         tot_mask += (uint64_t)ploidy * b.ng;
         tot_mec += ploidy;
         // read splits per (tile, haplotype): enough CTAs to saturate HBM on big blocks, 1 (no atomics) on small ones
-        uint32_t splits = std::min<uint32_t>(16, std::max<uint32_t>(1, in.n_reads / 4096));
+        uint32_t splits = std::min<uint32_t>(8, std::max<uint32_t>(1, in.n_reads / 8192));
         if (splits > 1) any_split = true;
         hist_splits.push_back(splits);
         done_off.push_back(tot_done);
@@ -364,7 +364,12 @@ struct Engine {
             k_hist_zero<<<dim3(64, (unsigned)n), 256, 0, ctx->stream>>>(a);
             ctx->tim.n_launches++;
         }
-        k_hist<<<(unsigned)ctas, FB_HIST_THREADS, 0, ctx->stream>>>(a);
+        static bool hist_attr = false;
+        if (!hist_attr) {
+            FB_CK(cudaFuncSetAttribute(k_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_HIST_SMEM));
+            hist_attr = true;
+        }
+        k_hist<<<(unsigned)ctas, FB_HIST_THREADS, FB_HIST_SMEM, ctx->stream>>>(a);
         cudaEvent_t e1 = fb_event(ctx);
         hist_ev.push_back(std::make_pair(e0, e1));
         ctx->tim.n_launches++;

@@ -406,21 +406,23 @@ __global__ void __launch_bounds__(FB_SWEEP_WARPS * 32) k_sweep(SweepArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// K2 hap_histogram.  One CTA per (instance, tile of 1024 positions, haplotype, read split).  Every thread owns 4
-// consecutive positions; all threads of the CTA process the same read at the same time (each its own columns), so the
-// counters live in REGISTERS with static indexing and no atomics: per position total weight T and the sums C1 (allele
-// bit 0 set), C2 (allele bit 1 set), C3 (both), from which n3 = C3, n1 = C1-C3, n2 = C2-C3, n0 = T-C1-C2+C3.  32-bit
-// partial sums are flushed to 64 bit every 28 reads (28 * 2^26 < 2^32).  Reads of the wanted haplotype that overlap the
-// tile are compacted into shared memory 256 at a time and streamed in batches of 4 independent loads.
+// K2 hap_histogram.  One CTA per (instance, tile of 512 positions, haplotype, read split).  Lane l of every warp owns
+// group l of the tile (16 positions); the 8 warps take the matching reads round-robin, four reads in flight per warp,
+// each read row arriving as fully coalesced 512 B (quals) + 128 B (alleles) + 64 B (presence) per warp.  Per position a
+// lane keeps 32-bit partial sums T (all alleles) and C1 (allele bit 0 set) in registers and flushes them every 28 rows
+// into 64-bit tables in shared memory (layout [k][lane]: conflict free); alleles 2/3 and zero-weight keys are rare and
+// go straight to shared-memory atomics.  n3 = C3, n1 = C1-C3, n2 = C2-C3, n0 = T-C1-C2+C3.
 // With several read splits per (tile, haplotype) the partial tables are merged with 64-bit global atomics (exact integer
 // adds: deterministic) and the last CTA to finish derives the is-max planes.
 // Reproduces utils_frags.rs:160-184 set_to_seq_dict / hap_block_from_partition; the planes are the consensus test of
 // utils_frags.rs:53-69.
 // ---------------------------------------------------------------------------------------------------------------------
 #define FB_HIST_THREADS 256
-#define FB_HIST_TILE_GROUPS 64  // 1024 positions
-#define FB_HIST_LIST 256
+#define FB_HIST_WARPS 8
+#define FB_HIST_TILE_GROUPS 32  // 512 positions
+#define FB_HIST_LIST 1024
 #define FB_HIST_BATCH 4
+#define FB_HIST_SMEM ((FB_HIST_WARPS * 2 + 2) * 512 * 8)
 
 struct HistArgs {
     DFragsDev fr;
@@ -461,15 +463,21 @@ __global__ void k_hist_zero(HistArgs a) {
 __global__ void __launch_bounds__(FB_HIST_THREADS) k_hist(HistArgs a) {
     __shared__ uint32_t lut_s[256];
     __shared__ uint4 s_list[FB_HIST_LIST];
-    __shared__ int s_n;
-    __shared__ int s_last;
-    __shared__ int s_zero_any, s_zero_other;
+    // dynamic shared memory: per-warp private 64-bit tables T, C1 (no atomics on the flush path) + shared C2, C3
+    extern __shared__ __align__(16) unsigned long long hist_dyn[];
+    unsigned long long(*wtab)[2][512] = reinterpret_cast<unsigned long long(*)[2][512]>(hist_dyn);  // [warp][T|C1][k*32+lane]
+    unsigned long long(*tab)[512] = reinterpret_cast<unsigned long long(*)[512]>(hist_dyn + FB_HIST_WARPS * 2 * 512);  // C2, C3
+    __shared__ uint32_t zf_tab[512];            // bit a: a zero-weight cell inserted allele key a
+    __shared__ int s_n, s_last, s_zero_any, s_zero_other;
     const int t = threadIdx.x;
+    const uint32_t lane = t & 31, warp = t >> 5;
     if (t == 0) {
         s_n = 0;
         s_zero_any = 0;
         s_zero_other = 0;
     }
+    for (int i = t; i < (FB_HIST_WARPS * 2 + 2) * 512; i += FB_HIST_THREADS) hist_dyn[i] = 0ULL;
+    for (int i = t; i < 512; i += FB_HIST_THREADS) zf_tab[i] = 0;
     __syncthreads();
     for (int i = t; i < 256; i += FB_HIST_THREADS) {
         const uint32_t v = a.use_phred ? a.lut[i] : (1u << 26);
@@ -493,110 +501,116 @@ __global__ void __launch_bounds__(FB_HIST_THREADS) k_hist(HistArgs a) {
     const uint8_t *__restrict__ assign = a.assign[a.assign_cur ? cur : buf] + in.assign_off;
     const RInfo *__restrict__ rinfo = a.rinfo + in.read_off;
     const uint32_t tg0 = tile * FB_HIST_TILE_GROUPS;  // first block-local group of the tile
-    const uint32_t G = tg0 + (t >> 2);                // this thread's block-local group
-    const uint32_t sub = t & 3;                       // which 4 cells of the group
+    const uint32_t G = tg0 + lane;                    // this lane's block-local group
     const uint32_t r_begin = (uint32_t)((uint64_t)in.n_reads * split / S);
     const uint32_t r_end = (uint32_t)((uint64_t)in.n_reads * (split + 1) / S);
-    const uint32_t *__restrict__ qual32 = reinterpret_cast<const uint32_t *>(a.fr.qual);
-    uint32_t t32[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0}, c2[4] = {0, 0, 0, 0}, c3[4] = {0, 0, 0, 0};
-    unsigned long long T[4] = {0, 0, 0, 0}, C1[4] = {0, 0, 0, 0}, C2[4] = {0, 0, 0, 0}, C3[4] = {0, 0, 0, 0};
-    uint32_t zf = 0;  // bit k*4+allele: a zero-weight cell inserted that allele key
     const uint32_t one = a.one;
     // optional position filter (types_structs.rs:173: HapNode::new keeps positions inside snp_endpoints only)
-    uint32_t flt4 = 0xFu;
+    uint32_t flt16 = 0xFFFFu;
     if (in.flt_lo != 0 || in.flt_hi != 0xFFFFFFFFu) {
-        flt4 = 0;
-        for (uint32_t k = 0; k < 4; ++k) {
-            const uint32_t pos = G * 16 + sub * 4 + k;
-            if (pos >= in.flt_lo && pos <= in.flt_hi) flt4 |= 1u << k;
+        flt16 = 0;
+        for (uint32_t k = 0; k < 16; ++k) {
+            const uint32_t pos = G * 16 + k;
+            if (pos >= in.flt_lo && pos <= in.flt_hi) flt16 |= 1u << k;
         }
+    }
+    uint32_t t32[16], c1[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        t32[k] = 0;
+        c1[k] = 0;
     }
     int since_flush = 0;
     __syncthreads();
     const bool lut_zero = s_zero_any != 0, lut_zero_only_q0 = s_zero_other == 0;
+    auto flush = [&]() {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            wtab[warp][0][k * 32 + lane] += (unsigned long long)t32[k];
+            wtab[warp][1][k * 32 + lane] += (unsigned long long)c1[k];
+            t32[k] = 0;
+            c1[k] = 0;
+        }
+    };
     for (uint32_t base = r_begin; base < r_end; base += FB_HIST_LIST) {
         // reads are sorted by first position: once a chunk starts right of the tile, nothing later overlaps it
         if (rinfo[base].lg0 >= tg0 + FB_HIST_TILE_GROUPS) break;
-        const uint32_t rl = base + t;
-        if (rl < r_end) {
-            const RInfo ri = rinfo[rl];
-            if (assign[rl] == h && ri.lg1 > tg0 && ri.lg0 < tg0 + FB_HIST_TILE_GROUPS) {
-                const int o = atomicAdd(&s_n, 1);  // order is irrelevant: integer adds commute
-                s_list[o] = make_uint4(ri.gbase, ri.lg0, ri.lg1, 0u);
+#pragma unroll
+        for (int x = 0; x < FB_HIST_LIST / FB_HIST_THREADS; ++x) {
+            const uint32_t rl = base + x * FB_HIST_THREADS + t;
+            if (rl < r_end) {
+                const RInfo ri = rinfo[rl];
+                if (assign[rl] == h && ri.lg1 > tg0 && ri.lg0 < tg0 + FB_HIST_TILE_GROUPS) {
+                    const int o = atomicAdd(&s_n, 1);  // order is irrelevant: integer adds commute
+                    s_list[o] = make_uint4(ri.gbase, ri.lg0, ri.lg1, 0u);
+                }
             }
         }
         __syncthreads();
         const int n = s_n;
-        // double-buffered batches: the loads of batch e0+4 are in flight while batch e0 is accumulated
-        uint32_t q[FB_HIST_BATCH], al[FB_HIST_BATCH], pr[FB_HIST_BATCH];
-        uint32_t qn[FB_HIST_BATCH], aln[FB_HIST_BATCH], prn[FB_HIST_BATCH];
-        auto load_batch = [&](int e0, uint32_t(&qq)[FB_HIST_BATCH], uint32_t(&aa)[FB_HIST_BATCH],
-                              uint32_t(&pp)[FB_HIST_BATCH]) {
+        // every warp takes FB_HIST_BATCH consecutive entries per round; their loads are issued together
+        for (int e0 = (int)warp * FB_HIST_BATCH; e0 < n; e0 += FB_HIST_WARPS * FB_HIST_BATCH) {
+            uint4 q[FB_HIST_BATCH];
+            uint32_t al[FB_HIST_BATCH], pr[FB_HIST_BATCH];
 #pragma unroll
             for (int b = 0; b < FB_HIST_BATCH; ++b) {
-                qq[b] = 0;
-                aa[b] = 0;
-                pp[b] = 0;
+                q[b] = make_uint4(0, 0, 0, 0);
+                al[b] = 0;
+                pr[b] = 0;
                 if (e0 + b < n) {
                     const uint4 en = s_list[e0 + b];
                     if (G >= en.y && G < en.z) {
                         const uint32_t g = en.x + G;
-                        qq[b] = qual32[(uint64_t)g * 4 + sub];
-                        aa[b] = a.fr.allele[g];
-                        pp[b] = a.fr.present[g];
+                        q[b] = a.fr.qual[g];
+                        al[b] = a.fr.allele[g];
+                        pr[b] = a.fr.present[g];
                     }
                 }
             }
-        };
-        load_batch(0, qn, aln, prn);
-        for (int e0 = 0; e0 < n; e0 += FB_HIST_BATCH) {
 #pragma unroll
             for (int b = 0; b < FB_HIST_BATCH; ++b) {
-                q[b] = qn[b];
-                al[b] = aln[b];
-                pr[b] = prn[b];
-            }
-            if (e0 + FB_HIST_BATCH < n) load_batch(e0 + FB_HIST_BATCH, qn, aln, prn);
+                const uint32_t P16 = pr[b] & flt16;
+                if (P16 == 0) continue;  // this lane's group is not covered by the read
+                const uint32_t A0 = al[b] & P16, A1 = (al[b] >> 16) & P16;
+                const uint32_t qq[4] = {q[b].x, q[b].y, q[b].z, q[b].w};
 #pragma unroll
-            for (int b = 0; b < FB_HIST_BATCH; ++b) {
-                const uint32_t P4 = (pr[b] >> (sub * 4)) & flt4;
-                if (P4 == 0) continue;  // this thread's four positions are not covered by the read
-                const uint32_t A0 = (al[b] >> (sub * 4)) & P4;
-                const uint32_t A1 = (al[b] >> (16 + sub * 4)) & P4;
-                uint32_t w[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) w[k] = lut_s[__byte_perm(q[b], 0, 0x4440 | k)];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (P4 & (1u << k)) t32[k] = fb_add_fma(t32[k], w[k], one);
-                    if (A0 & (1u << k)) c1[k] = fb_add_fma(c1[k], w[k], one);
+                for (int k = 0; k < 16; ++k) {
+                    const uint32_t w = lut_s[__byte_perm(qq[k >> 2], 0, 0x4440 | (k & 3))];
+                    if (P16 & (1u << k)) t32[k] = fb_add_fma(t32[k], w, one);
+                    if (A0 & (1u << k)) c1[k] = fb_add_fma(c1[k], w, one);
                 }
-                if (A1) {  // alleles 2/3 are rare: keep their bookkeeping off the common path
-                    const uint32_t A3 = A0 & A1;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (A1 & (1u << k)) c2[k] += w[k];
-                        if (A3 & (1u << k)) c3[k] += w[k];
+                if (A1) {  // alleles 2/3 are rare: straight to the shared tables
+                    for (uint32_t bits = A1; bits;) {
+                        const int k = __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        const unsigned long long w = lut_s[(qq[k >> 2] >> (8 * (k & 3))) & 0xFFu];
+                        atomicAdd(&tab[0][k * 32 + lane], w);
+                        if (A0 & (1u << k)) atomicAdd(&tab[1][k * 32 + lane], w);
                     }
                 }
-                // zero-weight keys: a cell whose weight is 0 still inserts its allele key (utils_frags.rs:165-166)
-                if (lut_zero && (lut_zero_only_q0 ? ((q[b] - 0x01010101u) & ~q[b] & 0x80808080u) != 0u : true)) {
+                // zero-weight keys: a cell whose weight is 0 still inserts its allele key (utils_frags.rs:165-166).
+                // When only q = 0 maps to weight 0 a zero-byte test of the quality words filters the common case.
+                if (lut_zero) {
+                    bool maybe = true;
+                    if (lut_zero_only_q0) {
+                        uint32_t z = 0;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if ((P4 & (1u << k)) && w[k] == 0)
-                            zf |= 1u << (k * 4 + (((A0 >> k) & 1u) | (((A1 >> k) & 1u) << 1)));
+                        for (int x = 0; x < 4; ++x) z |= (qq[x] - 0x01010101u) & ~qq[x] & 0x80808080u;
+                        maybe = z != 0;
+                    }
+                    if (maybe) {
+                        for (uint32_t bits = P16; bits;) {
+                            const int k = __ffs(bits) - 1;
+                            bits &= bits - 1;
+                            if (lut_s[(qq[k >> 2] >> (8 * (k & 3))) & 0xFFu] == 0)
+                                atomicOr(&zf_tab[k * 32 + lane], 1u << (((A0 >> k) & 1u) | (((A1 >> k) & 1u) << 1)));
+                        }
+                    }
                 }
             }
             since_flush += FB_HIST_BATCH;
             if (since_flush >= 28) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    T[k] += t32[k];
-                    C1[k] += c1[k];
-                    C2[k] += c2[k];
-                    C3[k] += c3[k];
-                    t32[k] = c1[k] = c2[k] = c3[k] = 0;
-                }
+                flush();
                 since_flush = 0;
             }
         }
@@ -604,33 +618,41 @@ __global__ void __launch_bounds__(FB_HIST_THREADS) k_hist(HistArgs a) {
         if (t == 0) s_n = 0;
         __syncthreads();
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        T[k] += t32[k];
-        C1[k] += c1[k];
-        C2[k] += c2[k];
-        C3[k] += c3[k];
-    }
-    // epilogue
-    const bool in_range = G < in.ng;
+    flush();
+    __syncthreads();
+    // epilogue: thread t finalises positions 2t and 2t+1 of the tile
+    const uint32_t eg = (uint32_t)t >> 3;            // group of the tile
+    const uint32_t ek = ((uint32_t)t & 7u) * 2;      // first of the two positions inside the group
+    const uint32_t EG = tg0 + eg;
+    const bool in_range = EG < in.ng;
     unsigned long long *out = reinterpret_cast<unsigned long long *>(a.cnt[buf] + in.cnt_off) +
-                              (((uint64_t)h * in.ng + G) * 16 + sub * 4) * 4;
-    unsigned long long c4[4][4];
+                              (((uint64_t)h * in.ng + EG) * 16 + ek) * 4;
+    unsigned long long c4[2][4];
+    uint32_t zf[2];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        c4[k][3] = C3[k];
-        c4[k][1] = C1[k] - C3[k];
-        c4[k][2] = C2[k] - C3[k];
-        c4[k][0] = T[k] - C1[k] - C2[k] + C3[k];
+    for (int x = 0; x < 2; ++x) {
+        const uint32_t idx = (ek + x) * 32 + eg;
+        unsigned long long T = 0, C1 = 0;
+#pragma unroll
+        for (int w8 = 0; w8 < FB_HIST_WARPS; ++w8) {
+            T += wtab[w8][0][idx];
+            C1 += wtab[w8][1][idx];
+        }
+        const unsigned long long C2 = tab[0][idx], C3 = tab[1][idx];
+        c4[x][3] = C3;
+        c4[x][1] = C1 - C3;
+        c4[x][2] = C2 - C3;
+        c4[x][0] = T - C1 - C2 + C3;
+        zf[x] = zf_tab[idx];
     }
     if (S > 1) {
         if (in_range) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
+            for (int x = 0; x < 2; ++x)
 #pragma unroll
                 for (int av = 0; av < 4; ++av) {
-                    if (c4[k][av]) atomicAdd(out + k * 4 + av, c4[k][av]);
-                    if (zf & (1u << (k * 4 + av))) atomicOr(out + k * 4 + av, FB_PRESENT);
+                    if (c4[x][av]) atomicAdd(out + x * 4 + av, c4[x][av]);
+                    if (zf[x] & (1u << av)) atomicOr(out + x * 4 + av, FB_PRESENT);
                 }
         }
         __threadfence();
@@ -644,45 +666,46 @@ __global__ void __launch_bounds__(FB_HIST_THREADS) k_hist(HistArgs a) {
         __threadfence();
         if (in_range) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const ulonglong2 x = __ldcg(reinterpret_cast<const ulonglong2 *>(out + k * 4));
-                const ulonglong2 y = __ldcg(reinterpret_cast<const ulonglong2 *>(out + k * 4) + 1);
-                c4[k][0] = x.x;
-                c4[k][1] = x.y;
-                c4[k][2] = y.x;
-                c4[k][3] = y.y;
+            for (int x = 0; x < 2; ++x) {
+                const ulonglong2 u = __ldcg(reinterpret_cast<const ulonglong2 *>(out + x * 4));
+                const ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2 *>(out + x * 4) + 1);
+                c4[x][0] = u.x;
+                c4[x][1] = u.y;
+                c4[x][2] = v.x;
+                c4[x][3] = v.y;
+                zf[x] = 0;  // presence of zero-weight keys already sits in bit 62
             }
         }
-        zf = 0;  // presence of zero-weight keys already sits in bit 62
     }
     uint32_t pl[4] = {0, 0, 0, 0};
     if (in_range) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int x = 0; x < 2; ++x) {
             unsigned long long mx = 0;
 #pragma unroll
             for (int av = 0; av < 4; ++av) {
-                unsigned long long v = c4[k][av] & FB_CNT_MASK;
-                if (v > 0 || (zf & (1u << (k * 4 + av)))) c4[k][av] |= FB_PRESENT;
+                const unsigned long long v = c4[x][av] & FB_CNT_MASK;
+                if (v > 0 || (zf[x] & (1u << av))) c4[x][av] |= FB_PRESENT;
                 mx = v > mx ? v : mx;
             }
-            reinterpret_cast<ulonglong2 *>(out + k * 4)[0] = make_ulonglong2(c4[k][0], c4[k][1]);
-            reinterpret_cast<ulonglong2 *>(out + k * 4)[1] = make_ulonglong2(c4[k][2], c4[k][3]);
+            reinterpret_cast<ulonglong2 *>(out + x * 4)[0] = make_ulonglong2(c4[x][0], c4[x][1]);
+            reinterpret_cast<ulonglong2 *>(out + x * 4)[1] = make_ulonglong2(c4[x][2], c4[x][3]);
             if (mx > 0) {
 #pragma unroll
                 for (int av = 0; av < 4; ++av)
-                    if ((c4[k][av] & FB_CNT_MASK) == mx) pl[av] |= 1u << (sub * 4 + k);
+                    if ((c4[x][av] & FB_CNT_MASK) == mx) pl[av] |= 1u << (ek + x);
             }
         }
     }
-    // combine the 4 threads of a group
+    // combine the 8 threads of a group
 #pragma unroll
     for (int av = 0; av < 4; ++av) {
         pl[av] |= __shfl_xor_sync(0xFFFFFFFFu, pl[av], 1);
         pl[av] |= __shfl_xor_sync(0xFFFFFFFFu, pl[av], 2);
+        pl[av] |= __shfl_xor_sync(0xFFFFFFFFu, pl[av], 4);
     }
-    if (in_range && sub == 0)
-        a.masks[buf][in.mask_off + (uint64_t)h * in.ng + G] = make_uint2(pl[0] | (pl[1] << 16), pl[2] | (pl[3] << 16));
+    if (in_range && (t & 7) == 0)
+        a.masks[buf][in.mask_off + (uint64_t)h * in.ng + EG] = make_uint2(pl[0] | (pl[1] << 16), pl[2] | (pl[3] << 16));
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -194,7 +194,8 @@ int fb_frags_upload(fb_ctx *ctx, const fb_frags *fr, fb_dfrags **out) {
         return rc;
     }
     cudaEvent_t e1 = fb_event(ctx);
-    cudaMemsetAsync(df->d_qual, 0, (ng + 1) * sizeof(uint4), ctx->stream);
+    // absent cells carry quality byte 0xFF (never read: masked by `present`), so a zero byte always is a real q = 0 cell
+    cudaMemsetAsync(df->d_qual, 0xFF, (ng + 1) * sizeof(uint4), ctx->stream);
     cudaMemsetAsync(df->d_allele, 0, (ng + 1) * sizeof(uint32_t), ctx->stream);
     cudaMemsetAsync(df->d_present, 0, (ng + 2) * sizeof(uint16_t), ctx->stream);
     cudaMemsetAsync(d_err, 0xFF, sizeof(unsigned long long), ctx->stream);
