@@ -148,6 +148,23 @@ __device__ __forceinline__ uint32_t fb_masked_sum_fma(const uint32_t (&w)[16], u
     return s;
 }
 
+// acc += w when (bits & m) != 0, as `and` + `setp` + a predicated add.  With the 16 tests of one bit word issued back to
+// back ptxas turns the tests into two R2P (7 predicates each) + two LOP3.P instead of 16 LOP3.P, and picks
+// IMAD.IADD / IADD3 for the adds to balance the FMA and ALU pipes (profiles/: the scoring kernels are bound by the ALU
+// pipe and by issue slots, not by HBM).
+__device__ __forceinline__ void fb_padd(uint32_t &acc, uint32_t bits, uint32_t m, uint32_t w) {
+    asm("{\n.reg .pred p;\n.reg .u32 t;\nand.b32 t, %1, %2;\nsetp.ne.u32 p, t, 0;\n@p add.u32 %0, %0, %3;\n}"
+        : "+r"(acc)
+        : "r"(bits), "r"(m), "r"(w));
+}
+// sum of w[k] over the set bits of `bits` (16 low bits), haplotype-outer / cell-inner order (see fb_padd)
+__device__ __forceinline__ uint32_t fb_masked_sum_p(const uint32_t (&w)[16], uint32_t bits) {
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) fb_padd(s, bits, 1u << k, w[k]);
+    return s;
+}
+
 // LUT weights of the 16 cells of a group WITHOUT zeroing absent cells (callers mask their bit sets with `present`)
 __device__ __forceinline__ void fb_group_weights_raw(uint4 q, const uint32_t *__restrict__ lut, uint32_t (&w)[16]) {
     const uint32_t qq[4] = {q.x, q.y, q.z, q.w};

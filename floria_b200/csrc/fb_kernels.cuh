@@ -188,7 +188,6 @@ __device__ void fb_sweep_body(const SweepArgs &a, const InstDev &in, int ii, uin
     const int cur = a.st[ii].cur;
     const uint2 *__restrict__ masks = a.masks[cur] + in.mask_off;
     const uint32_t g0 = a.fr.gptr[ri.rid], g1 = g0 + (ri.lg1 - ri.lg0);
-    const uint32_t one = a.one;
     // MOVES needs only `diff` per haplotype (opt_iterate); SCORE also reports `same`
     unsigned long long acc[P], emptyw[P], total = 0;  // acc = diff (MOVES) or same (SCORE) weight sums
     uint32_t ne_cnt[P];
@@ -198,53 +197,25 @@ __device__ void fb_sweep_body(const SweepArgs &a, const InstDev &in, int ii, uin
         emptyw[h] = 0;
         ne_cnt[h] = 0;
     }
-    // scoring of one 16-cell group against every haplotype
+    // scoring of one 16-cell group against every haplotype: the 16 LUT weights first, then haplotype by haplotype a
+    // masked sum over one bit word (fb_masked_sum_p: two R2P + 16 predicated adds per haplotype)
     auto score_group = [&](const uint4 q, const uint32_t al, const uint32_t pr, const uint32_t g) {
             const uint32_t lg = ri.lg0 + (g - g0);
-            // bit sets first (cells outer / haplotypes inner below keeps only one weight live: fewer registers, more warps)
-            uint32_t sel[P], ebs[P];
-            uint32_t any_e = 0;
+            uint32_t w[16];
+            fb_group_weights_raw(q, lut_s, w);
+            if (MODE == FB_SWEEP_SCORE) total += fb_masked_sum_p(w, pr);
 #pragma unroll
             for (int h = 0; h < P; ++h) {
                 const uint2 m = masks[(uint32_t)h * in.ng + lg];
                 uint32_t sb, ne;
                 fb_group_masks(al, m, sb, ne);
-                sel[h] = MODE == FB_SWEEP_SCORE ? (sb & pr) : (pr & ne & ~sb);
-                ebs[h] = pr & ~ne & 0xFFFFu;
-                any_e |= ebs[h];
-                ne_cnt[h] += __popc(ebs[h]);
-            }
-            uint32_t a32[P], e32[P], t32 = 0;
-#pragma unroll
-            for (int h = 0; h < P; ++h) {
-                a32[h] = 0;
-                e32[h] = 0;
-            }
-            const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const uint32_t w = lut_s[__byte_perm(qq[k >> 2], 0, 0x4440 | (k & 3))];
-                if (MODE == FB_SWEEP_SCORE) {
-                    if (pr & (1u << k)) t32 = fb_add_fma(t32, w, one);
+                const uint32_t sel = MODE == FB_SWEEP_SCORE ? (sb & pr) : (pr & ne & ~sb);
+                const uint32_t eb = pr & ~ne & 0xFFFFu;
+                acc[h] += fb_masked_sum_p(w, sel);
+                if (eb) {  // cells on positions the haplotype does not cover: rare inside a block
+                    ne_cnt[h] += __popc(eb);
+                    if (MODE == FB_SWEEP_SCORE) emptyw[h] += fb_masked_sum(w, eb);
                 }
-#pragma unroll
-                for (int h = 0; h < P; ++h)
-                    if (sel[h] & (1u << k)) a32[h] = fb_add_fma(a32[h], w, one);
-            }
-            if (MODE == FB_SWEEP_SCORE && any_e) {
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const uint32_t w = lut_s[__byte_perm(qq[k >> 2], 0, 0x4440 | (k & 3))];
-#pragma unroll
-                    for (int h = 0; h < P; ++h)
-                        if (ebs[h] & (1u << k)) e32[h] += w;
-                }
-            }
-            total += t32;
-#pragma unroll
-            for (int h = 0; h < P; ++h) {
-                acc[h] += a32[h];
-                emptyw[h] += e32[h];
             }
     };
     if (TMA) {
@@ -504,7 +475,6 @@ __global__ void __launch_bounds__(FB_HIST_THREADS) k_hist(HistArgs a) {
     const uint32_t G = tg0 + lane;                    // this lane's block-local group
     const uint32_t r_begin = (uint32_t)((uint64_t)in.n_reads * split / S);
     const uint32_t r_end = (uint32_t)((uint64_t)in.n_reads * (split + 1) / S);
-    const uint32_t one = a.one;
     // optional position filter (types_structs.rs:173: HapNode::new keeps positions inside snp_endpoints only)
     uint32_t flt16 = 0xFFFFu;
     if (in.flt_lo != 0 || in.flt_hi != 0xFFFFFFFFu) {
@@ -573,11 +543,18 @@ __global__ void __launch_bounds__(FB_HIST_THREADS) k_hist(HistArgs a) {
                 if (P16 == 0) continue;  // this lane's group is not covered by the read
                 const uint32_t A0 = al[b] & P16, A1 = (al[b] >> 16) & P16;
                 const uint32_t qq[4] = {q[b].x, q[b].y, q[b].z, q[b].w};
+                {
+                    uint32_t w[16];
+                    fb_group_weights_raw(q[b], lut_s, w);
+                    if (P16 == 0xFFFFu) {  // fully covered group (the common case): no tests for the totals
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const uint32_t w = lut_s[__byte_perm(qq[k >> 2], 0, 0x4440 | (k & 3))];
-                    if (P16 & (1u << k)) t32[k] = fb_add_fma(t32[k], w, one);
-                    if (A0 & (1u << k)) c1[k] = fb_add_fma(c1[k], w, one);
+                        for (int k = 0; k < 16; ++k) t32[k] += w[k];
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) fb_padd(t32[k], P16, 1u << k, w[k]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) fb_padd(c1[k], A0, 1u << k, w[k]);
                 }
                 if (A1) {  // alleles 2/3 are rare: straight to the shared tables
                     for (uint32_t bits = A1; bits;) {
