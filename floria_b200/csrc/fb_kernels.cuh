@@ -484,11 +484,12 @@ __global__ void __launch_bounds__(FB_HIST_THREADS) k_hist(HistArgs a) {
             if (pos >= in.flt_lo && pos <= in.flt_hi) flt16 |= 1u << k;
         }
     }
-    uint32_t t32[16], c1[16];
+    uint32_t t32[16], c1[16], c2[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
         t32[k] = 0;
         c1[k] = 0;
+        c2[k] = 0;
     }
     int since_flush = 0;
     __syncthreads();
@@ -498,8 +499,10 @@ __global__ void __launch_bounds__(FB_HIST_THREADS) k_hist(HistArgs a) {
         for (int k = 0; k < 16; ++k) {
             wtab[warp][0][k * 32 + lane] += (unsigned long long)t32[k];
             wtab[warp][1][k * 32 + lane] += (unsigned long long)c1[k];
+            if (c2[k]) atomicAdd(&tab[0][k * 32 + lane], (unsigned long long)c2[k]);
             t32[k] = 0;
             c1[k] = 0;
+            c2[k] = 0;
         }
     };
     for (uint32_t base = r_begin; base < r_end; base += FB_HIST_LIST) {
@@ -524,7 +527,7 @@ __global__ void __launch_bounds__(FB_HIST_THREADS) k_hist(HistArgs a) {
             uint32_t al[FB_HIST_BATCH], pr[FB_HIST_BATCH];
 #pragma unroll
             for (int b = 0; b < FB_HIST_BATCH; ++b) {
-                q[b] = make_uint4(0, 0, 0, 0);
+                q[b] = make_uint4(~0u, ~0u, ~0u, ~0u);  // uncovered: every bit word below is 0, the weights are unused
                 al[b] = 0;
                 pr[b] = 0;
                 if (e0 + b < n) {
@@ -540,7 +543,7 @@ __global__ void __launch_bounds__(FB_HIST_THREADS) k_hist(HistArgs a) {
 #pragma unroll
             for (int b = 0; b < FB_HIST_BATCH; ++b) {
                 const uint32_t P16 = pr[b] & flt16;
-                if (P16 == 0) continue;  // this lane's group is not covered by the read
+                if (__all_sync(0xFFFFFFFFu, P16 == 0)) continue;  // no lane's group is covered by the read (warp-uniform)
                 const uint32_t A0 = al[b] & P16, A1 = (al[b] >> 16) & P16;
                 const uint32_t qq[4] = {q[b].x, q[b].y, q[b].z, q[b].w};
                 {
@@ -555,14 +558,14 @@ __global__ void __launch_bounds__(FB_HIST_THREADS) k_hist(HistArgs a) {
                     }
 #pragma unroll
                     for (int k = 0; k < 16; ++k) fb_padd(c1[k], A0, 1u << k, w[k]);
-                }
-                if (A1) {  // alleles 2/3 are rare: straight to the shared tables
-                    for (uint32_t bits = A1; bits;) {
-                        const int k = __ffs(bits) - 1;
-                        bits &= bits - 1;
-                        const unsigned long long w = lut_s[(qq[k >> 2] >> (8 * (k & 3))) & 0xFFu];
-                        atomicAdd(&tab[0][k * 32 + lane], w);
-                        if (A0 & (1u << k)) atomicAdd(&tab[1][k * 32 + lane], w);
+                    if (__any_sync(0xFFFFFFFFu, A1 != 0)) {  // allele bit 1 (alleles 2/3): warp-uniform branch
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) fb_padd(c2[k], A1, 1u << k, w[k]);
+                        for (uint32_t bits = A1 & A0; bits;) {  // allele 3 is rare: straight to the shared table
+                            const int k = __ffs(bits) - 1;
+                            bits &= bits - 1;
+                            atomicAdd(&tab[1][k * 32 + lane], (unsigned long long)lut_s[(qq[k >> 2] >> (8 * (k & 3))) & 0xFFu]);
+                        }
                     }
                 }
                 // zero-weight keys: a cell whose weight is 0 still inserts its allele key (utils_frags.rs:165-166).
@@ -586,7 +589,7 @@ __global__ void __launch_bounds__(FB_HIST_THREADS) k_hist(HistArgs a) {
                 }
             }
             since_flush += FB_HIST_BATCH;
-            if (since_flush >= 28) {
+            if (since_flush >= 60) {  // 63 rows of weights <= 2^26 fit 32 bits
                 flush();
                 since_flush = 0;
             }
