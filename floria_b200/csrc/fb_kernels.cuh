@@ -706,17 +706,10 @@ struct MecArgs {
     int which, buf, only_active;
 };
 
-__device__ __forceinline__ void fb_sort4(unsigned long long (&v)[4], int n) {
-    // stable insertion sort ascending of the first n entries
-    for (int i = 1; i < n; ++i) {
-        unsigned long long x = v[i];
-        int j = i - 1;
-        while (j >= 0 && v[j] > x) {
-            v[j + 1] = v[j];
-            --j;
-        }
-        v[j + 1] = x;
-    }
+__device__ __forceinline__ void fb_cswap(unsigned long long &x, unsigned long long &y) {
+    const unsigned long long lo = x < y ? x : y, hi = x < y ? y : x;
+    x = lo;
+    y = hi;
 }
 
 __global__ void __launch_bounds__(256) k_mec(MecArgs a) {
@@ -727,68 +720,78 @@ __global__ void __launch_bounds__(256) k_mec(MecArgs a) {
     const InstDev in = a.inst[ii];
     if (a.only_active && !a.st[ii].active) return;
     const uint32_t h = (uint32_t)(wid - a.hap_prefix[ii]);
-    const int cur = a.st[ii].cur;
-    const int buf = a.which == 0 ? cur : (a.which == 1 ? (cur ^ 1) : a.buf);
+    const int cur_buf = a.st[ii].cur;
+    const int buf = a.which == 0 ? cur_buf : (a.which == 1 ? (cur_buf ^ 1) : a.buf);
     const ulonglong2 *__restrict__ c2 =
         reinterpret_cast<const ulonglong2 *>(a.cnt[buf] + in.cnt_off + (uint64_t)h * in.ng * 64);
     const uint32_t npos = in.ng * 16;
     SeqSum bases, errors;
     bases.init();
     errors.init();
+    ulonglong2 x_n = make_ulonglong2(0ULL, 0ULL), y_n = x_n;
+    if (lane < npos) {
+        x_n = c2[(uint64_t)lane * 2];
+        y_n = c2[(uint64_t)lane * 2 + 1];
+    }
     for (uint32_t p0 = 0; p0 < npos; p0 += 32) {
-        const uint32_t p = p0 + lane;
-        unsigned long long v[4];
-        int n = 0;
-        if (p < npos) {
-            ulonglong2 x = c2[(uint64_t)p * 2], y = c2[(uint64_t)p * 2 + 1];
-            unsigned long long c[4] = {x.x, x.y, y.x, y.y};
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (c[k] & FB_PRESENT) v[n++] = c[k] & FB_CNT_MASK;  // allele_counts (keys present), ascending allele
+        const ulonglong2 x = x_n, y = y_n;
+        {  // next chunk's counts are in flight while this one is folded into the sums
+            const uint32_t pn = p0 + 32 + lane;
+            x_n = make_ulonglong2(0ULL, 0ULL);
+            y_n = x_n;
+            if (pn < npos) {
+                x_n = c2[(uint64_t)pn * 2];
+                y_n = c2[(uint64_t)pn * 2 + 1];
+            }
         }
-        for (int k = n; k < 4; ++k) v[k] = 0;
-        fb_sort4(v, n);  // allele_counts.sort_by(count): stable, ascending
-        long long mx = n ? (long long)v[n - 1] : 0;
-        long long others = 0;
-        for (int k = 0; k + 1 < n; ++k) others += (long long)v[k];
-        const bool has_eps = n > 0 && mx <= (1LL << 26);  // cons_bases <= 1.0
-        const unsigned any = __ballot_sync(0xFFFFFFFFu, n > 0);
-        if (!any) continue;
+        // allele_counts (keys present) sorted ascending by count (local_clustering.rs:229-236).  An absent key holds 0
+        // and adding 0.0 changes nothing, so all four words go through a sorting network as items.
+        const bool anyp = ((x.x | x.y | y.x | y.y) & FB_PRESENT) != 0;
+        unsigned long long v0 = x.x & FB_CNT_MASK, v1 = x.y & FB_CNT_MASK, v2 = y.x & FB_CNT_MASK, v3 = y.y & FB_CNT_MASK;
+        fb_cswap(v0, v1);
+        fb_cswap(v2, v3);
+        fb_cswap(v0, v2);
+        fb_cswap(v1, v3);
+        fb_cswap(v1, v2);
+        const long long mx = (long long)v3;                  // cons_bases
+        const long long others = (long long)(v0 + v1 + v2);  // the non-consensus counts, added in ascending order
+        const bool has_eps = anyp && mx <= (1LL << 26);      // cons_bases <= 1.0
+        if (!__ballot_sync(0xFFFFFFFFu, anyp)) continue;
         // bases: one dyadic item per position
         {
-            long long tot = (long long)fb_warp_sum_u64((unsigned long long)mx);
+            const long long tot = (long long)fb_warp_sum_u64((unsigned long long)mx);
             if (!bases.add_dyadic_run(tot)) {
-                for (int l = 0; l < 32; ++l) {
-                    long long m_l = __shfl_sync(0xFFFFFFFFu, mx, l);
-                    int n_l = __shfl_sync(0xFFFFFFFFu, n, l);
-                    if (n_l) bases.add_dyadic(m_l);
-                }
+                for (int l = 0; l < 32; ++l) bases.add_dyadic(__shfl_sync(0xFFFFFFFFu, mx, l));
             }
         }
-        // errors: up to 3 dyadic items then an optional epsilon per position
+        // errors: per position up to 3 dyadic items then an optional epsilon.  Runs of lanes between two epsilon items
+        // are added as one exact lump (prefix sums) whenever SeqSum proves that identical to item-by-item addition.
         {
-            const unsigned anyE = __ballot_sync(0xFFFFFFFFu, has_eps);
-            bool done = false;
-            if (!anyE) {
-                long long tot = (long long)fb_warp_sum_u64((unsigned long long)others);
-                done = errors.add_dyadic_run(tot);
+            long long pre = others;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long t = __shfl_up_sync(0xFFFFFFFFu, pre, o);
+                if ((int)lane >= o) pre += t;
             }
-            if (!done) {
-                for (int l = 0; l < 32; ++l) {
-                    int n_l = __shfl_sync(0xFFFFFFFFu, n, l);
-                    long long o_l = __shfl_sync(0xFFFFFFFFu, others, l);
-                    long long v0 = __shfl_sync(0xFFFFFFFFu, (long long)v[0], l);
-                    long long v1 = __shfl_sync(0xFFFFFFFFu, (long long)v[1], l);
-                    long long v2 = __shfl_sync(0xFFFFFFFFu, (long long)v[2], l);
-                    int e_l = __shfl_sync(0xFFFFFFFFu, (int)has_eps, l);
-                    if (n_l == 0) continue;
-                    if (!errors.add_dyadic_run(o_l)) {
-                        if (n_l > 1) errors.add_dyadic(v0);
-                        if (n_l > 2) errors.add_dyadic(v1);
-                        if (n_l > 3) errors.add_dyadic(v2);
+            const unsigned E = __ballot_sync(0xFFFFFFFFu, has_eps);
+            int cur = 0;
+            while (cur < 32) {
+                const unsigned rest = E >> cur;
+                const int e = rest ? cur + __ffs(rest) - 1 : 31;  // last lane of the run (its epsilon, if any, follows)
+                const long long hi_sum = __shfl_sync(0xFFFFFFFFu, pre, e);
+                const long long lo_sum = cur ? __shfl_sync(0xFFFFFFFFu, pre, cur - 1) : 0;
+                if (!errors.add_dyadic_run(hi_sum - lo_sum)) {
+                    for (int l = cur; l <= e; ++l) {
+                        const long long o_l = __shfl_sync(0xFFFFFFFFu, others, l);
+                        if (errors.add_dyadic_run(o_l)) continue;
+                        errors.add_dyadic((long long)__shfl_sync(0xFFFFFFFFu, v0, l));
+                        errors.add_dyadic((long long)__shfl_sync(0xFFFFFFFFu, v1, l));
+                        errors.add_dyadic((long long)__shfl_sync(0xFFFFFFFFu, v2, l));
                     }
-                    if (e_l) errors.add_eps(a.eps, a.eps_safe);
                 }
+                if (!rest) break;
+                errors.add_eps(a.eps, a.eps_safe);
+                cur = e + 1;
             }
         }
     }
