@@ -378,11 +378,15 @@ __global__ void __launch_bounds__(FB_SWEEP_WARPS * 32) k_sweep(SweepArgs a) {
 
 // ---------------------------------------------------------------------------------------------------------------------
 // K2 hap_histogram.  One CTA per (instance, tile of 512 positions, haplotype, read split).  Lane l of every warp owns
-// group l of the tile (16 positions); the 8 warps take the matching reads round-robin, four reads in flight per warp,
-// each read row arriving as fully coalesced 512 B (quals) + 128 B (alleles) + 64 B (presence) per warp.  Per position a
-// lane keeps 32-bit partial sums T (all alleles) and C1 (allele bit 0 set) in registers and flushes them every 28 rows
-// into 64-bit tables in shared memory (layout [k][lane]: conflict free); alleles 2/3 and zero-weight keys are rare and
-// go straight to shared-memory atomics.  n3 = C3, n1 = C1-C3, n2 = C2-C3, n0 = T-C1-C2+C3.
+// group l of the tile (16 positions); the 8 warps take the matching reads round-robin.  A read's slice of the tile
+// is staged into a per-warp ring of shared-memory stages by cp.async (LDGSTS: every lane copies its own group's 16 B of
+// quals, 4 B of alleles and the 4-byte word holding its 2 B of presence into a lane-private slot) several rows ahead,
+// so the row loads cost no registers and stay in flight while earlier rows are accumulated.  (A 1-D TMA bulk-copy
+// variant of the same ring was measured slower: three UBLKCP per row cost ~60 issue slots of address set-up, see
+// profiles/.)  Per position a lane keeps 32-bit partial sums T (all alleles), C1 (allele bit 0 set) and C2 (allele
+// bit 1 set) in registers (fb_padd: R2P-unpacked predicates) and flushes them every 60 rows into 64-bit tables in
+// shared memory held as two 32-bit halves (native 32-bit shared atomics, carry into the high half); allele 3 and
+// zero-weight keys are rare and go straight to shared-memory atomics.  n3 = C3, n1 = C1-C3, n2 = C2-C3, n0 = T-C1-C2+C3.
 // With several read splits per (tile, haplotype) the partial tables are merged with 64-bit global atomics (exact integer
 // adds: deterministic) and the last CTA to finish derives the is-max planes.
 // Reproduces utils_frags.rs:160-184 set_to_seq_dict / hap_block_from_partition; the planes are the consensus test of
@@ -391,9 +395,29 @@ __global__ void __launch_bounds__(FB_SWEEP_WARPS * 32) k_sweep(SweepArgs a) {
 #define FB_HIST_THREADS 256
 #define FB_HIST_WARPS 8
 #define FB_HIST_TILE_GROUPS 32  // 512 positions
-#define FB_HIST_LIST 1024
-#define FB_HIST_BATCH 4
-#define FB_HIST_SMEM ((FB_HIST_WARPS * 2 + 2) * 512 * 8)
+#define FB_HIST_LIST 512
+#define FB_HIST_STAGES 4
+
+struct __align__(16) HistStage {
+    uint4 qual[32];       // lane-private slots
+    uint32_t allele[32];
+    uint32_t present[32];  // the aligned 4-byte word holding the lane's 16-bit presence mask
+};
+// dynamic shared memory: T, C1, C2, C3 tables as [table][lo|hi][512] 32-bit words, then the per-warp stage rings
+#define FB_HIST_TAB_BYTES (4 * 2 * 512 * 4)
+#define FB_HIST_SMEM (FB_HIST_TAB_BYTES + FB_HIST_WARPS * FB_HIST_STAGES * (int)sizeof(HistStage))
+
+__device__ __forceinline__ void fb_cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(fb_smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void fb_cp_async4(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(fb_smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void fb_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void fb_cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 
 struct HistArgs {
     DFragsDev fr;
@@ -431,23 +455,30 @@ __global__ void k_hist_zero(HistArgs a) {
         p[x] = make_ulonglong2(0ULL, 0ULL);
 }
 
-__global__ void __launch_bounds__(FB_HIST_THREADS) k_hist(HistArgs a) {
+// 64-bit add into a (lo, hi) pair of 32-bit shared-memory words
+__device__ __forceinline__ void fb_tab_add(uint32_t *lo, uint32_t *hi, uint32_t idx, uint32_t v) {
+    if (v) {
+        const uint32_t old = atomicAdd(&lo[idx], v);
+        if (old > ~v) atomicAdd(&hi[idx], 1u);
+    }
+}
+
+__global__ void __launch_bounds__(FB_HIST_THREADS, 2) k_hist(HistArgs a) {
     __shared__ uint32_t lut_s[256];
     __shared__ uint4 s_list[FB_HIST_LIST];
-    // dynamic shared memory: per-warp private 64-bit tables T, C1 (no atomics on the flush path) + shared C2, C3
-    extern __shared__ __align__(16) unsigned long long hist_dyn[];
-    unsigned long long(*wtab)[2][512] = reinterpret_cast<unsigned long long(*)[2][512]>(hist_dyn);  // [warp][T|C1][k*32+lane]
-    unsigned long long(*tab)[512] = reinterpret_cast<unsigned long long(*)[512]>(hist_dyn + FB_HIST_WARPS * 2 * 512);  // C2, C3
-    __shared__ uint32_t zf_tab[512];            // bit a: a zero-weight cell inserted allele key a
+    extern __shared__ __align__(128) uint8_t hist_dyn[];
+    uint32_t(*tab)[2][512] = reinterpret_cast<uint32_t(*)[2][512]>(hist_dyn);  // [T|C1|C2|C3][lo|hi][k*32+lane]
+    __shared__ uint32_t zf_tab[512];  // bit a: a zero-weight cell inserted allele key a
     __shared__ int s_n, s_last, s_zero_any, s_zero_other;
     const int t = threadIdx.x;
     const uint32_t lane = t & 31, warp = t >> 5;
+    HistStage *stg = reinterpret_cast<HistStage *>(hist_dyn + FB_HIST_TAB_BYTES) + warp * FB_HIST_STAGES;
     if (t == 0) {
         s_n = 0;
         s_zero_any = 0;
         s_zero_other = 0;
     }
-    for (int i = t; i < (FB_HIST_WARPS * 2 + 2) * 512; i += FB_HIST_THREADS) hist_dyn[i] = 0ULL;
+    for (int i = t; i < FB_HIST_TAB_BYTES / 4; i += FB_HIST_THREADS) reinterpret_cast<uint32_t *>(hist_dyn)[i] = 0u;
     for (int i = t; i < 512; i += FB_HIST_THREADS) zf_tab[i] = 0;
     __syncthreads();
     for (int i = t; i < 256; i += FB_HIST_THREADS) {
@@ -492,18 +523,33 @@ __global__ void __launch_bounds__(FB_HIST_THREADS) k_hist(HistArgs a) {
         c2[k] = 0;
     }
     int since_flush = 0;
+    uint32_t it0 = 0;  // rows this warp has pushed through its stage ring so far (stage = it % STAGES, parity = it / STAGES)
     __syncthreads();
     const bool lut_zero = s_zero_any != 0, lut_zero_only_q0 = s_zero_other == 0;
     auto flush = [&]() {
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            wtab[warp][0][k * 32 + lane] += (unsigned long long)t32[k];
-            wtab[warp][1][k * 32 + lane] += (unsigned long long)c1[k];
-            if (c2[k]) atomicAdd(&tab[0][k * 32 + lane], (unsigned long long)c2[k]);
+            const uint32_t idx = k * 32 + lane;
+            fb_tab_add(tab[0][0], tab[0][1], idx, t32[k]);
+            fb_tab_add(tab[1][0], tab[1][1], idx, c1[k]);
+            fb_tab_add(tab[2][0], tab[2][1], idx, c2[k]);
             t32[k] = 0;
             c1[k] = 0;
             c2[k] = 0;
         }
+    };
+    // every lane: start the copies of its group of list entry e into its slot of stage `it % STAGES` (one commit group
+    // per row, also when the lane has nothing to copy, so that the group counts of all lanes agree)
+    auto issue = [&](uint32_t e, uint32_t it) {
+        const uint4 en = s_list[e];
+        if (G >= en.y && G < en.z) {
+            HistStage &sg = stg[it % FB_HIST_STAGES];
+            const uint32_t g = en.x + G;
+            fb_cp_async16(&sg.qual[lane], a.fr.qual + g);
+            fb_cp_async4(&sg.allele[lane], a.fr.allele + g);
+            fb_cp_async4(&sg.present[lane], a.fr.present + (g & ~1u));
+        }
+        fb_cp_async_commit();
     };
     for (uint32_t base = r_begin; base < r_end; base += FB_HIST_LIST) {
         // reads are sorted by first position: once a chunk starts right of the tile, nothing later overlaps it
@@ -520,80 +566,79 @@ __global__ void __launch_bounds__(FB_HIST_THREADS) k_hist(HistArgs a) {
             }
         }
         __syncthreads();
-        const int n = s_n;
-        // every warp takes FB_HIST_BATCH consecutive entries per round; their loads are issued together
-        for (int e0 = (int)warp * FB_HIST_BATCH; e0 < n; e0 += FB_HIST_WARPS * FB_HIST_BATCH) {
-            uint4 q[FB_HIST_BATCH];
-            uint32_t al[FB_HIST_BATCH], pr[FB_HIST_BATCH];
+        const uint32_t n = (uint32_t)s_n;
+        const uint32_t cnt_w = n > warp ? (n - warp + FB_HIST_WARPS - 1) / FB_HIST_WARPS : 0u;  // entries warp, warp+8, ...
+        // prologue: FB_HIST_STAGES - 1 rows in flight (empty commit groups pad a short list)
 #pragma unroll
-            for (int b = 0; b < FB_HIST_BATCH; ++b) {
-                q[b] = make_uint4(~0u, ~0u, ~0u, ~0u);  // uncovered: every bit word below is 0, the weights are unused
-                al[b] = 0;
-                pr[b] = 0;
-                if (e0 + b < n) {
-                    const uint4 en = s_list[e0 + b];
-                    if (G >= en.y && G < en.z) {
-                        const uint32_t g = en.x + G;
-                        q[b] = a.fr.qual[g];
-                        al[b] = a.fr.allele[g];
-                        pr[b] = a.fr.present[g];
+        for (uint32_t i = 0; i < FB_HIST_STAGES - 1; ++i) {
+            if (i < cnt_w)
+                issue(warp + i * FB_HIST_WARPS, it0 + i);
+            else
+                fb_cp_async_commit();
+        }
+        for (uint32_t i = 0; i < cnt_w; ++i) {
+            const uint32_t it = it0 + i;
+            // keep the ring full: row i + STAGES - 1 goes into the stage consumed in the previous iteration
+            if (i + FB_HIST_STAGES - 1 < cnt_w)
+                issue(warp + (i + FB_HIST_STAGES - 1) * FB_HIST_WARPS, it + FB_HIST_STAGES - 1);
+            else
+                fb_cp_async_commit();
+            fb_cp_async_wait<FB_HIST_STAGES - 1>();  // this lane's copies of row i have landed (slots are lane-private)
+            const uint4 en = s_list[warp + i * FB_HIST_WARPS];
+            const HistStage &sg = stg[it % FB_HIST_STAGES];
+            uint4 q = make_uint4(~0u, ~0u, ~0u, ~0u);  // uncovered group: every bit word below is 0, the weights are unused
+            uint32_t al = 0, pr = 0;
+            if (G >= en.y && G < en.z) {
+                q = sg.qual[lane];
+                al = sg.allele[lane];
+                pr = (sg.present[lane] >> (16u * ((en.x + G) & 1u))) & 0xFFFFu;
+            }
+            const uint32_t P16 = pr & flt16;
+            const uint32_t A0 = al & P16, A1 = (al >> 16) & P16;
+            const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
+            {
+                uint32_t w[16];
+                fb_group_weights_raw(q, lut_s, w);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) fb_padd(t32[k], P16, 1u << k, w[k]);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) fb_padd(c1[k], A0, 1u << k, w[k]);
+                if (__any_sync(0xFFFFFFFFu, A1 != 0)) {  // allele bit 1 (alleles 2/3): warp-uniform branch
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) fb_padd(c2[k], A1, 1u << k, w[k]);
+                    for (uint32_t bits = A1 & A0; bits;) {  // allele 3 is rare: straight to the shared table
+                        const int k = __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        fb_tab_add(tab[3][0], tab[3][1], k * 32 + lane, lut_s[(qq[k >> 2] >> (8 * (k & 3))) & 0xFFu]);
                     }
                 }
             }
+            // zero-weight keys: a cell whose weight is 0 still inserts its allele key (utils_frags.rs:165-166).
+            // When only q = 0 maps to weight 0 a zero-byte test of the quality words filters the common case.
+            if (lut_zero) {
+                bool maybe = true;
+                if (lut_zero_only_q0) {
+                    uint32_t z = 0;
 #pragma unroll
-            for (int b = 0; b < FB_HIST_BATCH; ++b) {
-                const uint32_t P16 = pr[b] & flt16;
-                if (__all_sync(0xFFFFFFFFu, P16 == 0)) continue;  // no lane's group is covered by the read (warp-uniform)
-                const uint32_t A0 = al[b] & P16, A1 = (al[b] >> 16) & P16;
-                const uint32_t qq[4] = {q[b].x, q[b].y, q[b].z, q[b].w};
-                {
-                    uint32_t w[16];
-                    fb_group_weights_raw(q[b], lut_s, w);
-                    if (P16 == 0xFFFFu) {  // fully covered group (the common case): no tests for the totals
-#pragma unroll
-                        for (int k = 0; k < 16; ++k) t32[k] += w[k];
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 16; ++k) fb_padd(t32[k], P16, 1u << k, w[k]);
-                    }
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) fb_padd(c1[k], A0, 1u << k, w[k]);
-                    if (__any_sync(0xFFFFFFFFu, A1 != 0)) {  // allele bit 1 (alleles 2/3): warp-uniform branch
-#pragma unroll
-                        for (int k = 0; k < 16; ++k) fb_padd(c2[k], A1, 1u << k, w[k]);
-                        for (uint32_t bits = A1 & A0; bits;) {  // allele 3 is rare: straight to the shared table
-                            const int k = __ffs(bits) - 1;
-                            bits &= bits - 1;
-                            atomicAdd(&tab[1][k * 32 + lane], (unsigned long long)lut_s[(qq[k >> 2] >> (8 * (k & 3))) & 0xFFu]);
-                        }
-                    }
+                    for (int x = 0; x < 4; ++x) z |= (qq[x] - 0x01010101u) & ~qq[x] & 0x80808080u;
+                    maybe = z != 0;
                 }
-                // zero-weight keys: a cell whose weight is 0 still inserts its allele key (utils_frags.rs:165-166).
-                // When only q = 0 maps to weight 0 a zero-byte test of the quality words filters the common case.
-                if (lut_zero) {
-                    bool maybe = true;
-                    if (lut_zero_only_q0) {
-                        uint32_t z = 0;
-#pragma unroll
-                        for (int x = 0; x < 4; ++x) z |= (qq[x] - 0x01010101u) & ~qq[x] & 0x80808080u;
-                        maybe = z != 0;
-                    }
-                    if (maybe) {
-                        for (uint32_t bits = P16; bits;) {
-                            const int k = __ffs(bits) - 1;
-                            bits &= bits - 1;
-                            if (lut_s[(qq[k >> 2] >> (8 * (k & 3))) & 0xFFu] == 0)
-                                atomicOr(&zf_tab[k * 32 + lane], 1u << (((A0 >> k) & 1u) | (((A1 >> k) & 1u) << 1)));
-                        }
+                if (maybe) {
+                    for (uint32_t bits = P16; bits;) {
+                        const int k = __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        if (lut_s[(qq[k >> 2] >> (8 * (k & 3))) & 0xFFu] == 0)
+                            atomicOr(&zf_tab[k * 32 + lane], 1u << (((A0 >> k) & 1u) | (((A1 >> k) & 1u) << 1)));
                     }
                 }
             }
-            since_flush += FB_HIST_BATCH;
-            if (since_flush >= 60) {  // 63 rows of weights <= 2^26 fit 32 bits
+            if (++since_flush >= 60) {  // 63 rows of weights <= 2^26 fit 32 bits
                 flush();
                 since_flush = 0;
             }
         }
+        it0 += cnt_w;
+        fb_cp_async_wait<0>();
         __syncthreads();
         if (t == 0) s_n = 0;
         __syncthreads();
@@ -612,13 +657,10 @@ __global__ void __launch_bounds__(FB_HIST_THREADS) k_hist(HistArgs a) {
 #pragma unroll
     for (int x = 0; x < 2; ++x) {
         const uint32_t idx = (ek + x) * 32 + eg;
-        unsigned long long T = 0, C1 = 0;
-#pragma unroll
-        for (int w8 = 0; w8 < FB_HIST_WARPS; ++w8) {
-            T += wtab[w8][0][idx];
-            C1 += wtab[w8][1][idx];
-        }
-        const unsigned long long C2 = tab[0][idx], C3 = tab[1][idx];
+        const unsigned long long T = tab[0][0][idx] | ((unsigned long long)tab[0][1][idx] << 32);
+        const unsigned long long C1 = tab[1][0][idx] | ((unsigned long long)tab[1][1][idx] << 32);
+        const unsigned long long C2 = tab[2][0][idx] | ((unsigned long long)tab[2][1][idx] << 32);
+        const unsigned long long C3 = tab[3][0][idx] | ((unsigned long long)tab[3][1][idx] << 32);
         c4[x][3] = C3;
         c4[x][1] = C1 - C3;
         c4[x][2] = C2 - C3;
