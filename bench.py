@@ -244,14 +244,17 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
+    # rank 0 samples its GPU's clocks during the timed region (NVML in every rank at once was measured to slow the
+    # host side of all ranks: the queries serialise in the driver)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
-    sampler.start()
+    if sampler:
+        sampler.start()
     t_before = ctx.timings()
     ev, cells, res = one_pass(resident, args.steps, True)
     t_after = ctx.timings()
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     my_ms = sum(ev)
     barrier()
     ev2, cells2, res2 = one_pass(e2e_fn, args.steps, True)
