@@ -99,6 +99,8 @@ def load_library():
                                        C.c_double, u8p, u8p, u8p, C.POINTER(C.c_void_p)]
     L.fb_bench_sweep_hist.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, u8p, C.POINTER(FbParams), C.c_uint32,
                                       C.POINTER(C.c_float), C.POINTER(C.c_float), u64p]
+    L.fb_bench_block_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, u8p, C.POINTER(FbParams), u64p, u64p, i64p,
+                                        i64p, u32p]
     L.fb_bench_download_planes.argtypes = [C.c_void_p, C.c_void_p, u64p, u8p, u32p, C.POINTER(C.c_uint16)]
     _lib = L
     return L
@@ -219,6 +221,23 @@ class Context:
                                              sw.ctypes.data_as(C.POINTER(C.c_float)),
                                              hs.ctypes.data_as(C.POINTER(C.c_float)), C.byref(cells)))
         return sw, hs, int(cells.value)
+
+    def bench_block_tables(self, dfrags, ploidy, hap, params):
+        """raw k_hist count words [ploidy, n_pos, 4] and SCORE-mode sweep sums (same_q26, diff_q26, n_empty) of one block
+        made of all reads of a resident contig (full-size property tests)."""
+        hap = np.ascontiguousarray(hap, np.uint8)
+        npos = C.c_uint64(0)
+        self._chk(self.L.fb_bench_block_tables(self.h, dfrags.handle, ploidy, ptr(hap, u8p), C.byref(params),
+                                               C.byref(npos), None, None, None, None))
+        n_pos, n = int(npos.value), len(hap)
+        counts = np.zeros((ploidy, n_pos, 4), np.uint64)
+        sq = np.zeros((n, ploidy), np.int64)
+        dq = np.zeros((n, ploidy), np.int64)
+        ne = np.zeros((n, ploidy), np.uint32)
+        self._chk(self.L.fb_bench_block_tables(self.h, dfrags.handle, ploidy, ptr(hap, u8p), C.byref(params),
+                                               C.byref(npos), ptr(counts, u64p), ptr(sq, i64p), ptr(dq, i64p),
+                                               ptr(ne, u32p)))
+        return counts, sq, dq, ne
 
     def download_planes(self, dfrags):
         ng = C.c_uint64(0)

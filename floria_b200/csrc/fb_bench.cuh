@@ -150,6 +150,55 @@ int fb_bench_sweep_hist(fb_ctx *ctx, const fb_dfrags *df, uint32_t ploidy, const
     return FB_OK;
 }
 
+int fb_bench_block_tables(fb_ctx *ctx, const fb_dfrags *df, uint32_t ploidy, const uint8_t *hap, const fb_params *prm,
+                          uint64_t *n_pos, uint64_t *counts, int64_t *same_q26, int64_t *diff_q26, uint32_t *n_empty) {
+    if (!ctx) return FB_ERR_ARG;
+    if (!df || !hap || !prm) FB_FAIL(FB_ERR_ARG, "null argument");
+    FB_CK(cudaSetDevice(ctx->device));
+    ctx->ev_used = 0;
+    int rc = fb_check_params(ctx, prm, ploidy);
+    if (rc) return rc;
+    Engine e;
+    e.ctx = ctx;
+    e.df = df;
+    std::vector<uint32_t> reads(df->n_reads);
+    for (uint64_t i = 0; i < df->n_reads; ++i) reads[i] = (uint32_t)i;
+    int b = e.add_block(reads);
+    e.add_instance(b, ploidy);
+    if ((rc = e.finalize_and_upload(prm->epsilon))) return rc;
+    const uint64_t npos = (uint64_t)e.inst[0].ng * 16;
+    if (n_pos) *n_pos = npos;
+    if (!counts && !same_q26 && !diff_q26 && !n_empty) return FB_OK;  // size query
+    FB_CK(cudaMemcpyAsync(e.d_assign[0], hap, df->n_reads, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = e.launch_sizes(0))) return rc;
+    if ((rc = e.launch_hist(0, 1, 0))) return rc;
+    if (counts) FB_CK(cudaMemcpyAsync(counts, e.d_cnt[0], e.tot_cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    const uint64_t n = df->n_reads * (uint64_t)ploidy;
+    long long *d_sq = nullptr, *d_dq = nullptr;
+    uint32_t *d_ne = nullptr;
+    if ((rc = fb_dalloc(ctx, &d_sq, n)) || (rc = fb_dalloc(ctx, &d_dq, n)) || (rc = fb_dalloc(ctx, &d_ne, n))) return rc;
+    SweepArgs a = e.sweep_args(FB_SWEEP_SCORE);
+    a.o_same_q26 = d_sq;
+    a.o_diff_q26 = d_dq;
+    a.o_nempty = d_ne;
+    rc = e.launch_sweep(a);
+    if (!rc) {
+        if (same_q26) cudaMemcpyAsync(same_q26, d_sq, n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (diff_q26) cudaMemcpyAsync(diff_q26, d_dq, n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (n_empty) cudaMemcpyAsync(n_empty, d_ne, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+        if (ce == cudaSuccess) ce = cudaGetLastError();
+        if (ce != cudaSuccess) {
+            ctx->err = std::string("fb_bench_block_tables: ") + cudaGetErrorString(ce);
+            rc = FB_ERR_CUDA;
+        }
+    }
+    fb_cache_free(d_sq);
+    fb_cache_free(d_dq);
+    fb_cache_free(d_ne);
+    return rc;
+}
+
 int fb_bench_download_planes(fb_ctx *ctx, const fb_dfrags *df, uint64_t *n_groups, uint8_t *qual, uint32_t *allele,
                              uint16_t *present) {
     if (!ctx) return FB_ERR_ARG;

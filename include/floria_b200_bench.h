@@ -24,6 +24,14 @@ int fb_bench_synth_dense(fb_ctx *, uint64_t n_reads, uint32_t n_snps, uint32_t p
 int fb_bench_sweep_hist(fb_ctx *, const fb_dfrags *df, uint32_t ploidy, const uint8_t *hap, const fb_params *,
                         uint32_t iters, float *sweep_ms, float *hist_ms, uint64_t *cells);
 
+/* Test: one block made of ALL reads of `df` with partition `hap`: the raw count table of k_hist
+ * ([ploidy][n_pos][4] words, value in the low 62 bits in units of 2^-26, bit 62 = allele key present) and the
+ * SCORE-mode sweep of every read against every haplotype (same / diff weight sums in units of 2^-26, number of cells on
+ * empty positions; each [n_reads][ploidy]).  With all output pointers NULL only *n_pos is returned (size query).
+ * Used by the full-size property tests (checksums that tie k_hist to k_sweep, linearity in the partition). */
+int fb_bench_block_tables(fb_ctx *, const fb_dfrags *df, uint32_t ploidy, const uint8_t *hap, const fb_params *,
+                          uint64_t *n_pos, uint64_t *counts, int64_t *same_q26, int64_t *diff_q26, uint32_t *n_empty);
+
 /* Debug/test: copy the packed planes of a resident contig back to the host (any pointer may be NULL). */
 int fb_bench_download_planes(fb_ctx *, const fb_dfrags *df, uint64_t *n_groups, uint8_t *qual /*[16*ng]*/,
                              uint32_t *allele /*[ng]*/, uint16_t *present /*[ng]*/);

@@ -22,6 +22,11 @@ def test_library_exports_every_declared_symbol():
     L = api.load_library()
     for name in sorted(declared):
         assert hasattr(L, name), f"{name} is declared in include/floria_b200.h but not exported"
+    # every other header under include/ (measurement helpers) must resolve too
+    for h in sorted(os.listdir(os.path.join(ROOT, "include"))):
+        if h.endswith(".h") and h != "floria_b200.h":
+            for name in set(re.findall(r"\b(fb_[a-z_0-9]+)\s*\(", open(os.path.join(ROOT, "include", h)).read())):
+                assert hasattr(L, name), f"{name} is declared in include/{h} but not exported"
 
 
 def test_no_cpu_fallback_without_device():
