@@ -26,6 +26,7 @@
 
 #define FB_BEAM_THREADS 256
 #define FB_BEAM_WARPS (FB_BEAM_THREADS / 32)
+#define FB_BEAM_RG 128  // reads of up to this many groups (2048 positions) are staged in shared memory
 
 struct BeamTapDev {
     double *same, *diff, *logp;
@@ -60,7 +61,8 @@ struct BeamParams {
 struct BeamSmem {
     uint32_t off_nd_score, off_nd_err, off_nd_ref, off_st_hash, off_sc_same, off_sc_diff, off_st_hi, off_st_mark,
         off_free, off_live, off_ch_score, off_ch_parent, off_ch_part, off_ch_class, off_ch_diff, off_hp_score,
-        off_hp_item, off_lut, off_wscr, off_misc, off_job, off_addnew, off_plain, off_sc_pv, off_ch_fold, off_ch_m, total;
+        off_hp_item, off_lut, off_wscr, off_misc, off_job, off_addnew, off_plain, off_sc_pv, off_ch_fold, off_ch_m, off_rq,
+        off_ral, off_rpr, total;
     __host__ __device__ void layout(uint32_t P, uint32_t W, uint32_t NS) {
         uint32_t o = 0;
         auto take = [&](uint32_t bytes) {
@@ -94,6 +96,9 @@ struct BeamSmem {
         off_sc_pv = take(NS * 8);
         off_ch_fold = take(W * P * 8);
         off_ch_m = take(W * P * 4);
+        off_rq = take(2 * FB_BEAM_RG * 16);   // staged planes of the current / next read (double buffered)
+        off_ral = take(2 * FB_BEAM_RG * 4);
+        off_rpr = take(2 * FB_BEAM_RG * 2);
         total = o;
     }
 };
@@ -137,11 +142,14 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
     int *addnew = reinterpret_cast<int *>(smem + L.off_addnew);
     int *plain = reinterpret_cast<int *>(smem + L.off_plain);
     struct Misc {
-        unsigned long long delta;
+        unsigned long long delta[2];  // delta(read) of the current / next read (step parity)
         int n_nodes[2];
         int n_live, n_free, n_jobs_copy, n_jobs_inplace;
     };
     Misc *ms = reinterpret_cast<Misc *>(smem + L.off_misc);
+    uint4 *rq = reinterpret_cast<uint4 *>(smem + L.off_rq);            // [2][FB_BEAM_RG]
+    uint32_t *ral = reinterpret_cast<uint32_t *>(smem + L.off_ral);    // [2][FB_BEAM_RG]
+    uint16_t *rpr = reinterpret_cast<uint16_t *>(smem + L.off_rpr);    // [2][FB_BEAM_RG]
 
     uint32_t *hist = reinterpret_cast<uint32_t *>(slot + bp.hist_off);
     const uint32_t *__restrict__ qual32 = reinterpret_cast<const uint32_t *>(bp.fr.qual);
@@ -183,7 +191,7 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
                 ND_REF(0, 0, h) = 0;
             }
         }
-        long long pt[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        long long pt[24] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         long long tc = clock64();
 #define PROF(i)                         \
     if (bp.prof && tid == 0) {          \
@@ -191,12 +199,48 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
         pt[i] += n_ - tc;               \
         tc = n_;                        \
     }
+        const double ln_p = log((double)P);
+        const bool div_pow2 = (fb_f64_bits(bp.div_factor) & 0xFFFFFFFFFFFFFULL) == 0 && bp.div_factor > 1e-300 && bp.div_factor < 1e300;
+        const double inv_div = 1.0 / bp.div_factor;
         int gen = 0;
         uint32_t prev_start = 0;  // block-local position0 from which the hashes are valid
         int gmax = -1;            // last block-local group touched so far
         unsigned long long cells = 0, tapn = 0;
         RInfo ri_next = rinfo[0];
         RExtra rx_next = rextra[0];
+        // Everything of a step that depends on the read only is prepared one step ahead, off the critical path, by the
+        // warps that idle while warp 0 runs phase 2: the read's planes are staged in shared memory (reads of up to
+        // FB_BEAM_RG groups; longer ones are read from global memory) and delta(read) is summed.
+        auto stage_read = [&](const RInfo &rn, int par, int w0, int nw) {  // warps [w0, w0 + nw) cooperate
+            const uint32_t ngr = rn.lg1 - rn.lg0, gb = rn.gbase + rn.lg0;
+            if (ngr <= FB_BEAM_RG && (int)warp >= w0 && (int)warp < w0 + nw)
+                for (uint32_t x = (warp - w0) * 32 + lane; x < ngr; x += nw * 32) {
+                    rq[par * FB_BEAM_RG + x] = bp.fr.qual[gb + x];
+                    ral[par * FB_BEAM_RG + x] = bp.fr.allele[gb + x];
+                    rpr[par * FB_BEAM_RG + x] = bp.fr.present[gb + x];
+                }
+        };
+        auto read_delta = [&](const RInfo &rn, int par) {  // one warp: delta(read) = sum of G(pos, allele) * weight
+            unsigned long long d = 0;
+            for (uint32_t x = lane; x < (rn.lg1 - rn.lg0) * 4; x += 32) {
+                const uint32_t lg = rn.lg0 + (x >> 2), sub = x & 3;
+                const uint32_t g = rn.gbase + lg;
+                const uint32_t q = qual32[(uint64_t)g * 4 + sub];
+                const uint32_t al = bp.fr.allele[g], pr = bp.fr.present[g];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t c = sub * 4 + k;
+                    if ((pr >> c) & 1u) {
+                        const uint32_t av = ((al >> c) & 1u) | (((al >> (16 + c)) & 1u) << 1);
+                        d += fb_G((in.ag0 + lg) * 16u + c, av) * (unsigned long long)lut_s[(q >> (8 * k)) & 0xFFu];
+                    }
+                }
+            }
+            d = fb_warp_sum_u64(d);
+            if (lane == 0) ms->delta[par] = d;
+        };
+        stage_read(ri_next, 0, 0, FB_BEAM_WARPS - 1);
+        if (warp == FB_BEAM_WARPS - 1) read_delta(ri_next, 0);
         __syncthreads();
 
         for (uint32_t step = 0; step < in.n_reads; ++step) {
@@ -209,16 +253,24 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
             }
             const uint32_t cur_start = rx.first0;
             const uint32_t g0 = ri.gbase + ri.lg0, g1 = ri.gbase + ri.lg1;  // global groups of the read
+            const int par = (int)(step & 1u);
+            const bool staged = (ri.lg1 - ri.lg0) <= FB_BEAM_RG;
+            const uint4 *__restrict__ rq_c = rq + par * FB_BEAM_RG;
+            const uint32_t *__restrict__ ral_c = ral + par * FB_BEAM_RG;
+            const uint16_t *__restrict__ rpr_c = rpr + par * FB_BEAM_RG;
             const int n_nodes = ms->n_nodes[gen];
             const int n_live = ms->n_live;
             const int gmax_new = max(gmax, (int)ri.lg1 - 1);
             const uint32_t wend = (uint32_t)(gmax_new + 1) * 16u;  // one past the last live window position
 
             // ---- phase 1 (all warps): per live state: window advance of the hash, score of the read, p-value --------
-            for (int li = warp; li < n_live; li += FB_BEAM_WARPS) {
-                const int s = live[li];
+            // tasks: [0, n_live) score a live state; [n_live, 2 n_live) advance a live state's hash window (only when the
+            // window start moved).  The two kinds are independent, so they run on different warps.
+            const int n_tasks = cur_start > prev_start ? 2 * n_live : n_live;
+            for (int task = warp; task < n_tasks; task += FB_BEAM_WARPS) {
+                const int s = live[task < n_live ? task : task - n_live];
                 const int hi = st_hi[s];
-                if (cur_start > prev_start) {
+                if (task >= n_live) {
                     // drop positions [prev_start, cur_start) from the state's hash
                     unsigned long long sub = 0;
                     const uint32_t pend = min(cur_start, (uint32_t)(hi + 1) * 16u);
@@ -231,14 +283,26 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
                     }
                     sub = fb_warp_sum_u64(sub);
                     if (lane == 0) st_hash[s] -= sub;
+                    continue;
                 }
+                long long q0 = 0;
+                if (bp.prof && tid == 0) q0 = clock64();
                 const uint2 *mk = ST_MASK(s);
                 unsigned long long total = 0, same = 0, emptyw = 0;
                 uint32_t ne_cnt = 0;
+                int last_diff = -1, first_empty = INT_MAX;  // block-local positions of the last diff / first empty cell
                 for (uint32_t g = g0 + lane; g < g1; g += 32) {
-                    uint4 q = bp.fr.qual[g];
-                    uint32_t al = bp.fr.allele[g];
-                    uint32_t pr = bp.fr.present[g];
+                    uint4 q;
+                    uint32_t al, pr;
+                    if (staged) {
+                        q = rq_c[g - g0];
+                        al = ral_c[g - g0];
+                        pr = rpr_c[g - g0];
+                    } else {
+                        q = bp.fr.qual[g];
+                        al = bp.fr.allele[g];
+                        pr = bp.fr.present[g];
+                    }
                     uint32_t w[16];
                     fb_group_weights(q, pr, lut_s, w);
                     uint32_t t = 0;
@@ -254,20 +318,31 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
                     if (eb) {
                         emptyw += fb_masked_sum(w, eb);
                         ne_cnt += __popc(eb);
+                        first_empty = min(first_empty, (int)(lg * 16u) + __ffs(eb) - 1);
                     }
+                    const uint32_t db = pr & ne & ~sb & 0xFFFFu;
+                    if (db) last_diff = max(last_diff, (int)(lg * 16u) + 31 - __clz(db));
                 }
+                if (bp.prof && tid == 0) { long long n_ = clock64(); pt[16] += n_ - q0; q0 = n_; }
                 total = fb_warp_sum_u64(total);
                 same = fb_warp_sum_u64(same);
                 emptyw = fb_warp_sum_u64(emptyw);
                 ne_cnt = fb_warp_sum_u32(ne_cnt);
                 const long long diff_q = (long long)(total - same - emptyw);
+                if (bp.prof && tid == 0) { long long n_ = clock64(); pt[17] += n_ - q0; q0 = n_; }
                 double diff_f;
                 if (ne_cnt == 0)
                     diff_f = fb_q26_to_f64(diff_q);
                 else if (bp.eps_safe)
                     diff_f = fb_q26_to_f64(diff_q + (long long)ne_cnt * (long long)(bp.eps * FB_Q26));
+                else if (__reduce_max_sync(0xFFFFFFFFu, last_diff) < __reduce_min_sync(0xFFFFFFFFu, first_empty))
+                    // every empty position lies right of every diff position (the usual case: the read's tail runs past
+                    // the haplotype's coverage): the reference's sum is the exact dyadic part followed by ne_cnt
+                    // consecutive `+= epsilon`, which fb_add_eps_n evaluates in closed form per binade
+                    diff_f = fb_add_eps_n(fb_q26_to_f64(diff_q), bp.eps, ne_cnt);
                 else
                     diff_f = fb_replay_diff(bp.fr, g0, g1, mk, ri.lg0, hi, lut_s, bp.eps, wscr);
+                if (bp.prof && tid == 0) { long long n_ = clock64(); pt[18] += n_ - q0 + (long long)(diff_f * 0.0); q0 = n_; }
                 {
                     // stable_binom_cdf_p_rev (utils_frags.rs:211-248) with its two log terms evaluated on two lanes; the
                     // operations and their order are those of fb_stable_binom_cdf_p_rev (global_clustering.rs:81-88).
@@ -285,47 +360,112 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
                         const double t1 = __shfl_sync(0xFFFFFFFFu, t, 1);
                         double rel_ent = t + t1;
                         if (a < bp.eps) rel_ent = -rel_ent;
-                        pvs = -1.0 * n64 / bp.div_factor * rel_ent;
+                        // x / div_factor == x * (1 / div_factor) bit for bit when div_factor is a power of two (the
+                        // reference's DIV_FACTOR is 0.25): skip the software division on the critical path
+                        pvs = (div_pow2 ? -1.0 * n64 * inv_div : -1.0 * n64 / bp.div_factor) * rel_ent;
                     }
                     if (lane == 0) {
                         sc_same[s] = same_f;
                         sc_diff[s] = diff_f;
                         sc_pv[s] = 1.0 * pvs;
                     }
+                    if (bp.prof && tid == 0) { long long n_ = clock64(); pt[19] += n_ - q0 + (long long)(pvs * 0.0); q0 = n_; }
                 }
-            }
-            // delta(read) = sum over its cells of G(pos, allele) * weight, by the last warp (least loaded)
-            if (warp == FB_BEAM_WARPS - 1) {
-                unsigned long long d = 0;
-                for (uint32_t x = lane; x < (ri.lg1 - ri.lg0) * 4; x += 32) {
-                    const uint32_t lg = ri.lg0 + (x >> 2), sub = x & 3;
-                    const uint32_t g = ri.gbase + lg;
-                    const uint32_t q = qual32[(uint64_t)g * 4 + sub];
-                    const uint32_t al = bp.fr.allele[g], pr = bp.fr.present[g];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t c = sub * 4 + k;
-                        if ((pr >> c) & 1u) {
-                            const uint32_t av = ((al >> c) & 1u) | (((al >> (16 + c)) & 1u) << 1);
-                            d += fb_G((in.ag0 + lg) * 16u + c, av) * (unsigned long long)lut_s[(q >> (8 * k)) & 0xFFu];
-                        }
-                    }
-                }
-                d = fb_warp_sum_u64(d);
-                if (lane == 0) ms->delta = d;
             }
             __syncthreads();
             PROF(0)
 
             // ---- phase 2 (warp 0): pruning, child scores, equality classes, exact BinaryHeap emulation, next generation;
-            //      the other warps prefetch the next read's groups into L2 ------------------------------------------------
+            //      the other warps stage the next read (planes -> shared memory, delta) ------------------------------------------------
             if (warp != 0) {
                 if (step + 1 < in.n_reads) {
-                    const uint32_t ng0 = ri_next.gbase + ri_next.lg0, ng1 = ri_next.gbase + ri_next.lg1;
-                    for (uint32_t g = ng0 + (tid - 32) * 8; g < ng1; g += (FB_BEAM_THREADS - 32) * 8) {
-                        fb_prefetch_l2(bp.fr.qual + g);          // 8 groups = 128 B of quals
-                        if (((g - ng0) & 31) == 0) fb_prefetch_l2(bp.fr.allele + g);
-                        if (((g - ng0) & 63) == 0) fb_prefetch_l2(bp.fr.present + g);
+                    stage_read(ri_next, par ^ 1, 1, FB_BEAM_WARPS - 2);
+                    if (warp == FB_BEAM_WARPS - 1) read_delta(ri_next, par ^ 1);
+                }
+                // wait until warp 0 has published the job list of this step (named barrier 1: warp 0 only arrives and goes
+                // on with the next generation's node tables, so that bookkeeping overlaps the materialisation)
+                asm volatile("bar.sync 1, %0;" ::"n"(FB_BEAM_THREADS) : "memory");
+                    // ---- phase 3 (warps 1..7): materialise the new states (types_structs.rs:368-373 on the dense layout) ---------
+                    {
+                    const int nj_copy = ms->n_jobs_copy, nj_inpl = ms->n_jobs_inplace;
+                    const int gs = (int)(cur_start >> 4);
+                    const uint8_t *__restrict__ qual8 = reinterpret_cast<const uint8_t *>(bp.fr.qual);
+                    // copies: groups [gs, gmax_new]; in place: the read's groups only.  One thread per (job, group, position):
+                    // a warp touches 1 KB of contiguous counts (two 16-byte accesses per lane), and the is-max planes of a
+                    // group are assembled with one ballot per allele.
+                    for (int pass = 0; pass < 2; ++pass) {
+                        const int nj = pass == 0 ? nj_copy : nj_inpl;
+                        const int glo = pass == 0 ? gs : (int)ri.lg0;
+                        const int ghi = pass == 0 ? gmax_new : (int)ri.lg1 - 1;
+                        const int npj = (ghi - glo + 1) * 16;  // positions per job
+                        const int total = nj * npj;
+                        for (int base = 0; base < total; base += FB_BEAM_THREADS - 32) {
+                            const int idx = base + tid - 32;
+                            const bool act = idx < total;
+                            const uint32_t k = (uint32_t)tid & 15u;
+                            bool im0 = false, im1 = false, im2 = false, im3 = false;
+                            int lg = 0;
+                            uint32_t dst_state = 0;
+                            if (act) {
+                                const int jn = idx / npj, rem = idx - jn * npj;
+                                const BeamJob jb = pass == 0 ? jobs[jn] : jobs[(int)Wm + 1 - jn];
+                                lg = glo + (rem >> 4);
+                                dst_state = jb.dst;
+                                const uint64_t pos = (uint64_t)lg * 16 + k;
+                                unsigned long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+                                if (lg <= jb.src_hi) {
+                                    const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(ST_CNT(jb.src) + pos * 4);
+                                    const ulonglong2 v0 = src[0], v1 = src[1];
+                                    c0 = v0.x;
+                                    c1 = v0.y;
+                                    c2 = v1.x;
+                                    c3 = v1.y;
+                                }
+                                if (lg >= (int)ri.lg0 && lg < (int)ri.lg1) {
+                                    const uint32_t g = ri.gbase + (uint32_t)lg;
+                                    // the three loads are independent (absent cells carry a valid dummy quality byte)
+                                    uint32_t pr, al, qb;
+                                    if (staged) {
+                                        const uint32_t x = (uint32_t)lg - ri.lg0;
+                                        pr = rpr_c[x];
+                                        al = ral_c[x];
+                                        qb = reinterpret_cast<const uint8_t *>(rq_c)[x * 16 + k];
+                                    } else {
+                                        pr = bp.fr.present[g];
+                                        al = bp.fr.allele[g];
+                                        qb = qual8[(uint64_t)g * 16 + k];
+                                    }
+                                    if ((pr >> k) & 1u) {
+                                        const uint32_t av = ((al >> k) & 1u) | (((al >> (16 + k)) & 1u) << 1);
+                                        const unsigned long long w = lut_s[qb];
+                                        if (av == 0) c0 = (c0 + w) | FB_PRESENT;
+                                        if (av == 1) c1 = (c1 + w) | FB_PRESENT;
+                                        if (av == 2) c2 = (c2 + w) | FB_PRESENT;
+                                        if (av == 3) c3 = (c3 + w) | FB_PRESENT;
+                                    }
+                                }
+                                ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(ST_CNT(jb.dst) + pos * 4);
+                                dst[0] = make_ulonglong2(c0, c1);
+                                dst[1] = make_ulonglong2(c2, c3);
+                                const unsigned long long m0 = c0 & FB_CNT_MASK, m1 = c1 & FB_CNT_MASK, m2 = c2 & FB_CNT_MASK,
+                                                         m3 = c3 & FB_CNT_MASK;
+                                unsigned long long mx = m0 > m1 ? m0 : m1;
+                                const unsigned long long my = m2 > m3 ? m2 : m3;
+                                mx = mx > my ? mx : my;
+                                if (mx > 0) {
+                                    im0 = m0 == mx;
+                                    im1 = m1 == mx;
+                                    im2 = m2 == mx;
+                                    im3 = m3 == mx;
+                                }
+                            }
+                            const uint32_t sh = lane & 16u;
+                            const uint32_t b0 = (__ballot_sync(0xFFFFFFFFu, im0) >> sh) & 0xFFFFu;
+                            const uint32_t b1 = (__ballot_sync(0xFFFFFFFFu, im1) >> sh) & 0xFFFFu;
+                            const uint32_t b2 = (__ballot_sync(0xFFFFFFFFu, im2) >> sh) & 0xFFFFu;
+                            const uint32_t b3 = (__ballot_sync(0xFFFFFFFFu, im3) >> sh) & 0xFFFFu;
+                            if (act && k == 0) ST_MASK(dst_state)[lg] = make_uint2(b0 | (b1 << 16), b2 | (b3 << 16));
+                        }
                     }
                 }
             } else {
@@ -352,19 +492,35 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
                                 }
                             }
                         }
-                        // utils_frags.rs:250-258 log_sum_exp
+                        // utils_frags.rs:250-258 log_sum_exp and the pruning test p[j] - lse > cutoff
+                        // (global_clustering.rs:93-98).  lse = mx + ln(S) with 1 <= S <= P, so p[j] - lse lies in
+                        // [d - ln P, d] for d = p[j] - mx: outside the band cutoff < d <= cutoff + ln P the decision
+                        // needs no exp/log at all (margins of 1e-6 dwarf every rounding error of the full formula, whose
+                        // terms are below 2^40); inside the band the reference formula is evaluated as written.
                         double mx = pv[0];
 #pragma unroll
                         for (int j = 1; j < P; ++j) mx = pv[j] > mx ? pv[j] : mx;
-                        double sum = 0.0;
+                        const double band_hi = bp.cutoff + ln_p + 1e-6, band_lo = bp.cutoff - 1e-6;
+                        bool need_lse = false;
 #pragma unroll
-                        for (int j = 0; j < P; ++j) sum += exp(pv[j] - mx);
-                        const double lse = mx + log(sum);
+                        for (int j = 0; j < P; ++j) {
+                            const double d = pv[j] - mx;
+                            need_lse |= (d > band_lo) && (d <= band_hi);
+                        }
+                        double lse = 0.0;
+                        if (need_lse || !(fabs(mx) < 1e12)) {
+                            double sum = 0.0;
+#pragma unroll
+                            for (int j = 0; j < P; ++j) sum += exp(pv[j] - mx);
+                            lse = mx + log(sum);
+                            need_lse = true;
+                        }
 #pragma unroll
                         for (int j = 0; j < P; ++j) {
                             {
                                 double sc = -1.0;  // < 0 marks "pruned" (scores are sums of non-negative terms)
-                                if (pv[j] - lse > bp.cutoff) {
+                                const bool keep = need_lse ? (pv[j] - lse > bp.cutoff) : (pv[j] - mx > band_hi);
+                                if (keep) {
                                     double mec = 0.0;  // new_error_vec.iter().map(|x| x.1).sum()
 #pragma unroll
                                     for (int h = 0; h < P; ++h) {
@@ -401,7 +557,7 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
                     nc += __popc(bal);
                     __syncwarp();
                 }
-                const unsigned long long delta = ms->delta;
+                const unsigned long long delta = ms->delta[par];
                 // (c) one 64-bit fold of each child's tuple of (virtual) state hashes
                 for (int c0 = 0; c0 < nc; c0 += 32) {
                     const int c = c0 + (int)lane;
@@ -569,9 +725,16 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
                     ms->n_jobs_copy = nj_copy;
                     ms->n_jobs_inplace = nj_inpl;
                     ms->n_nodes[gen ^ 1] = len;
-                    if (bp.prof) pt[9] += nj_copy * 1000 + nj_inpl;
+                    if (bp.prof) {
+                        pt[13] += nj_copy;
+                        pt[14] += nj_inpl;
+                        pt[15] += n_live;
+                        pt[9] += n_nodes;
+                    }
                 }
                 __syncwarp();
+                __threadfence_block();
+                asm volatile("bar.arrive 1, %0;" ::"n"(FB_BEAM_THREADS) : "memory");  // releases warps 1..7 into phase 3
                 // next generation's node tables + history (one lane per entry)
                 {
                     const int ng2 = gen ^ 1;
@@ -630,93 +793,7 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
                     }
                 }
             }
-            __syncthreads();
             PROF(1)
-
-            // ---- phase 3 (all warps): materialise the new states (types_structs.rs:368-373 on the dense layout) --------------
-            {
-                const int nj_copy = ms->n_jobs_copy, nj_inpl = ms->n_jobs_inplace;
-                const int gs = (int)(cur_start >> 4);
-                // copies: groups [gs, gmax_new]; in place: the read's groups only
-                for (int pass = 0; pass < 2; ++pass) {
-                    const int nj = pass == 0 ? nj_copy : nj_inpl;
-                    const int glo = pass == 0 ? gs : (int)ri.lg0;
-                    const int ghi = pass == 0 ? gmax_new : (int)ri.lg1 - 1;
-                    const int nq = (ghi - glo + 1) * 4;  // quarters per job
-                    const int total = nj * nq;
-                    for (int base = 0; base < total; base += FB_BEAM_THREADS) {
-                        const int idx = base + tid;
-                        const bool act = idx < total;
-                        uint32_t pl[4] = {0, 0, 0, 0};
-                        int lg = 0;
-                        uint32_t sub = 0;
-                        BeamJob jb;
-                        jb.src = jb.dst = jb._pad = 0;
-                        jb.src_hi = -1;
-                        if (act) {
-                            const int jn = idx / nq, qx = idx % nq;
-                            jb = pass == 0 ? jobs[jn] : jobs[(int)Wm + 1 - jn];
-                            lg = glo + (qx >> 2);
-                            sub = (uint32_t)qx & 3u;
-                            unsigned long long wv[16];
-                            const ulonglong2 *src =
-                                reinterpret_cast<const ulonglong2 *>(ST_CNT(jb.src) + ((uint64_t)lg * 16 + sub * 4) * 4);
-                            if (lg <= jb.src_hi) {
-#pragma unroll
-                                for (int x = 0; x < 8; ++x) {
-                                    ulonglong2 v = src[x];
-                                    wv[2 * x] = v.x;
-                                    wv[2 * x + 1] = v.y;
-                                }
-                            } else {
-#pragma unroll
-                                for (int x = 0; x < 16; ++x) wv[x] = 0ULL;
-                            }
-                            if (lg >= (int)ri.lg0 && lg < (int)ri.lg1) {
-                                const uint32_t g = ri.gbase + (uint32_t)lg;
-                                const uint32_t q = qual32[(uint64_t)g * 4 + sub];
-                                const uint32_t al = bp.fr.allele[g], pr = bp.fr.present[g];
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    const uint32_t c = sub * 4 + k;
-                                    if ((pr >> c) & 1u) {
-                                        const uint32_t av = ((al >> c) & 1u) | (((al >> (16 + c)) & 1u) << 1);
-                                        const unsigned long long w = lut_s[(q >> (8 * k)) & 0xFFu];
-#pragma unroll
-                                        for (int a = 0; a < 4; ++a)
-                                            if ((uint32_t)a == av) wv[k * 4 + a] = (wv[k * 4 + a] + w) | FB_PRESENT;
-                                    }
-                                }
-                            }
-                            ulonglong2 *dst =
-                                reinterpret_cast<ulonglong2 *>(ST_CNT(jb.dst) + ((uint64_t)lg * 16 + sub * 4) * 4);
-#pragma unroll
-                            for (int x = 0; x < 8; ++x) dst[x] = make_ulonglong2(wv[2 * x], wv[2 * x + 1]);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                unsigned long long mx = 0;
-#pragma unroll
-                                for (int a = 0; a < 4; ++a) {
-                                    unsigned long long v = wv[k * 4 + a] & FB_CNT_MASK;
-                                    mx = v > mx ? v : mx;
-                                }
-                                if (mx > 0) {
-#pragma unroll
-                                    for (int a = 0; a < 4; ++a)
-                                        if ((wv[k * 4 + a] & FB_CNT_MASK) == mx) pl[a] |= 1u << (sub * 4 + k);
-                                }
-                            }
-                        }
-#pragma unroll
-                        for (int a = 0; a < 4; ++a) {
-                            pl[a] |= __shfl_xor_sync(0xFFFFFFFFu, pl[a], 1);
-                            pl[a] |= __shfl_xor_sync(0xFFFFFFFFu, pl[a], 2);
-                        }
-                        if (act && sub == 0)
-                            ST_MASK(jb.dst)[lg] = make_uint2(pl[0] | (pl[1] << 16), pl[2] | (pl[3] << 16));
-                    }
-                }
-            }
             cells += (unsigned long long)n_nodes * rx.nnz;
             tapn += (unsigned long long)n_nodes * P;
             gen ^= 1;
@@ -751,6 +828,7 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
             if (bp.prof) {
                 PROF(5)
                 for (int i = 0; i < 12; ++i) atomicAdd(bp.prof + i, (unsigned long long)pt[i]);
+                for (int i = 13; i < 24; ++i) atomicAdd(bp.prof + i, (unsigned long long)pt[i]);
                 atomicAdd(bp.prof + 12, (unsigned long long)in.n_reads);
             }
         }

@@ -109,11 +109,11 @@ static int fb_run_beam(fb_ctx *ctx, Engine &e, const fb_params *prm, const BeamT
     unsigned long long *d_prof = nullptr;
     const bool prof = getenv("FB_BEAM_PROF") != nullptr;
     if (prof) {
-        if ((rc = fb_dalloc(ctx, &d_prof, 16))) {
+        if ((rc = fb_dalloc(ctx, &d_prof, 24))) {
             cleanup();
             return rc;
         }
-        cudaMemsetAsync(d_prof, 0, 128, ctx->stream);
+        cudaMemsetAsync(d_prof, 0, 192, ctx->stream);
         bp.prof = d_prof;
     }
     cudaEvent_t e0 = fb_event(ctx);
@@ -135,17 +135,18 @@ static int fb_run_beam(fb_ctx *ctx, Engine &e, const fb_params *prm, const BeamT
     }
     cudaEventElapsedTime(&br.beam_ms, e0, e1);
     if (prof) {
-        unsigned long long h[16];
-        cudaMemcpy(h, d_prof, 128, cudaMemcpyDeviceToHost);
+        unsigned long long h[24];
+        cudaMemcpy(h, d_prof, 192, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[k_beam prof] scoring warp 0, cycles/step: loop %.0f | reductions %.0f | diff_f %.0f | p-value %.0f\n", h[16] / (double)std::max<unsigned long long>(h[12], 1), h[17] / (double)std::max<unsigned long long>(h[12], 1), h[18] / (double)std::max<unsigned long long>(h[12], 1), h[19] / (double)std::max<unsigned long long>(h[12], 1));
         fb_cache_free(d_prof);
         double steps = (double)std::max<unsigned long long>(h[12], 1);
         fprintf(stderr,
                 "[k_beam prof] %.3f ms, %d instances on %llu CTAs, %.0f steps; cycles/step: phase1(score) %.0f | warp0: lse %.0f "
                 "compact+fold+dups+classes %.0f heap %.0f nextgen %.0f | phase3(copy) %.0f | children/step %.1f survivors/step %.1f "
-                "copyjobs/step %.2f inplace/step %.2f | backtrack total %.0f\n",
+                "copyjobs/step %.2f inplace/step %.2f live states/step %.2f nodes/step %.2f | backtrack total %.0f\n",
                 br.beam_ms, (int)order.size(), (unsigned long long)n_slots, steps, h[0] / steps, h[6] / steps, h[7] / steps,
-                h[8] / steps, h[1] / steps, h[2] / steps, h[10] / steps, h[11] / steps, (h[9] / 1000) / steps,
-                (h[9] % 1000) / steps, (double)h[5]);
+                h[8] / steps, h[1] / steps, h[2] / steps, h[10] / steps, h[11] / steps, h[13] / steps, h[14] / steps,
+                h[15] / steps, h[9] / steps, (double)h[5]);
     }
     cleanup();
     return FB_OK;

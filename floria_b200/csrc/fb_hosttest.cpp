@@ -52,4 +52,5 @@ double ht_binom(unsigned long long n, unsigned long long k, double p, double div
 double ht_lse(const double *p, int n) { return fb_log_sum_exp(p, n); }
 double ht_mec_threshold(unsigned ploidy, double eps, unsigned s) { return fb_mec_threshold(ploidy, eps, s); }
 int ht_eps_safe(double eps) { return fb_eps_is_safe(eps); }
+double ht_add_eps_n(double S, double eps, unsigned long long m) { return fb_add_eps_n(S, eps, m); }
 }

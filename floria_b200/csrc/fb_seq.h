@@ -112,6 +112,75 @@ struct SeqSum {
     }
 };
 
+// ---- m consecutive `S += eps` in O(number of binades crossed) ---------------------------------------------------------
+// The reference adds epsilon once per empty position (utils_frags.rs:45-48), so a read whose tail lies beyond a
+// haplotype's coverage costs hundreds of dependent f64 adds.  While S stays inside one binade its ulp u is constant and
+// S is a multiple of u, so fl(S + eps) = S + c with the same c = round-to-nearest(eps / u) * u at every step (unless
+// eps / u ends in exactly .5, where ties-to-even alternates: those steps are done one by one).  k steps are therefore
+// S + k*c, exactly, as long as S + k*c stays below the top of the binade; the step that crosses it is a real add.
+// Bit-identical to the loop `for (i < m) S += eps` for S >= 0, eps > 0 (tests/test_abi_and_host_logic.py).
+FB_HD uint64_t fb_f64_bits(double x) {
+#if defined(__CUDA_ARCH__)
+    return (uint64_t)__double_as_longlong(x);
+#else
+    union {
+        double d;
+        uint64_t u;
+    } v;
+    v.d = x;
+    return v.u;
+#endif
+}
+FB_HD double fb_bits_f64(uint64_t b) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)b);
+#else
+    union {
+        double d;
+        uint64_t u;
+    } v;
+    v.u = b;
+    return v.d;
+#endif
+}
+FB_HD double fb_add_eps_n(double S, double eps, unsigned long long m) {
+    while (m > 0) {
+        const uint64_t sb = fb_f64_bits(S), eb = fb_f64_bits(eps);
+        const int es = (int)((sb >> 52) & 0x7FF), ee = (int)((eb >> 52) & 0x7FF);  // biased exponents
+        // bulk steps need: S and eps normal, eps < 2^e(S) (so that eps / ulp(S) < 2^52 and has an exact fraction)
+        if (es > 0 && es < 0x7FE && ee > 0 && ee < es) {
+            const uint64_t sq = (sb & 0xFFFFFFFFFFFFFULL) | (1ULL << 52);  // S / u, in [2^52, 2^53)
+            const uint64_t em = (eb & 0xFFFFFFFFFFFFFULL) | (1ULL << 52);  // eps = em * 2^(ee - 1075)
+            const int sh = es - ee;                                        // eps / u = em >> sh, sh >= 1
+            uint64_t q, rem2;  // q = floor(eps / u); rem2: 0 below one half, 1 exactly one half, 2 above
+            if (sh > 53) {
+                q = 0;
+                rem2 = 0;
+            } else {
+                q = sh >= 64 ? 0 : (em >> sh);
+                const uint64_t frac = em & ((1ULL << sh) - 1ULL), half = 1ULL << (sh - 1);
+                rem2 = frac > half ? 2 : (frac == half ? 1 : 0);
+            }
+            if (rem2 != 1) {
+                const uint64_t cq = q + (rem2 == 2 ? 1ULL : 0ULL);
+                if (cq == 0) return S;  // eps < u / 2: every add rounds back to S
+                const uint64_t room = ((1ULL << 53) - 1ULL) - sq;
+                uint64_t k = room / cq;
+                if (k > m) k = m;
+                if (k > 0) {
+                    const uint64_t nq = sq + k * cq;  // < 2^53: same binade
+                    S = fb_bits_f64((sb & 0xFFF0000000000000ULL) | (nq & 0xFFFFFFFFFFFFFULL));
+                    m -= k;
+                    continue;
+                }
+            }
+        }
+        S = S + eps;  // a real add: binade crossing, tie, or S not yet above eps
+        m -= 1;
+    }
+    return S;
+}
+
 // epsilon is "safe" when it is itself a multiple of 2^-26: then every quantity on the path is exact and the sum is
 // order independent (the dyadic-epsilon gate of BASELINE.md §4).
 FB_HD int fb_eps_is_safe(double eps) {

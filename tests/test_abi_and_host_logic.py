@@ -124,3 +124,25 @@ def test_scalar_formulas_match_oracle(ht):
     for s in (1, 2, 3):
         for p in (2, 3, 4, 5, 6):
             assert ht.ht_mec_threshold(p, 0.04, s) == oracle.mec_threshold(p, 0.04, s)
+
+
+def test_add_eps_n_equals_the_plain_loop(ht):
+    """fb_add_eps_n (m consecutive `S += eps` in closed form per binade) must be bit-identical to the loop."""
+    ht.ht_add_eps_n.restype = C.c_double
+    ht.ht_add_eps_n.argtypes = [C.c_double, C.c_double, C.c_ulonglong]
+    rng = np.random.default_rng(5)
+    cases = []
+    for eps in [0.04, 0.01, 0.03125, 0.1, 1e-3, 0.3, 2.0 ** -30 * 3, 0.04 * (1 + 2.0 ** -52), 0.75]:
+        for S in [0.0, 2.0 ** -26, 0.5, 1.0 - 2.0 ** -53, 1.0, 3.96875, 17.25, 1023.999, 2.0 ** 20 + 0.5, 7.0 * 2.0 ** -26]:
+            for m in [0, 1, 2, 3, 17, 100, 1000, 4097]:
+                cases.append((S, eps, m))
+    for _ in range(400):
+        S = float(rng.integers(0, 2 ** 40)) * 2.0 ** -26 if rng.random() < 0.5 else float(rng.random() * 10.0 ** float(rng.integers(-3, 6)))
+        cases.append((S, float(rng.random() * 0.2 + 1e-4), int(rng.integers(0, 3000))))
+    for S, eps, m in cases:
+        want = np.float64(S)
+        e = np.float64(eps)
+        for _ in range(m):
+            want = want + e
+        got = ht.ht_add_eps_n(S, eps, m)
+        assert np.float64(got).view(np.uint64) == np.float64(want).view(np.uint64), (S, eps, m, got, float(want))
