@@ -24,7 +24,11 @@
 #include "fb_common.cuh"
 #include "fb_kernels.cuh"
 
+// CTA sizes the kernel is instantiated for: 256 threads (one CTA per SM: lowest latency per read step, used when there are
+// fewer instances than SMs can hold) and 128 threads (two CTAs per SM: the dependent chains of two instances interleave,
+// used for many-instance work queues such as a batched metagenome)
 #define FB_BEAM_THREADS 256
+#define FB_BEAM_THREADS_SMALL 128
 #define FB_BEAM_WARPS (FB_BEAM_THREADS / 32)
 #define FB_BEAM_RG 128  // reads of up to this many groups (2048 positions) are staged in shared memory
 
@@ -111,8 +115,9 @@ struct BeamJob {
 
 __device__ __forceinline__ void fb_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-template <int P>
+template <int P, int NT>
 __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii, uint8_t *smem, uint8_t *slot) {
+    constexpr int NW = NT / 32;  // warps of the CTA
     const int tid = threadIdx.x;
     const uint32_t lane = tid & 31, warp = tid >> 5;
     BeamSmem L;
@@ -172,7 +177,7 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
         const RExtra *__restrict__ rextra = bp.rextra + in.read_off;
 
         // ---- init: one root node over the empty state (global_clustering.rs:29-47) ---------------------------------
-        for (uint32_t s = tid; s < NS; s += FB_BEAM_THREADS) {
+        for (uint32_t s = tid; s < NS; s += NT) {
             st_hash[s] = 0;
             st_hi[s] = -1;
             st_mark[s] = 0;
@@ -239,8 +244,8 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
             d = fb_warp_sum_u64(d);
             if (lane == 0) ms->delta[par] = d;
         };
-        stage_read(ri_next, 0, 0, FB_BEAM_WARPS - 1);
-        if (warp == FB_BEAM_WARPS - 1) read_delta(ri_next, 0);
+        stage_read(ri_next, 0, 0, NW - 1);
+        if (warp == NW - 1) read_delta(ri_next, 0);
         __syncthreads();
 
         for (uint32_t step = 0; step < in.n_reads; ++step) {
@@ -267,7 +272,7 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
             // tasks: [0, n_live) score a live state; [n_live, 2 n_live) advance a live state's hash window (only when the
             // window start moved).  The two kinds are independent, so they run on different warps.
             const int n_tasks = cur_start > prev_start ? 2 * n_live : n_live;
-            for (int task = warp; task < n_tasks; task += FB_BEAM_WARPS) {
+            for (int task = warp; task < n_tasks; task += NW) {
                 const int s = live[task < n_live ? task : task - n_live];
                 const int hi = st_hi[s];
                 if (task >= n_live) {
@@ -379,12 +384,12 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
             //      the other warps stage the next read (planes -> shared memory, delta) ------------------------------------------------
             if (warp != 0) {
                 if (step + 1 < in.n_reads) {
-                    stage_read(ri_next, par ^ 1, 1, FB_BEAM_WARPS - 2);
-                    if (warp == FB_BEAM_WARPS - 1) read_delta(ri_next, par ^ 1);
+                    stage_read(ri_next, par ^ 1, 1, NW - 2);
+                    if (warp == NW - 1) read_delta(ri_next, par ^ 1);
                 }
                 // wait until warp 0 has published the job list of this step (named barrier 1: warp 0 only arrives and goes
                 // on with the next generation's node tables, so that bookkeeping overlaps the materialisation)
-                asm volatile("bar.sync 1, %0;" ::"n"(FB_BEAM_THREADS) : "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
                     // ---- phase 3 (warps 1..7): materialise the new states (types_structs.rs:368-373 on the dense layout) ---------
                     {
                     const int nj_copy = ms->n_jobs_copy, nj_inpl = ms->n_jobs_inplace;
@@ -399,7 +404,7 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
                         const int ghi = pass == 0 ? gmax_new : (int)ri.lg1 - 1;
                         const int npj = (ghi - glo + 1) * 16;  // positions per job
                         const int total = nj * npj;
-                        for (int base = 0; base < total; base += FB_BEAM_THREADS - 32) {
+                        for (int base = 0; base < total; base += NT - 32) {
                             const int idx = base + tid - 32;
                             const bool act = idx < total;
                             const uint32_t k = (uint32_t)tid & 15u;
@@ -734,7 +739,7 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
                 }
                 __syncwarp();
                 __threadfence_block();
-                asm volatile("bar.arrive 1, %0;" ::"n"(FB_BEAM_THREADS) : "memory");  // releases warps 1..7 into phase 3
+                asm volatile("bar.arrive 1, %0;" ::"n"(NT) : "memory");  // releases warps 1..7 into phase 3
                 // next generation's node tables + history (one lane per entry)
                 {
                     const int ng2 = gen ^ 1;
@@ -841,7 +846,8 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
     }
 }
 
-__global__ void __launch_bounds__(FB_BEAM_THREADS, 1) k_beam(BeamParams bp) {
+template <int NT>
+__global__ void __launch_bounds__(NT, FB_BEAM_THREADS / NT) k_beam(BeamParams bp) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ int s_work;
     const int tid = threadIdx.x;
@@ -849,7 +855,7 @@ __global__ void __launch_bounds__(FB_BEAM_THREADS, 1) k_beam(BeamParams bp) {
         BeamSmem L;
         L.layout(bp.maxP, bp.maxW, bp.maxNS);
         uint32_t *lut_s = reinterpret_cast<uint32_t *>(smem + L.off_lut);
-        for (int i = tid; i < 256; i += FB_BEAM_THREADS) lut_s[i] = bp.lut[i];
+        for (int i = tid; i < 256; i += NT) lut_s[i] = bp.lut[i];
     }
     uint8_t *slot = bp.scratch + (uint64_t)blockIdx.x * bp.slot_bytes;
     for (;;) {
@@ -860,13 +866,13 @@ __global__ void __launch_bounds__(FB_BEAM_THREADS, 1) k_beam(BeamParams bp) {
         if (wk >= bp.n_work) break;
         const int ii = bp.order[wk];
         switch (bp.inst[ii].ploidy) {
-            case 2: fb_beam_instance<2>(bp, ii, smem, slot); break;
-            case 3: fb_beam_instance<3>(bp, ii, smem, slot); break;
-            case 4: fb_beam_instance<4>(bp, ii, smem, slot); break;
-            case 5: fb_beam_instance<5>(bp, ii, smem, slot); break;
-            case 6: fb_beam_instance<6>(bp, ii, smem, slot); break;
-            case 7: fb_beam_instance<7>(bp, ii, smem, slot); break;
-            case 8: fb_beam_instance<8>(bp, ii, smem, slot); break;
+            case 2: fb_beam_instance<2, NT>(bp, ii, smem, slot); break;
+            case 3: fb_beam_instance<3, NT>(bp, ii, smem, slot); break;
+            case 4: fb_beam_instance<4, NT>(bp, ii, smem, slot); break;
+            case 5: fb_beam_instance<5, NT>(bp, ii, smem, slot); break;
+            case 6: fb_beam_instance<6, NT>(bp, ii, smem, slot); break;
+            case 7: fb_beam_instance<7, NT>(bp, ii, smem, slot); break;
+            case 8: fb_beam_instance<8, NT>(bp, ii, smem, slot); break;
             default: break;
         }
     }

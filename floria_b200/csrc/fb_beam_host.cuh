@@ -43,9 +43,15 @@ static int fb_run_beam(fb_ctx *ctx, Engine &e, const fb_params *prm, const BeamT
     BeamSmem L;
     L.layout(maxP, maxW, maxNS);
     if (L.total > 200 * 1024) FB_FAIL(FB_ERR_LIMIT, "beam search needs %u bytes of shared memory", L.total);
-    FB_CK(cudaFuncSetAttribute(k_beam, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    // many instances: 128-thread CTAs, two per SM (the per-read dependency chains of two instances interleave);
+    // few instances: 256-thread CTAs, one per SM (shortest chain per step)
+    const bool small_cta = order.size() >= (size_t)ctx->sm_count * 2 && maxW <= FB_BEAM_THREADS_SMALL &&
+                           !(getenv("FB_BEAM_CTA") && atoi(getenv("FB_BEAM_CTA")) == 256);
+    const int nt = small_cta ? FB_BEAM_THREADS_SMALL : FB_BEAM_THREADS;
+    auto kern = small_cta ? k_beam<FB_BEAM_THREADS_SMALL> : k_beam<FB_BEAM_THREADS>;
+    FB_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     int occ = 1;
-    FB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_beam, FB_BEAM_THREADS, L.total));
+    FB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nt, L.total));
     if (occ < 1) occ = 1;
     const uint64_t pool_bytes = (max_pool + 255) & ~255ULL;
     const uint64_t hist_bytes = (((uint64_t)maxR * maxW * 4) + 255) & ~255ULL;
@@ -117,7 +123,7 @@ static int fb_run_beam(fb_ctx *ctx, Engine &e, const fb_params *prm, const BeamT
         bp.prof = d_prof;
     }
     cudaEvent_t e0 = fb_event(ctx);
-    k_beam<<<(unsigned)n_slots, FB_BEAM_THREADS, L.total, ctx->stream>>>(bp);
+    kern<<<(unsigned)n_slots, nt, L.total, ctx->stream>>>(bp);
     cudaEvent_t e1 = fb_event(ctx);
     ctx->tim.n_launches++;
     ctx->tim.n_beam_launches++;

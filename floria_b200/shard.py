@@ -34,6 +34,45 @@ def block_costs(frags, blk_lo, blk_hi, max_ploidy):
     return out
 
 
+def concat_contigs(contigs, blocks, gap=64):
+    """Batch several contigs into ONE fb_phase_blocks call: contig k's SNP positions are shifted by the total length of
+    the contigs before it (+ `gap`), so reads stay sorted by Frag::cmp, no read of one contig can overlap a block of
+    another, and every block is phased exactly as in a per-contig call (blocks are independent units,
+    graph_processing.rs:345-362).  This is how a rank pushes its whole share of a many-contig work queue through the
+    GPU at once instead of one latency-bound call per contig.
+    contigs: list of Frags; blocks: list of (blk_lo, blk_hi) arrays (1-based SNP ranges per contig).
+    Returns (frags, blk_lo, blk_hi, block_contig, read_offset[k], pos_offset[k])."""
+    from .frags import Frags
+
+    row_ptr, pos, allele, qual, first, last = [np.zeros(1, np.uint64)], [], [], [], [], []
+    lo_all, hi_all, owner = [], [], []
+    read_off, pos_off = [], []
+    p0, c0, r0 = 0, 0, 0
+    for k, (fr, (lo, hi)) in enumerate(zip(contigs, blocks)):
+        read_off.append(r0)
+        pos_off.append(p0)
+        row_ptr.append(fr.row_ptr[1:] + np.uint64(c0))
+        pos.append(fr.pos + np.uint32(p0))
+        allele.append(fr.allele)
+        qual.append(fr.qual)
+        first.append(fr.first + np.uint32(p0))
+        last.append(fr.last + np.uint32(p0))
+        lo_all.append(np.asarray(lo, np.uint32) + np.uint32(p0))
+        hi_all.append(np.asarray(hi, np.uint32) + np.uint32(p0))
+        owner.append(np.full(len(lo), k, np.int64))
+        span = max(int(fr.last.max()) if fr.n_reads else 0, int(np.max(hi)) if len(hi) else 0)
+        p0 += span + gap
+        c0 += fr.nnz
+        r0 += fr.n_reads
+        if p0 >= 2 ** 32 - 2 ** 20:
+            raise ValueError("batched contigs exceed the 32-bit SNP index space")
+    cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)
+    frags = Frags(cat(row_ptr, np.uint64), cat(pos, np.uint32), cat(allele, np.uint8), cat(qual, np.uint8),
+                  cat(first, np.uint32), cat(last, np.uint32))
+    return (frags, cat(lo_all, np.uint32), cat(hi_all, np.uint32), cat(owner, np.int64), np.array(read_off, np.int64),
+            np.array(pos_off, np.int64))
+
+
 def gather_records(unit_ids, read_ptr, read_ids, hap, best_ploidy, device, dst=0):
     """Variable-length gather of per-unit partition records to rank `dst`.
     Every rank passes the records of the units it owns; returns on dst a dict unit_id -> (best_ploidy, read_ids, hap)

@@ -3,6 +3,7 @@ import os
 import socket
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -75,3 +76,70 @@ def test_gather_records_world2_gloo():
 def test_gather_records_single_process():
     res = shard.gather_records([4, 2], [0, 2, 3], [10, 11, 20], [0, 1, 0], [2, 1], torch.device("cpu"))
     assert res[4][0] == 2 and list(res[4][1]) == [10, 11] and list(res[2][2]) == [0]
+
+
+def _metagenome(n_contigs, n_reads, n_snps):
+    from floria_b200 import api, synth
+
+    contigs, blocks = [], []
+    for k in range(n_contigs):
+        c = synth.config5_contig(k, n_reads=n_reads, n_snps=n_snps, span_mean=40)
+        contigs.append(c.frags)
+        blocks.append(api.get_range_with_lengths(c.snp_to_genome_pos, 4000, 4000 // 3, 0.0005))
+    return contigs, blocks
+
+
+def test_concat_contigs_is_equivalent_to_per_contig_calls_oracle():
+    """configs[4]-shaped input (many small contigs, mixed ploidy 2..6) at reduced size: one batched call over the
+    concatenated contigs gives, block for block, the per-contig results (CPU oracle on both sides)."""
+    import oracle
+    from floria_b200 import default_params, shard
+
+    contigs, blocks = _metagenome(4, 90, 80)
+    prm = default_params(epsilon=0.04, max_ploidy=4)
+    fr, lo, hi, owner, read_off, _ = shard.concat_contigs(contigs, blocks)
+    assert fr.is_sorted()
+    big = oracle.phase_blocks(fr, lo, hi, prm, n_threads=4)
+    j = 0
+    for k, (c, (clo, chi)) in enumerate(zip(contigs, blocks)):
+        one = oracle.phase_blocks(c, clo, chi, prm, n_threads=2)
+        for b in range(one.n_blocks):
+            assert owner[j] == k
+            assert big.best_ploidy[j] == one.best_ploidy[b]
+            a0, a1 = int(big.read_ptr[j]), int(big.read_ptr[j + 1])
+            b0, b1 = int(one.read_ptr[b]), int(one.read_ptr[b + 1])
+            assert np.array_equal(big.read_ids[a0:a1] - read_off[k], one.read_ids[b0:b1])
+            assert np.array_equal(big.hap[a0:a1], one.hap[b0:b1])
+            assert np.array_equal(big.mec_vector[j].view(np.uint64), one.mec_vector[b].view(np.uint64))
+            j += 1
+    assert j == big.n_blocks
+
+
+@pytest.mark.gpu
+def test_batched_metagenome_matches_oracle_and_per_contig_calls_gpu():
+    """The same equivalence through the CUDA path, plus bit-exact agreement of the batched call with the oracle."""
+    import oracle
+    from floria_b200 import api, default_params, shard
+
+    contigs, blocks = _metagenome(6, 120, 100)
+    prm = default_params(epsilon=0.04, max_ploidy=6)
+    fr, lo, hi, owner, read_off, _ = shard.concat_contigs(contigs, blocks)
+    ctx = api.Context(0)
+    try:
+        big = ctx.phase_blocks(fr, lo, hi, prm)
+        ref = oracle.phase_blocks(fr, lo, hi, prm, n_threads=8)
+        assert np.array_equal(big.best_ploidy, ref.best_ploidy) and np.array_equal(big.hap, ref.hap)
+        assert np.array_equal(big.mec_vector.view(np.uint64), ref.mec_vector.view(np.uint64))
+        assert big.cells == ref.cells
+        j = 0
+        for k, (c, (clo, chi)) in enumerate(zip(contigs, blocks)):
+            one = ctx.phase_blocks(c, clo, chi, prm)
+            for b in range(one.n_blocks):
+                a0, a1 = int(big.read_ptr[j]), int(big.read_ptr[j + 1])
+                b0, b1 = int(one.read_ptr[b]), int(one.read_ptr[b + 1])
+                assert big.best_ploidy[j] == one.best_ploidy[b]
+                assert np.array_equal(big.hap[a0:a1], one.hap[b0:b1])
+                j += 1
+        assert j == big.n_blocks
+    finally:
+        ctx.close()
