@@ -179,6 +179,25 @@ __device__ __forceinline__ unsigned long long fb_warp_sum_u64(unsigned long long
 }
 __device__ __forceinline__ uint32_t fb_warp_sum_u32(uint32_t v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
 
+// sub-warp teams of L consecutive lanes (L = 32, 8 or 2): short reads get a team each instead of a whole warp.  Every
+// shuffle of a team names only the team's lanes in its mask, so the teams of a warp may diverge freely.
+template <int L>
+__device__ __forceinline__ uint32_t fb_team_mask() {
+    return L == 32 ? 0xFFFFFFFFu : (((1u << (L & 31)) - 1u) << ((fb_lane() / L) * L));
+}
+template <int L>
+__device__ __forceinline__ unsigned long long fb_team_sum_u64(unsigned long long v, uint32_t mask) {
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+    return v;
+}
+template <int L>
+__device__ __forceinline__ uint32_t fb_team_sum_u32(uint32_t v, uint32_t mask) {
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+    return v;
+}
+
 // first index i in [0,n] with prefix[i+1] > x, for an ascending prefix array of n+1 entries (prefix[0] == 0)
 __device__ __forceinline__ int fb_upper_seg(const uint64_t *__restrict__ prefix, int n, uint64_t x) {
     int lo = 0, hi = n;

@@ -159,6 +159,7 @@ struct Engine {
     uint8_t *d_assign[2] = {nullptr, nullptr};
     uint64_t *d_cnt[2] = {nullptr, nullptr};
     uint2 *d_masks[2] = {nullptr, nullptr};
+    int sweep_team = 0;  // lanes per read of k_sweep (0 = not chosen yet)
     double *d_mec[2] = {nullptr, nullptr};
     double *d_gain = nullptr;
     MoveRec *d_moves = nullptr;
@@ -429,26 +430,38 @@ struct Engine {
         cudaEvent_t e0 = fb_event(ctx);
         uint32_t pmax = 1;
         for (const InstDev &in : inst) pmax = std::max(pmax, in.ploidy);
-        const unsigned grid = (unsigned)((tot_assign + FB_SWEEP_WARPS - 1) / FB_SWEEP_WARPS);
+        // lanes per read: a whole warp for long reads, teams of 8 / 2 lanes when the reads span few 16-SNP groups
+        if (sweep_team == 0) {
+            uint64_t g = 0;
+            for (const RInfo &r : rinfo) g += r.lg1 - r.lg0;
+            const double avg = rinfo.empty() ? 32.0 : (double)g / (double)rinfo.size();
+            sweep_team = avg > 12.0 ? 32 : (avg > 2.5 ? 8 : 2);
+            if (getenv("FB_SWEEP_TEAM")) sweep_team = atoi(getenv("FB_SWEEP_TEAM"));
+        }
         // FB_SWEEP_TMA=1 selects the cp.async.bulk (1-D TMA) staged variant.  Measured on configs[2] (profiles/): the sweep
         // is instruction-issue bound, so the staging does not pay (p=4: 5.0 vs 4.7 ms, p=2: 3.0 vs 2.5 ms); default off.
         static const bool use_tma = getenv("FB_SWEEP_TMA") && atoi(getenv("FB_SWEEP_TMA")) != 0;
         const unsigned blk = FB_SWEEP_WARPS * 32;
-        if (use_tma) {
-            if (pmax <= 2)
-                k_sweep<2, true><<<grid, blk, 0, ctx->stream>>>(a);
-            else if (pmax <= 4)
-                k_sweep<4, true><<<grid, blk, 0, ctx->stream>>>(a);
-            else
-                k_sweep<8, true><<<grid, blk, 0, ctx->stream>>>(a);
-        } else {
-            if (pmax <= 2)
-                k_sweep<2, false><<<grid, blk, 0, ctx->stream>>>(a);
-            else if (pmax <= 4)
-                k_sweep<4, false><<<grid, blk, 0, ctx->stream>>>(a);
-            else
-                k_sweep<8, false><<<grid, blk, 0, ctx->stream>>>(a);
-        }
+        const unsigned teams = FB_SWEEP_WARPS * (32 / (sweep_team == 8 ? 8 : (sweep_team == 2 ? 2 : 32)));
+        const unsigned grid = (unsigned)((tot_assign + teams - 1) / teams);
+#define FB_LAUNCH_SWEEP(TMA_, L_)                                            \
+    do {                                                                     \
+        if (pmax <= 2)                                                       \
+            k_sweep<2, TMA_, L_><<<grid, blk, 0, ctx->stream>>>(a);          \
+        else if (pmax <= 4)                                                  \
+            k_sweep<4, TMA_, L_><<<grid, blk, 0, ctx->stream>>>(a);          \
+        else                                                                 \
+            k_sweep<8, TMA_, L_><<<grid, blk, 0, ctx->stream>>>(a);          \
+    } while (0)
+        if (sweep_team == 8)
+            FB_LAUNCH_SWEEP(false, 8);
+        else if (sweep_team == 2)
+            FB_LAUNCH_SWEEP(false, 2);
+        else if (use_tma)
+            FB_LAUNCH_SWEEP(true, 32);
+        else
+            FB_LAUNCH_SWEEP(false, 32);
+#undef FB_LAUNCH_SWEEP
         cudaEvent_t e1 = fb_event(ctx);
         sweep_ev.push_back(std::make_pair(e0, e1));
         ctx->tim.n_launches++;

@@ -92,12 +92,16 @@ struct SweepArgs {
 // Planes of groups beyond `hi` are empty.  Per chunk of 32 groups the lanes are split by ballot into runs of
 // epsilon-free lanes (added as ONE exact integer lump when SeqSum proves that identical to item-by-item addition)
 // and lanes holding epsilon items (replayed item by item).
-__device__ double fb_replay_diff(const DFragsDev &fr, uint32_t g0, uint32_t g1, const uint2 *__restrict__ mh,
-                                 uint32_t lg0, int hi, const uint32_t *lut, double eps, uint32_t *wscratch /*16 per warp*/) {
-    const uint32_t lane = fb_lane();
+template <int L>
+__device__ double fb_replay_diff_t(const DFragsDev &fr, uint32_t g0, uint32_t g1, const uint2 *__restrict__ mh,
+                                   uint32_t lg0, int hi, const uint32_t *lut, double eps, uint32_t *wscratch /*16 per team*/) {
+    const uint32_t lane = fb_lane() % L;               // lane inside the team
+    const uint32_t tmask = fb_team_mask<L>();          // the team's lanes
+    const uint32_t tshift = (fb_lane() / L) * L;
+    const uint32_t lowmask = L == 32 ? 0xFFFFFFFFu : ((1u << (L & 31)) - 1u);
     SeqSum ss;
     ss.init();
-    for (uint32_t base = g0; base < g1; base += 32) {
+    for (uint32_t base = g0; base < g1; base += L) {
         uint32_t g = base + lane;
         bool valid = g < g1;
         uint32_t w[16];
@@ -118,32 +122,32 @@ __device__ double fb_replay_diff(const DFragsDev &fr, uint32_t g0, uint32_t g1, 
             for (int k = 0; k < 16; ++k) w[k] = 0;
         }
         const long long Wl = (long long)fb_masked_sum(w, diffbits);
-        const unsigned E = __ballot_sync(0xFFFFFFFFu, emptybits != 0);
+        const unsigned E = (__ballot_sync(tmask, emptybits != 0) >> tshift) & lowmask;
         // inclusive prefix sums of the per-lane dyadic sums
         long long pre = Wl;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            long long v = __shfl_up_sync(0xFFFFFFFFu, pre, o);
+        for (int o = 1; o < L; o <<= 1) {
+            long long v = __shfl_up_sync(tmask, pre, o, L);
             if ((int)lane >= o) pre += v;
         }
         int cur = 0;
-        while (cur < 32) {
+        while (cur < L) {
             const unsigned rest = E >> cur;
-            const int e = rest ? cur + __ffs(rest) - 1 : 32;  // next lane holding epsilon items
+            const int e = rest ? cur + __ffs(rest) - 1 : L;  // next lane holding epsilon items
             if (e > cur) {
-                const long long hi_sum = __shfl_sync(0xFFFFFFFFu, pre, e - 1);
-                const long long lo_sum = cur ? __shfl_sync(0xFFFFFFFFu, pre, cur - 1) : 0;
+                const long long hi_sum = __shfl_sync(tmask, pre, e - 1, L);
+                const long long lo_sum = cur ? __shfl_sync(tmask, pre, cur - 1, L) : 0;
                 if (!ss.add_dyadic_run(hi_sum - lo_sum)) {
                     for (int l = cur; l < e; ++l) {
-                        const long long Wl_l = __shfl_sync(0xFFFFFFFFu, Wl, l);
+                        const long long Wl_l = __shfl_sync(tmask, Wl, l, L);
                         if (ss.add_dyadic_run(Wl_l)) continue;
-                        const uint32_t db = __shfl_sync(0xFFFFFFFFu, diffbits, l);
-                        __syncwarp();
+                        const uint32_t db = __shfl_sync(tmask, diffbits, l, L);
+                        __syncwarp(tmask);
                         if ((int)lane == l) {
 #pragma unroll
                             for (int k = 0; k < 16; ++k) wscratch[k] = w[k];
                         }
-                        __syncwarp();
+                        __syncwarp(tmask);
                         uint32_t bits = db;
                         while (bits) {
                             const int k = __ffs(bits) - 1;
@@ -153,18 +157,19 @@ __device__ double fb_replay_diff(const DFragsDev &fr, uint32_t g0, uint32_t g1, 
                     }
                 }
             }
-            if (e == 32) break;
-            const uint32_t eb = __shfl_sync(0xFFFFFFFFu, emptybits, e);
-            const uint32_t db = __shfl_sync(0xFFFFFFFFu, diffbits, e);
+            if (e == L) break;
+            const uint32_t eb = __shfl_sync(tmask, emptybits, e, L);
+            const uint32_t db = __shfl_sync(tmask, diffbits, e, L);
             if (db == 0) {
-                for (int n = __popc(eb); n > 0; --n) ss.add_eps(eps, 0);  // an all-epsilon lane needs no weights
+                ss.S = fb_add_eps_n(ss.S, eps, (unsigned long long)__popc(eb));  // an all-epsilon lane needs no weights
+                ss.tail = 1;
             } else {
-                __syncwarp();
+                __syncwarp(tmask);
                 if ((int)lane == e) {
 #pragma unroll
                     for (int k = 0; k < 16; ++k) wscratch[k] = w[k];
                 }
-                __syncwarp();
+                __syncwarp(tmask);
                 uint32_t bits = eb | db;
                 while (bits) {
                     const int k = __ffs(bits) - 1;
@@ -180,11 +185,16 @@ __device__ double fb_replay_diff(const DFragsDev &fr, uint32_t g0, uint32_t g1, 
     }
     return ss.S;
 }
+__device__ __forceinline__ double fb_replay_diff(const DFragsDev &fr, uint32_t g0, uint32_t g1, const uint2 *__restrict__ mh,
+                                                 uint32_t lg0, int hi, const uint32_t *lut, double eps, uint32_t *wscratch) {
+    return fb_replay_diff_t<32>(fr, g0, g1, mh, lg0, hi, lut, eps, wscratch);
+}
 
-template <int P, int MODE, bool TMA>
+template <int P, int MODE, bool TMA, int L>
 __device__ void fb_sweep_body(const SweepArgs &a, const InstDev &in, int ii, uint64_t slot, const RInfo ri,
                               const uint32_t *lut_s, uint32_t *wscratch, SweepStage *stg, uint64_t *bars) {
-    const uint32_t lane = fb_lane();
+    const uint32_t lane = fb_lane() % L;  // lane inside the team of L lanes that owns this read
+    const uint32_t tmask = fb_team_mask<L>();
     const int cur = a.st[ii].cur;
     const uint2 *__restrict__ masks = a.masks[cur] + in.mask_off;
     const uint32_t g0 = a.fr.gptr[ri.rid], g1 = g0 + (ri.lg1 - ri.lg0);
@@ -258,26 +268,26 @@ __device__ void fb_sweep_body(const SweepArgs &a, const InstDev &in, int ii, uin
             al_n = a.fr.allele[g];
             pr_n = a.fr.present[g];
         }
-        for (; g < g1; g += 32) {
+        for (; g < g1; g += L) {
             const uint4 q = q_n;
             const uint32_t al = al_n, pr = pr_n;
-            if (g + 32 < g1) {
-                q_n = a.fr.qual[g + 32];
-                al_n = a.fr.allele[g + 32];
-                pr_n = a.fr.present[g + 32];
+            if (g + L < g1) {
+                q_n = a.fr.qual[g + L];
+                al_n = a.fr.allele[g + L];
+                pr_n = a.fr.present[g + L];
             }
             score_group(q, al, pr, g);
         }
     }
     double diff_f[P];
     long long same_q[P], diff_q[P];
-    if (MODE == FB_SWEEP_SCORE) total = fb_warp_sum_u64(total);
+    if (MODE == FB_SWEEP_SCORE) total = fb_team_sum_u64<L>(total, tmask);
 #pragma unroll
     for (int h = 0; h < P; ++h) {
-        acc[h] = fb_warp_sum_u64(acc[h]);
-        ne_cnt[h] = fb_warp_sum_u32(ne_cnt[h]);
+        acc[h] = fb_team_sum_u64<L>(acc[h], tmask);
+        ne_cnt[h] = fb_team_sum_u32<L>(ne_cnt[h], tmask);
         if (MODE == FB_SWEEP_SCORE) {
-            emptyw[h] = fb_warp_sum_u64(emptyw[h]);
+            emptyw[h] = fb_team_sum_u64<L>(emptyw[h], tmask);
             same_q[h] = (long long)acc[h];
             diff_q[h] = (long long)(total - acc[h] - emptyw[h]);
         } else {
@@ -293,7 +303,7 @@ __device__ void fb_sweep_body(const SweepArgs &a, const InstDev &in, int ii, uin
             // every term is a multiple of 2^-26: the sum is exact in any order
             diff_f[h] = fb_q26_to_f64(diff_q[h] + (long long)ne_cnt[h] * (long long)(a.eps * FB_Q26));
         } else {
-            diff_f[h] = fb_replay_diff(a.fr, g0, g1, masks + (uint32_t)h * in.ng, ri.lg0, 0x7FFFFFFF, lut_s, a.eps, wscratch);
+            diff_f[h] = fb_replay_diff_t<L>(a.fr, g0, g1, masks + (uint32_t)h * in.ng, ri.lg0, 0x7FFFFFFF, lut_s, a.eps, wscratch);
         }
     }
     if (lane != 0) return;
@@ -329,22 +339,26 @@ __device__ void fb_sweep_body(const SweepArgs &a, const InstDev &in, int ii, uin
     }
 }
 
-template <int P, bool TMA>
+template <int P, bool TMA, int L>
 __device__ __forceinline__ void fb_sweep_dispatch(const SweepArgs &a, const InstDev &in, int ii, uint64_t slot,
                                                   const RInfo ri, const uint32_t *lut_s, uint32_t *ws, SweepStage *stg,
                                                   uint64_t *bars) {
     if (a.mode == FB_SWEEP_SCORE)
-        fb_sweep_body<P, FB_SWEEP_SCORE, TMA>(a, in, ii, slot, ri, lut_s, ws, stg, bars);
+        fb_sweep_body<P, FB_SWEEP_SCORE, TMA, L>(a, in, ii, slot, ri, lut_s, ws, stg, bars);
     else
-        fb_sweep_body<P, FB_SWEEP_MOVES, TMA>(a, in, ii, slot, ri, lut_s, ws, stg, bars);
+        fb_sweep_body<P, FB_SWEEP_MOVES, TMA, L>(a, in, ii, slot, ri, lut_s, ws, stg, bars);
 }
 
 // PMAX = largest ploidy this instantiation handles: the register budget of a kernel is that of its widest path, so the
-// host launches the narrowest variant that covers the batch (2, 4 or 8).
-template <int PMAX, bool TMA>
+// host launches the narrowest variant that covers the batch (2, 4 or 8).  L = lanes per read: a whole warp for long
+// reads, teams of 8 or 2 lanes for short ones (a paired short read has 1-2 groups; a 100-SNP read 7), so that the lanes
+// of a warp are not idle.  Teams diverge freely (fb_team_mask), e.g. across an instance boundary with another ploidy.
+template <int PMAX, bool TMA, int L>
 __global__ void __launch_bounds__(FB_SWEEP_WARPS * 32) k_sweep(SweepArgs a) {
+    static_assert(!TMA || L == 32, "the TMA staging is per warp");
+    constexpr int TEAMS = 32 / L;
     __shared__ uint32_t lut_s[256];
-    __shared__ uint32_t wscr[FB_SWEEP_WARPS][16];
+    __shared__ uint32_t wscr[FB_SWEEP_WARPS * TEAMS][16];
     __shared__ SweepStage stages[TMA ? FB_SWEEP_WARPS : 1][TMA ? FB_SWEEP_STAGES : 1];
     __shared__ __align__(8) uint64_t mbars[TMA ? FB_SWEEP_WARPS : 1][FB_SWEEP_STAGES];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut_s[i] = a.lut[i];
@@ -356,22 +370,23 @@ __global__ void __launch_bounds__(FB_SWEEP_WARPS * 32) k_sweep(SweepArgs a) {
     SweepStage *stg = stages[TMA ? (threadIdx.x >> 5) : 0];
     uint64_t *bars = mbars[TMA ? (threadIdx.x >> 5) : 0];
     const uint64_t total = a.assign_prefix[a.n_inst];
-    const uint64_t slot = (uint64_t)blockIdx.x * FB_SWEEP_WARPS + (threadIdx.x >> 5);
+    const uint32_t team = threadIdx.x / L;  // team index inside the CTA
+    const uint64_t slot = (uint64_t)blockIdx.x * (FB_SWEEP_WARPS * TEAMS) + team;
     if (slot >= total) return;
     const int ii = fb_upper_seg(a.assign_prefix, a.n_inst, slot);
     const InstDev in = a.inst[ii];
     if (a.mode == FB_SWEEP_MOVES && !a.st[ii].active) return;
     const RInfo ri = a.rinfo[in.read_off + (uint32_t)(slot - in.assign_off)];
-    uint32_t *ws = wscr[threadIdx.x >> 5];
+    uint32_t *ws = wscr[team];
     switch (in.ploidy) {
-        case 1: fb_sweep_dispatch<1, TMA>(a, in, ii, slot, ri, lut_s, ws, stg, bars); break;
-        case 2: fb_sweep_dispatch<2, TMA>(a, in, ii, slot, ri, lut_s, ws, stg, bars); break;
-        case 3: if (PMAX >= 3) fb_sweep_dispatch<(PMAX >= 3 ? 3 : 1), TMA>(a, in, ii, slot, ri, lut_s, ws, stg, bars); break;
-        case 4: if (PMAX >= 4) fb_sweep_dispatch<(PMAX >= 4 ? 4 : 1), TMA>(a, in, ii, slot, ri, lut_s, ws, stg, bars); break;
-        case 5: if (PMAX >= 5) fb_sweep_dispatch<(PMAX >= 5 ? 5 : 1), TMA>(a, in, ii, slot, ri, lut_s, ws, stg, bars); break;
-        case 6: if (PMAX >= 6) fb_sweep_dispatch<(PMAX >= 6 ? 6 : 1), TMA>(a, in, ii, slot, ri, lut_s, ws, stg, bars); break;
-        case 7: if (PMAX >= 7) fb_sweep_dispatch<(PMAX >= 7 ? 7 : 1), TMA>(a, in, ii, slot, ri, lut_s, ws, stg, bars); break;
-        case 8: if (PMAX >= 8) fb_sweep_dispatch<(PMAX >= 8 ? 8 : 1), TMA>(a, in, ii, slot, ri, lut_s, ws, stg, bars); break;
+        case 1: fb_sweep_dispatch<1, TMA, L>(a, in, ii, slot, ri, lut_s, ws, stg, bars); break;
+        case 2: fb_sweep_dispatch<2, TMA, L>(a, in, ii, slot, ri, lut_s, ws, stg, bars); break;
+        case 3: if (PMAX >= 3) fb_sweep_dispatch<(PMAX >= 3 ? 3 : 1), TMA, L>(a, in, ii, slot, ri, lut_s, ws, stg, bars); break;
+        case 4: if (PMAX >= 4) fb_sweep_dispatch<(PMAX >= 4 ? 4 : 1), TMA, L>(a, in, ii, slot, ri, lut_s, ws, stg, bars); break;
+        case 5: if (PMAX >= 5) fb_sweep_dispatch<(PMAX >= 5 ? 5 : 1), TMA, L>(a, in, ii, slot, ri, lut_s, ws, stg, bars); break;
+        case 6: if (PMAX >= 6) fb_sweep_dispatch<(PMAX >= 6 ? 6 : 1), TMA, L>(a, in, ii, slot, ri, lut_s, ws, stg, bars); break;
+        case 7: if (PMAX >= 7) fb_sweep_dispatch<(PMAX >= 7 ? 7 : 1), TMA, L>(a, in, ii, slot, ri, lut_s, ws, stg, bars); break;
+        case 8: if (PMAX >= 8) fb_sweep_dispatch<(PMAX >= 8 ? 8 : 1), TMA, L>(a, in, ii, slot, ri, lut_s, ws, stg, bars); break;
         default: break;
     }
 }

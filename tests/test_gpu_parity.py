@@ -131,6 +131,31 @@ def test_optimize_clustering_matches_oracle(ctx, case, eps, ploidy):
     assert gnr == onr
 
 
+@pytest.mark.parametrize("team", [32, 8, 2])
+@pytest.mark.parametrize("case", ["long", "short", "edge"])
+def test_sweep_team_sizes_match_oracle(ctx, monkeypatch, team, case):
+    """k_sweep gives a read a whole warp or a team of 8 / 2 lanes depending on how many 16-SNP groups the reads span
+    (chosen per launch from the average); every team size must give the oracle's answer on every kind of input,
+    including the exact epsilon replay (eps = 0.04) inside a team."""
+    monkeypatch.setenv("FB_SWEEP_TEAM", str(team))
+    fr = CASES[case]()
+    rng = np.random.default_rng(21)
+    sel = np.arange(fr.n_reads, dtype=np.uint32)
+    for eps in EPS:
+        prm = default_params(epsilon=eps)
+        for ploidy in (2, 3, 5):
+            hap = random_assignment(rng, len(sel), ploidy)
+            o_same, o_diff = oracle.score_reads(fr, sel, hap, ploidy, prm)
+            same, diff, _, _, _ = ctx.score_reads(fr, sel, hap, ploidy, prm)
+            assert_f64_identical(same, o_same, f"same team={team} p={ploidy}")
+            assert_f64_identical(diff, o_diff, f"diff team={team} p={ploidy}")
+            hap0 = random_assignment(rng, len(sel), ploidy, 0.0)
+            oh, osc, onr = oracle.optimize_clustering(fr, sel, hap0, ploidy, prm)
+            gh, gsc, gnr = ctx.optimize_clustering(fr, sel, hap0, ploidy, prm)
+            assert np.array_equal(gh, oh) and gnr == onr
+            assert_f64_identical([gsc], [osc], "score")
+
+
 def test_optimize_keeps_singleton_haplotypes(ctx):
     # `if new_part[i].len() == 1 { continue; }` (local_clustering.rs:346) and `partition[i].len() <= 1` (:301)
     fr = CASES["long"]()
