@@ -20,7 +20,6 @@ import os
 import statistics
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -43,54 +42,65 @@ def hbm_peak():
 
 
 class ClockSampler:
-    """SM clock / throttle-reason sampler (NVML in-process; nvidia-smi would stall the driver at start-up)."""
+    """SM clock / throttle-reason sampler.  Runs NVML in a CHILD PROCESS (started before the timed region, polled every
+    20 ms): an in-process sampler thread was measured to cost ~1 ms per 16 ms step (GIL hand-offs against the thread
+    that launches kernels), and nvidia-smi itself stalls for a second at start-up."""
 
+    CHILD = r"""
+import sys, time, pynvml as nv
+nv.nvmlInit()
+h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+print("max", nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM), flush=True)
+sys.stdin.readline()                      # "go"
+import select
+while True:
+    if select.select([sys.stdin], [], [], float(sys.argv[2]))[0]:
+        break                             # "stop"
+    print(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), int(nv.nvmlDeviceGetCurrentClocksEventReasons(h)), flush=True)
+"""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
                0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index, period=0.02):
-        self.index, self.period = index, period
-        self.sm, self.reasons, self.max_mhz = [], set(), None
-        self.stop_flag = threading.Event()
         self.ok = False
+        self.max_mhz = None
         try:
-            import pynvml
-
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
-            self.ok = True
+            # CUDA_VISIBLE_DEVICES remaps CUDA ordinals, not NVML indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                index = int(vis.split(",")[index])
+            self.p = subprocess.Popen([sys.executable, "-c", self.CHILD, str(index), str(period)], stdin=subprocess.PIPE,
+                                      stdout=subprocess.PIPE, text=True)
+            line = self.p.stdout.readline().split()
+            if line and line[0] == "max":
+                self.max_mhz = float(line[1])
+                self.ok = True
         except Exception as e:  # pragma: no cover
             self.err = str(e)
 
-    def _loop(self):
-        nv = self.nv
-        while not self.stop_flag.is_set():
-            try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-                for bit, name in self.REASONS.items():
-                    if r & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            time.sleep(self.period)
-
     def start(self):
         if self.ok:
-            self.sm, self.reasons = [], set()
-            self.stop_flag.clear()
-            self.thread = threading.Thread(target=self._loop, daemon=True)
-            self.thread.start()
+            self.p.stdin.write("go\n")
+            self.p.stdin.flush()
 
     def stop(self):
         if not self.ok:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
-        self.stop_flag.set()
-        self.thread.join(timeout=1)
-        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
-                "samples": len(self.sm), "reasons": sorted(self.reasons)}
+        try:
+            out, _ = self.p.communicate("stop\n", timeout=5)
+        except Exception:  # pragma: no cover
+            self.p.kill()
+            out = ""
+        sm, reasons = [], set()
+        for ln in out.splitlines():
+            f = ln.split()
+            if len(f) == 2:
+                sm.append(float(f[0]))
+                for bit, name in self.REASONS.items():
+                    if int(f[1]) & bit:
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "samples": len(sm),
+                "reasons": sorted(reasons)}
 
 
 def make_workload(rank):
@@ -339,7 +349,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

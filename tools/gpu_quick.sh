@@ -8,4 +8,7 @@ python tools/c3_once.py 100000 50000 2 5 2>&1 | tee gpurun_out/c3_p2.log
 python tools/prof_phase.py 2>&1 | tee gpurun_out/phase.log
 if [ -n "$NCU" ]; then
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_sweep|k_hist$' -c 2 -f -o gpurun_out/prof_c3 python tools/c3_once.py 100000 50000 4 1 > gpurun_out/prof_c3.log 2>&1
+ncu -i gpurun_out/prof_c3.ncu-rep --page raw --csv > gpurun_out/prof_c3.raw.csv 2>/dev/null
+ncu -i gpurun_out/prof_c3.ncu-rep --page source --csv > gpurun_out/prof_c3.source.csv 2>/dev/null
+rm -f gpurun_out/prof_c3.ncu-rep
 fi

@@ -14,7 +14,7 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
 
 
 def export(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    out = open(path).read() if path.endswith(".csv") else subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     res = []
