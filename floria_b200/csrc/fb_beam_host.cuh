@@ -45,8 +45,9 @@ static int fb_run_beam(fb_ctx *ctx, Engine &e, const fb_params *prm, const BeamT
     if (L.total > 200 * 1024) FB_FAIL(FB_ERR_LIMIT, "beam search needs %u bytes of shared memory", L.total);
     // many instances: 128-thread CTAs, two per SM (the per-read dependency chains of two instances interleave);
     // few instances: 256-thread CTAs, one per SM (shortest chain per step)
-    const bool small_cta = order.size() >= (size_t)ctx->sm_count * 2 && maxW <= FB_BEAM_THREADS_SMALL &&
-                           !(getenv("FB_BEAM_CTA") && atoi(getenv("FB_BEAM_CTA")) == 256);
+    const int forced = getenv("FB_BEAM_CTA") ? atoi(getenv("FB_BEAM_CTA")) : 0;  // tests / A-B runs: 128 or 256
+    const bool small_cta = maxW <= FB_BEAM_THREADS_SMALL && forced != FB_BEAM_THREADS &&
+                           (forced == FB_BEAM_THREADS_SMALL || order.size() >= (size_t)ctx->sm_count * 2);
     const int nt = small_cta ? FB_BEAM_THREADS_SMALL : FB_BEAM_THREADS;
     auto kern = small_cta ? k_beam<FB_BEAM_THREADS_SMALL> : k_beam<FB_BEAM_THREADS>;
     FB_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));

@@ -132,22 +132,6 @@ __device__ __forceinline__ uint32_t fb_masked_sum(const uint32_t (&w)[16], uint3
     return s;
 }
 
-// s + w computed as a multiply-add by an opaque 1 (a kernel parameter), so the add issues on the FMA pipe (IMAD)
-// instead of the ALU pipe that already carries the bit tests: ncu showed the scoring kernels ALU-pipe bound with the
-// FMA pipe idle (profiles/r01_*).
-__device__ __forceinline__ uint32_t fb_add_fma(uint32_t s, uint32_t w, uint32_t one) {
-    uint32_t r;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(one), "r"(s));
-    return r;
-}
-__device__ __forceinline__ uint32_t fb_masked_sum_fma(const uint32_t (&w)[16], uint32_t bits, uint32_t one) {
-    uint32_t s = 0;
-#pragma unroll
-    for (int k = 0; k < 16; ++k)
-        if (bits & (1u << k)) s = fb_add_fma(s, w[k], one);
-    return s;
-}
-
 // acc += w when (bits & m) != 0, as `and` + `setp` + a predicated add.  With the 16 tests of one bit word issued back to
 // back ptxas turns the tests into two R2P (7 predicates each) + two LOP3.P instead of 16 LOP3.P, and picks
 // IMAD.IADD / IADD3 for the adds to balance the FMA and ALU pipes (profiles/: the scoring kernels are bound by the ALU

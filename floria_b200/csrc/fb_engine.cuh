@@ -358,7 +358,6 @@ struct Engine {
         a.buf = buf;
         a.only_active = only_active;
         a.assign_cur = assign_cur;
-        a.one = 1u;
         cudaEvent_t e0 = fb_event(ctx);
         if (any_split) {
             cudaMemsetAsync(d_done, 0, std::max<uint64_t>(tot_done, 1) * 4, ctx->stream);
@@ -421,7 +420,6 @@ struct Engine {
         a.eps = eps;
         a.eps_safe = eps_safe;
         a.mode = mode;
-        a.one = 1u;
         a.gain = d_gain;
         return a;
     }

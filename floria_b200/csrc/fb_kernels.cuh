@@ -78,7 +78,6 @@ struct SweepArgs {
     double eps;
     int eps_safe;
     int mode;
-    uint32_t one;  // == 1, opaque to the compiler (see fb_add_fma)
     // MOVES
     double *gain;
     // SCORE (any may be null)
@@ -453,7 +452,6 @@ struct HistArgs {
     int buf;
     int only_active;  // skip instances whose optimize loop has finished
     int assign_cur;   // 1: read the partition from the CURRENT buffer whatever buffer the table is written to
-    uint32_t one;     // == 1, opaque to the compiler (see fb_add_fma)
 };
 
 // zero the count tables of the instances that merge with atomics
@@ -928,7 +926,6 @@ __global__ void __launch_bounds__(FB_SELECT_THREADS) k_select(SelectArgs a) {
     const int t = threadIdx.x;
     __shared__ uint32_t s_scan[FB_SELECT_THREADS];
     __shared__ uint32_t s_base;
-    __shared__ uint32_t s_M;
     if (t == 0) s_base = 0;
     __syncthreads();
     // 1. compaction in generation order: for i in 0..P, reads ascending, j ascending
@@ -967,7 +964,6 @@ __global__ void __launch_bounds__(FB_SELECT_THREADS) k_select(SelectArgs a) {
     }
     const uint32_t M = s_base;
     if (t == 0) {
-        s_M = M;
         st.n_moves = (int)M;
     }
     // new_part = partition.clone()

@@ -1,4 +1,5 @@
 // fb_lib.cu — the C-ABI of include/floria_b200.h.  Host logic only; kernels live in fb_kernels.cuh / fb_beam.cuh.
+#include <chrono>
 #include <math.h>
 #include <stdlib.h>
 
@@ -540,6 +541,9 @@ int fb_phase_blocks_resident(fb_ctx *ctx, const fb_dfrags *df, uint64_t n_blocks
     if (mp < 1) FB_FAIL(FB_ERR_ARG, "max_ploidy must be >= 1");
     ctx->ev_used = 0;
     cudaEvent_t ev_start = fb_event(ctx);
+    const bool hprof = getenv("FB_HOST_PROF") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tp[8] = {now(), 0, 0, 0, 0, 0, 0, 0};
 
     Engine e;
     e.ctx = ctx;
@@ -557,13 +561,17 @@ int fb_phase_blocks_resident(fb_ctx *ctx, const fb_dfrags *df, uint64_t n_blocks
             if (p == 1) first_inst[j] = ii;
         }
     }
+    tp[1] = now();
     if ((rc = e.finalize_and_upload(prm->epsilon))) return rc;
+    tp[2] = now();
 
     // beam_search_phasing for every instance with ploidy > 1 (ploidy 1: every read lands in haplotype 0)
     BeamRun br;
     if ((rc = fb_run_beam(ctx, e, prm, nullptr, br))) return rc;
+    tp[3] = now();
     // optimize_clustering
     if ((rc = e.run_optimize(prm->num_iter_optimize))) return rc;
+    tp[4] = now();
     // get_mec_stats_epsilon_no_phred on the optimized partition: unweighted histogram into the spare buffer
     if ((rc = e.launch_hist(1, 0, 0, 0, 1))) return rc;
     if ((rc = e.launch_mec(1, 0))) return rc;
@@ -583,6 +591,7 @@ int fb_phase_blocks_resident(fb_ctx *ctx, const fb_dfrags *df, uint64_t n_blocks
     cudaEvent_t ev_end = fb_event(ctx);
     FB_CK(cudaStreamSynchronize(ctx->stream));
     FB_CK(cudaGetLastError());
+    tp[5] = now();
 
     // ---- the ploidy loop and stopping rule of get_local_hap_blocks (graph_processing.rs:132-252), on the host -------------
     fb_block_results *r = (fb_block_results *)calloc(1, sizeof(fb_block_results));
@@ -665,6 +674,10 @@ int fb_phase_blocks_resident(fb_ctx *ctx, const fb_dfrags *df, uint64_t n_blocks
     ctx->tim.download_ms += ms;
     ctx->tim.beam_ms += br.beam_ms;
     *out = r;
+    if (hprof)
+        fprintf(stderr, "[fb_phase_blocks_resident host ms] plan %.2f | finalize+upload %.2f | beam (launch..sync) %.2f | optimize %.2f | "
+                        "final hist/mec + download %.2f | stopping rule + results %.2f\n",
+                tp[1] - tp[0], tp[2] - tp[1], tp[3] - tp[2], tp[4] - tp[3], tp[5] - tp[4], now() - tp[5]);
     return FB_OK;
 }
 

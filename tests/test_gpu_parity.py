@@ -205,6 +205,28 @@ def test_beam_search_high_ploidy_short_reads(ctx, ploidy):
     assert_f64_identical([gsc], [osc], "best score")
 
 
+@pytest.mark.parametrize("cta", [128, 256])
+def test_beam_cta_sizes_match_oracle(ctx, monkeypatch, cta):
+    """k_beam runs 256-thread CTAs (one per SM) for short work queues and 128-thread CTAs (two per SM) for long ones;
+    both instantiations must reproduce the oracle: assignments, score bits, and the whole phase_blocks result."""
+    monkeypatch.setenv("FB_BEAM_CTA", str(cta))
+    for case, ploidy, eps in (("long", 3, 0.04), ("short", 2, 0.03125), ("edge", 4, 0.04)):
+        fr = CASES[case]()
+        prm = default_params(epsilon=eps)
+        sel = np.arange(fr.n_reads, dtype=np.uint32)
+        oh, osc, _ = oracle.beam_search_phasing(fr, sel, ploidy, prm)
+        gh, gsc, _ = ctx.beam_search_phasing(fr, sel, ploidy, prm)
+        assert np.array_equal(gh, oh), f"cta={cta} {case}: {int((gh != oh).sum())} assignments differ"
+        assert_f64_identical([gsc], [osc], "beam score")
+    c = synth.make_contig(52, 260, 240, 3, span_mean=70)
+    prm = default_params(epsilon=0.04, max_ploidy=4)
+    lo, hi = api.get_range_with_lengths(c.snp_to_genome_pos, 6000, 2000, 0.0005)
+    g = ctx.phase_blocks(c.frags, lo, hi, prm)
+    o = oracle.phase_blocks(c.frags, lo, hi, prm, n_threads=4)
+    assert np.array_equal(g.best_ploidy, o.best_ploidy) and np.array_equal(g.hap, o.hap)
+    assert np.array_equal(bits(g.mec_vector), bits(o.mec_vector)) and g.cells == o.cells
+
+
 def test_beam_search_small_beam_and_single_read(ctx):
     fr = CASES["edge"]()
     for B in (1, 3):
