@@ -140,6 +140,9 @@ struct Engine {
     std::vector<InstDev> inst;
     std::vector<InstState> st;
     std::vector<uint64_t> assign_prefix, tile_prefix, hap_prefix, moves_off, done_off;
+    std::vector<uint64_t> mec_chunk_prefix;  // per (instance, haplotype): 32-position chunks of its count table
+    uint64_t *d_mec_chunk_prefix = nullptr;
+    MecChunk *d_mec_chunks = nullptr;
     std::vector<uint32_t> hist_splits;
     uint64_t tot_done = 0;
     uint32_t *d_hist_splits = nullptr, *d_done = nullptr;
@@ -173,6 +176,10 @@ struct Engine {
         fb_cache_free(d_assign_prefix);
         fb_cache_free(d_tile_prefix);
         fb_cache_free(d_hap_prefix);
+        fb_cache_free(d_mec_chunk_prefix);
+        fb_cache_free(d_mec_chunks);
+        d_mec_chunk_prefix = nullptr;
+        d_mec_chunks = nullptr;
         fb_cache_free(d_moves_off);
         fb_cache_free(d_moves_cap);
         fb_cache_free(d_rinfo);
@@ -303,6 +310,11 @@ struct Engine {
         if ((rc = fb_upload(ctx, &d_assign_prefix, assign_prefix))) return rc;
         if ((rc = fb_upload(ctx, &d_tile_prefix, tile_prefix))) return rc;
         if ((rc = fb_upload(ctx, &d_hap_prefix, hap_prefix))) return rc;
+        mec_chunk_prefix.assign(1, 0);
+        for (const InstDev &in : inst)
+            for (uint32_t h = 0; h < in.ploidy; ++h) mec_chunk_prefix.push_back(mec_chunk_prefix.back() + (in.ng + 1) / 2);
+        if ((rc = fb_upload(ctx, &d_mec_chunk_prefix, mec_chunk_prefix))) return rc;
+        if ((rc = fb_dalloc(ctx, &d_mec_chunks, (size_t)std::max<uint64_t>(mec_chunk_prefix.back(), 1)))) return rc;
         if ((rc = fb_upload(ctx, &d_moves_off, moves_off))) return rc;
         if ((rc = fb_upload(ctx, &d_moves_cap, moves_cap))) return rc;
         if ((rc = fb_upload(ctx, &d_rinfo, rinfo))) return rc;
@@ -386,6 +398,8 @@ struct Engine {
         a.st = d_st;
         a.n_inst = n;
         a.hap_prefix = d_hap_prefix;
+        a.chunk_prefix = d_mec_chunk_prefix;
+        a.chunks = d_mec_chunks;
         a.cnt[0] = d_cnt[0];
         a.cnt[1] = d_cnt[1];
         a.mec[0] = d_mec[0];
@@ -396,7 +410,14 @@ struct Engine {
         a.buf = buf;
         a.only_active = only_active;
         cudaEvent_t e0 = fb_event(ctx);
-        k_mec<<<(unsigned)((warps + 7) / 8), 256, 0, ctx->stream>>>(a);
+        const uint64_t n_chunks = mec_chunk_prefix.back();
+        if (n_chunks > 32 * warps) {  // long tables: chunk summaries first, then an ordered fold of the summaries
+            k_mec_chunks<<<(unsigned)((n_chunks + 7) / 8), 256, 0, ctx->stream>>>(a, warps);
+            k_mec<<<(unsigned)((warps + 7) / 8), 256, 0, ctx->stream>>>(a);
+            ctx->tim.n_launches++;
+        } else {
+            k_mec_flat<<<(unsigned)((warps + 7) / 8), 256, 0, ctx->stream>>>(a);
+        }
         cudaEvent_t e1 = fb_event(ctx);
         mec_ev.push_back(std::make_pair(e0, e1));
         ctx->tim.n_launches++;

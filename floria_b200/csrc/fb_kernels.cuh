@@ -749,11 +749,20 @@ __global__ void __launch_bounds__(FB_HIST_THREADS, 2) k_hist(HistArgs a) {
 // counts in ascending-count order; errors += epsilon when max <= 1.0.  The two f64 accumulators are emulated exactly
 // (SeqSum) in canonical position order.
 // ---------------------------------------------------------------------------------------------------------------------
+struct MecChunk {  // summary of 32 consecutive positions of one haplotype table
+    long long bases;   // sum of the consensus counts (units of 2^-26)
+    long long others;  // sum of the non-consensus counts
+    uint32_t eps;      // bit l: position l adds an epsilon (consensus count <= 1.0)
+    uint32_t _pad[3];
+};
+
 struct MecArgs {
     const InstDev *inst;
     const InstState *st;
     int n_inst;
-    const uint64_t *hap_prefix;  // [n_inst+1] prefix of ploidy(i)
+    const uint64_t *hap_prefix;    // [n_inst+1] prefix of ploidy(i)
+    const uint64_t *chunk_prefix;  // [n_haps+1] prefix of 32-position chunks per (instance, haplotype)
+    MecChunk *chunks;              // scratch, [chunk_prefix[n_haps]]
     const uint64_t *cnt[2];
     double *mec[2];  // [mec_off + h][2] = (bases, errors)
     double eps;
@@ -767,86 +776,221 @@ __device__ __forceinline__ void fb_cswap(unsigned long long &x, unsigned long lo
     y = hi;
 }
 
-__global__ void __launch_bounds__(256) k_mec(MecArgs a) {
+// one position of a haplotype table: allele_counts (keys present) sorted ascending by count
+// (local_clustering.rs:229-236).  An absent key holds 0 and adding 0.0 changes nothing, so all four words go through a
+// sorting network as items: v0 <= v1 <= v2 are the non-consensus counts, v3 the consensus count.
+struct MecPos {
+    unsigned long long v0, v1, v2, v3;
+    bool anyp, has_eps;
+};
+__device__ __forceinline__ MecPos fb_mec_pos(const ulonglong2 *__restrict__ c2, uint32_t p, uint32_t npos) {
+    MecPos r;
+    ulonglong2 x = make_ulonglong2(0ULL, 0ULL), y = x;
+    if (p < npos) {
+        x = c2[(uint64_t)p * 2];
+        y = c2[(uint64_t)p * 2 + 1];
+    }
+    r.anyp = ((x.x | x.y | y.x | y.y) & FB_PRESENT) != 0;
+    r.v0 = x.x & FB_CNT_MASK;
+    r.v1 = x.y & FB_CNT_MASK;
+    r.v2 = y.x & FB_CNT_MASK;
+    r.v3 = y.y & FB_CNT_MASK;
+    fb_cswap(r.v0, r.v1);
+    fb_cswap(r.v2, r.v3);
+    fb_cswap(r.v0, r.v2);
+    fb_cswap(r.v1, r.v3);
+    fb_cswap(r.v1, r.v2);
+    r.has_eps = r.anyp && r.v3 <= (1ULL << 26);  // cons_bases <= 1.0
+    return r;
+}
+
+__device__ __forceinline__ bool fb_mec_locate(const MecArgs &a, uint64_t hapidx, InstDev &in, uint32_t &h, int &buf) {
+    const int ii = fb_upper_seg(a.hap_prefix, a.n_inst, hapidx);
+    in = a.inst[ii];
+    if (a.only_active && !a.st[ii].active) return false;
+    h = (uint32_t)(hapidx - a.hap_prefix[ii]);
+    const int cur = a.st[ii].cur;
+    buf = a.which == 0 ? cur : (a.which == 1 ? (cur ^ 1) : a.buf);
+    return true;
+}
+
+// level 1: one warp per (instance, haplotype, chunk of 32 positions): exact integer sums + the epsilon mask
+__global__ void __launch_bounds__(256) k_mec_chunks(MecArgs a, uint64_t n_haps) {
+    const uint64_t wid = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wid >= a.chunk_prefix[n_haps]) return;
+    const uint32_t lane = fb_lane();
+    const uint64_t hapidx = (uint64_t)fb_upper_seg(a.chunk_prefix, (int)n_haps, wid);
+    InstDev in;
+    uint32_t h;
+    int buf;
+    if (!fb_mec_locate(a, hapidx, in, h, buf)) return;
+    const ulonglong2 *__restrict__ c2 =
+        reinterpret_cast<const ulonglong2 *>(a.cnt[buf] + in.cnt_off + (uint64_t)h * in.ng * 64);
+    const uint32_t p0 = (uint32_t)(wid - a.chunk_prefix[hapidx]) * 32u;
+    const MecPos m = fb_mec_pos(c2, p0 + lane, in.ng * 16);
+    const unsigned long long sb = fb_warp_sum_u64(m.v3), so = fb_warp_sum_u64(m.v0 + m.v1 + m.v2);
+    const unsigned e = __ballot_sync(0xFFFFFFFFu, m.has_eps);
+    if (lane == 0) {
+        MecChunk c;
+        c.bases = (long long)sb;
+        c.others = (long long)so;
+        c.eps = e;
+        c._pad[0] = c._pad[1] = c._pad[2] = 0;
+        a.chunks[wid] = c;
+    }
+}
+
+// errors of one chunk, position by position: per position up to 3 dyadic items then an optional epsilon.  Runs of lanes
+// between two epsilon items are added as one exact lump (prefix sums) whenever SeqSum proves that identical to
+// item-by-item addition.
+__device__ void fb_mec_chunk_detail(const ulonglong2 *__restrict__ c2, uint32_t npos, uint32_t p0, SeqSum &errors,
+                                    double eps, int eps_safe) {
+    const uint32_t lane = fb_lane();
+    const MecPos m = fb_mec_pos(c2, p0 + lane, npos);
+    const long long others = (long long)(m.v0 + m.v1 + m.v2);
+    long long pre = others;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long t = __shfl_up_sync(0xFFFFFFFFu, pre, o);
+        if ((int)lane >= o) pre += t;
+    }
+    const unsigned E = __ballot_sync(0xFFFFFFFFu, m.has_eps);
+    int cur = 0;
+    while (cur < 32) {
+        const unsigned rest = E >> cur;
+        const int e = rest ? cur + __ffs(rest) - 1 : 31;  // last lane of the run (its epsilon, if any, follows)
+        const long long hi_sum = __shfl_sync(0xFFFFFFFFu, pre, e);
+        const long long lo_sum = cur ? __shfl_sync(0xFFFFFFFFu, pre, cur - 1) : 0;
+        if (!errors.add_dyadic_run(hi_sum - lo_sum)) {
+            for (int l = cur; l <= e; ++l) {
+                const long long o_l = __shfl_sync(0xFFFFFFFFu, others, l);
+                if (errors.add_dyadic_run(o_l)) continue;
+                errors.add_dyadic((long long)__shfl_sync(0xFFFFFFFFu, m.v0, l));
+                errors.add_dyadic((long long)__shfl_sync(0xFFFFFFFFu, m.v1, l));
+                errors.add_dyadic((long long)__shfl_sync(0xFFFFFFFFu, m.v2, l));
+            }
+        }
+        if (!rest) break;
+        errors.add_eps(eps, eps_safe);
+        cur = e + 1;
+    }
+}
+
+// single-level variant for small tables (a few chunks per haplotype: the summaries would not pay): one warp per
+// (instance, haplotype) walks the chunks in order
+__global__ void __launch_bounds__(256) k_mec_flat(MecArgs a) {
     const uint64_t wid = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (wid >= a.hap_prefix[a.n_inst]) return;
-    const uint32_t lane = fb_lane();
-    const int ii = fb_upper_seg(a.hap_prefix, a.n_inst, wid);
-    const InstDev in = a.inst[ii];
-    if (a.only_active && !a.st[ii].active) return;
-    const uint32_t h = (uint32_t)(wid - a.hap_prefix[ii]);
-    const int cur_buf = a.st[ii].cur;
-    const int buf = a.which == 0 ? cur_buf : (a.which == 1 ? (cur_buf ^ 1) : a.buf);
+    InstDev in;
+    uint32_t h;
+    int buf;
+    if (!fb_mec_locate(a, wid, in, h, buf)) return;
     const ulonglong2 *__restrict__ c2 =
         reinterpret_cast<const ulonglong2 *>(a.cnt[buf] + in.cnt_off + (uint64_t)h * in.ng * 64);
     const uint32_t npos = in.ng * 16;
     SeqSum bases, errors;
     bases.init();
     errors.init();
-    ulonglong2 x_n = make_ulonglong2(0ULL, 0ULL), y_n = x_n;
-    if (lane < npos) {
-        x_n = c2[(uint64_t)lane * 2];
-        y_n = c2[(uint64_t)lane * 2 + 1];
-    }
     for (uint32_t p0 = 0; p0 < npos; p0 += 32) {
-        const ulonglong2 x = x_n, y = y_n;
-        {  // next chunk's counts are in flight while this one is folded into the sums
-            const uint32_t pn = p0 + 32 + lane;
-            x_n = make_ulonglong2(0ULL, 0ULL);
-            y_n = x_n;
-            if (pn < npos) {
-                x_n = c2[(uint64_t)pn * 2];
-                y_n = c2[(uint64_t)pn * 2 + 1];
-            }
+        const MecPos m = fb_mec_pos(c2, p0 + fb_lane(), npos);
+        if (!__ballot_sync(0xFFFFFFFFu, m.anyp)) continue;
+        const long long tot = (long long)fb_warp_sum_u64(m.v3);
+        if (!bases.add_dyadic_run(tot))
+            for (int l = 0; l < 32; ++l) bases.add_dyadic((long long)__shfl_sync(0xFFFFFFFFu, m.v3, l));
+        fb_mec_chunk_detail(c2, npos, p0, errors, a.eps, a.eps_safe);
+    }
+    if (fb_lane() == 0) {
+        a.mec[buf][((uint64_t)in.mec_off + h) * 2 + 0] = bases.S;
+        a.mec[buf][((uint64_t)in.mec_off + h) * 2 + 1] = errors.S;
+    }
+}
+
+// level 2: one warp per (instance, haplotype) folds the chunk summaries in position order: a lane holds one chunk, runs
+// of epsilon-free chunks are added as one exact lump, chunks with epsilon items (the thin ends of a table) or runs that
+// SeqSum cannot prove exact are expanded position by position.
+__global__ void __launch_bounds__(256) k_mec(MecArgs a) {
+    const uint64_t wid = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wid >= a.hap_prefix[a.n_inst]) return;
+    const uint32_t lane = fb_lane();
+    InstDev in;
+    uint32_t h;
+    int buf;
+    if (!fb_mec_locate(a, wid, in, h, buf)) return;
+    const ulonglong2 *__restrict__ c2 =
+        reinterpret_cast<const ulonglong2 *>(a.cnt[buf] + in.cnt_off + (uint64_t)h * in.ng * 64);
+    const uint32_t npos = in.ng * 16;
+    const MecChunk *__restrict__ ch = a.chunks + a.chunk_prefix[wid];
+    const uint32_t n_chunks = (uint32_t)(a.chunk_prefix[wid + 1] - a.chunk_prefix[wid]);
+    SeqSum bases, errors;
+    bases.init();
+    errors.init();
+    for (uint32_t c0 = 0; c0 < n_chunks; c0 += 32) {
+        const uint32_t c = c0 + lane;
+        long long sb = 0, so = 0;
+        uint32_t em = 0;
+        if (c < n_chunks) {
+            const MecChunk k = ch[c];
+            sb = k.bases;
+            so = k.others;
+            em = k.eps;
         }
-        // allele_counts (keys present) sorted ascending by count (local_clustering.rs:229-236).  An absent key holds 0
-        // and adding 0.0 changes nothing, so all four words go through a sorting network as items.
-        const bool anyp = ((x.x | x.y | y.x | y.y) & FB_PRESENT) != 0;
-        unsigned long long v0 = x.x & FB_CNT_MASK, v1 = x.y & FB_CNT_MASK, v2 = y.x & FB_CNT_MASK, v3 = y.y & FB_CNT_MASK;
-        fb_cswap(v0, v1);
-        fb_cswap(v2, v3);
-        fb_cswap(v0, v2);
-        fb_cswap(v1, v3);
-        fb_cswap(v1, v2);
-        const long long mx = (long long)v3;                  // cons_bases
-        const long long others = (long long)(v0 + v1 + v2);  // the non-consensus counts, added in ascending order
-        const bool has_eps = anyp && mx <= (1LL << 26);      // cons_bases <= 1.0
-        if (!__ballot_sync(0xFFFFFFFFu, anyp)) continue;
-        // bases: one dyadic item per position
+        // bases: dyadic items only (one per position)
         {
-            const long long tot = (long long)fb_warp_sum_u64((unsigned long long)mx);
+            const long long tot = (long long)fb_warp_sum_u64((unsigned long long)sb);
             if (!bases.add_dyadic_run(tot)) {
-                for (int l = 0; l < 32; ++l) bases.add_dyadic(__shfl_sync(0xFFFFFFFFu, mx, l));
+                for (int l = 0; l < 32; ++l) {
+                    const long long sb_l = __shfl_sync(0xFFFFFFFFu, sb, l);
+                    if (bases.add_dyadic_run(sb_l)) continue;
+                    const MecPos m = fb_mec_pos(c2, (c0 + l) * 32u + lane, npos);
+                    for (int q = 0; q < 32; ++q) bases.add_dyadic((long long)__shfl_sync(0xFFFFFFFFu, m.v3, q));
+                }
             }
         }
-        // errors: per position up to 3 dyadic items then an optional epsilon.  Runs of lanes between two epsilon items
-        // are added as one exact lump (prefix sums) whenever SeqSum proves that identical to item-by-item addition.
+        // errors
         {
-            long long pre = others;
+            long long pre = so;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const long long t = __shfl_up_sync(0xFFFFFFFFu, pre, o);
                 if ((int)lane >= o) pre += t;
             }
-            const unsigned E = __ballot_sync(0xFFFFFFFFu, has_eps);
+            const unsigned X = __ballot_sync(0xFFFFFFFFu, em != 0);  // chunks that hold epsilon items
+            // chunks whose only items are epsilons (a single read covers those positions: no non-consensus counts)
+            // contribute popc(mask) consecutive `+= epsilon`; a run of such chunks is one fb_add_eps_n
+            const unsigned Y = __ballot_sync(0xFFFFFFFFu, em != 0 && so == 0);
+            uint32_t pe = (em != 0 && so == 0) ? (uint32_t)__popc(em) : 0u;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, pe, o);
+                if ((int)lane >= o) pe += t;
+            }
             int cur = 0;
             while (cur < 32) {
-                const unsigned rest = E >> cur;
-                const int e = rest ? cur + __ffs(rest) - 1 : 31;  // last lane of the run (its epsilon, if any, follows)
-                const long long hi_sum = __shfl_sync(0xFFFFFFFFu, pre, e);
-                const long long lo_sum = cur ? __shfl_sync(0xFFFFFFFFu, pre, cur - 1) : 0;
-                if (!errors.add_dyadic_run(hi_sum - lo_sum)) {
-                    for (int l = cur; l <= e; ++l) {
-                        const long long o_l = __shfl_sync(0xFFFFFFFFu, others, l);
-                        if (errors.add_dyadic_run(o_l)) continue;
-                        errors.add_dyadic((long long)__shfl_sync(0xFFFFFFFFu, v0, l));
-                        errors.add_dyadic((long long)__shfl_sync(0xFFFFFFFFu, v1, l));
-                        errors.add_dyadic((long long)__shfl_sync(0xFFFFFFFFu, v2, l));
+                const unsigned rest = X >> cur;
+                const int e = rest ? cur + __ffs(rest) - 1 : 32;  // next chunk to expand
+                if (e > cur) {
+                    const long long hi_sum = __shfl_sync(0xFFFFFFFFu, pre, e - 1);
+                    const long long lo_sum = cur ? __shfl_sync(0xFFFFFFFFu, pre, cur - 1) : 0;
+                    if (!errors.add_dyadic_run(hi_sum - lo_sum)) {
+                        for (int l = cur; l < e; ++l) {
+                            const long long so_l = __shfl_sync(0xFFFFFFFFu, so, l);
+                            if (errors.add_dyadic_run(so_l)) continue;
+                            fb_mec_chunk_detail(c2, npos, (c0 + l) * 32u, errors, a.eps, a.eps_safe);
+                        }
                     }
                 }
-                if (!rest) break;
-                errors.add_eps(a.eps, a.eps_safe);
-                cur = e + 1;
+                if (e == 32) break;
+                if ((Y >> e) & 1u) {
+                    const unsigned inv = ~(Y >> e);
+                    const int r = inv ? __ffs(inv) - 1 : 32 - e;  // consecutive epsilon-only chunks from e on
+                    const uint32_t hi_n = __shfl_sync(0xFFFFFFFFu, pe, e + r - 1);
+                    const uint32_t lo_n = e ? __shfl_sync(0xFFFFFFFFu, pe, e - 1) : 0u;
+                    fb_seqsum_add_eps_n(errors, a.eps, a.eps_safe, (unsigned long long)(hi_n - lo_n));
+                    cur = e + r;
+                } else {
+                    fb_mec_chunk_detail(c2, npos, (c0 + e) * 32u, errors, a.eps, a.eps_safe);
+                    cur = e + 1;
+                }
             }
         }
     }

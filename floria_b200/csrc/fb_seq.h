@@ -181,6 +181,13 @@ FB_HD double fb_add_eps_n(double S, double eps, unsigned long long m) {
     return S;
 }
 
+// m consecutive SeqSum::add_eps in one step (same S and tail as the loop)
+FB_HD void fb_seqsum_add_eps_n(SeqSum &ss, double eps, int eps_safe, unsigned long long m) {
+    if (m == 0) return;
+    ss.S = fb_add_eps_n(ss.S, eps, m);
+    if (!eps_safe || ss.S >= 134217728.0) ss.tail = 1;
+}
+
 // epsilon is "safe" when it is itself a multiple of 2^-26: then every quantity on the path is exact and the sum is
 // order independent (the dyadic-epsilon gate of BASELINE.md §4).
 FB_HD int fb_eps_is_safe(double eps) {
