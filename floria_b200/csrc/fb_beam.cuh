@@ -181,6 +181,8 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
             st_hash[s] = 0;
             st_hi[s] = -1;
             st_mark[s] = 0;
+            plain[s] = 0;
+            addnew[s] = -1;
         }
         __syncthreads();
         if (tid == 0) {
@@ -664,7 +666,17 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
                 hp.score = hp_score;
                 hp.item = hp_item;
                 hp.len = 0;
-                for (int c = 0; c < nc; ++c) {
+                if (!anydup) {
+                    // no two children can be equal: the `exists` scan is vacuous, lane 0 runs the pushes back to back
+                    if (lane == 0)
+                        for (int c = 0; c < nc; ++c) {
+                            hp.push(ch_score[c], c);
+                            if ((uint32_t)hp.len > width) hp.pop();
+                        }
+                    hp.len = __shfl_sync(0xFFFFFFFFu, hp.len, 0);
+                    __syncwarp();
+                }
+                for (int c = 0; anydup && c < nc; ++c) {
                     const double sc = ch_score[c];
                     bool exists = false;
                     if (anydup) {
@@ -688,53 +700,66 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
                 const int len = hp.len;
                 PROF(8)
                 if (bp.prof && tid == 0) { pt[10] += nc; pt[11] += len; }
-                // (g) which states does the next generation need?
-                for (uint32_t s = lane; s < NS; s += 32) {
-                    plain[s] = 0;
-                    addnew[s] = -1;
-                    st_mark[s] = 0;
-                }
-                __syncwarp();
+                // (g) which states does the next generation need?  (plain / addnew / st_mark are cleared at the end of the
+                //     previous step, off the critical path)
                 for (int x = (int)lane; x < len * (int)P; x += 32) {
                     const int e = x / (int)P, i = x % (int)P;
                     const int c = hp_item[e];
                     if (i != (int)ch_part[c]) plain[ND_REF(gen, ch_parent[c], i)] = 1;
                 }
                 __syncwarp();
-                if (lane == 0) {
+                {
+                    // jobs: one per distinct state that receives the read, created by the first survivor that needs it
+                    // (match_any elects it), in survivor order: copies first [0, nj_copy) taking free ids in that order,
+                    // in-place ones stored from the back of the array
                     int nj_copy = 0, nj_inpl = 0;
                     int nfree = ms->n_free;
-                    // jobs: copies first [0, nj_copy), in-place ones stored from the back of the array
-                    for (int e = 0; e < len; ++e) {
-                        const int c = hp_item[e];
-                        const int s = ND_REF(gen, ch_parent[c], ch_part[c]);
-                        if (addnew[s] < 0) {
+                    const unsigned lt = (1u << lane) - 1u;
+                    for (int e0 = 0; e0 < len; e0 += 32) {
+                        const int e = e0 + (int)lane;
+                        int sx = -1;
+                        if (e < len) {
+                            const int c = hp_item[e];
+                            sx = ND_REF(gen, ch_parent[c], ch_part[c]);
+                        }
+                        const bool need = sx >= 0 && addnew[sx] < 0;  // not created by an earlier chunk
+                        __syncwarp();  // every lane has read addnew[] before an elected lane writes it below
+                        const unsigned grp = __match_any_sync(0xFFFFFFFFu, need ? sx : -1 - (int)lane);
+                        const bool leader = need && (int)lane == __ffs(grp) - 1;
+                        const bool cp = leader && plain[sx] != 0;
+                        const unsigned bc = __ballot_sync(0xFFFFFFFFu, cp), bi = __ballot_sync(0xFFFFFFFFu, leader && !cp);
+                        if (leader) {
                             BeamJob jb;
-                            jb.src = (uint32_t)s;
-                            jb.src_hi = st_hi[s];
+                            jb.src = (uint32_t)sx;
+                            jb.src_hi = st_hi[sx];
                             jb._pad = 0;
-                            if (!plain[s]) {
-                                addnew[s] = s;
-                                jb.dst = (uint32_t)s;
-                                jobs[(int)Wm + 1 - nj_inpl] = jb;
-                                nj_inpl++;
-                            } else {
-                                const int d = st_free[--nfree];
-                                addnew[s] = d;
+                            if (cp) {
+                                const int d = st_free[nfree - 1 - __popc(bc & lt)];
+                                addnew[sx] = d;
                                 jb.dst = (uint32_t)d;
-                                jobs[nj_copy++] = jb;
+                                jobs[nj_copy + __popc(bc & lt)] = jb;
+                            } else {
+                                addnew[sx] = sx;
+                                jb.dst = (uint32_t)sx;
+                                jobs[(int)Wm + 1 - (nj_inpl + __popc(bi & lt))] = jb;
                             }
                         }
+                        nj_copy += __popc(bc);
+                        nj_inpl += __popc(bi);
+                        nfree -= __popc(bc);
+                        __syncwarp();
                     }
-                    ms->n_free = nfree;
-                    ms->n_jobs_copy = nj_copy;
-                    ms->n_jobs_inplace = nj_inpl;
-                    ms->n_nodes[gen ^ 1] = len;
-                    if (bp.prof) {
-                        pt[13] += nj_copy;
-                        pt[14] += nj_inpl;
-                        pt[15] += n_live;
-                        pt[9] += n_nodes;
+                    if (lane == 0) {
+                        ms->n_free = nfree;
+                        ms->n_jobs_copy = nj_copy;
+                        ms->n_jobs_inplace = nj_inpl;
+                        ms->n_nodes[gen ^ 1] = len;
+                        if (bp.prof) {
+                            pt[13] += nj_copy;
+                            pt[14] += nj_inpl;
+                            pt[15] += n_live;
+                            pt[9] += n_nodes;
+                        }
                     }
                 }
                 __syncwarp();
@@ -762,6 +787,10 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
                     }
                 }
                 __syncwarp();
+                for (uint32_t sx = lane; sx < NS; sx += 32) {  // ready for the next step
+                    plain[sx] = 0;
+                    addnew[sx] = -1;
+                }
                 // per-state bookkeeping of the new states (each dst is written once; a copy's dst is never a src)
                 {
                     const int nj_copy = ms->n_jobs_copy, njt = nj_copy + ms->n_jobs_inplace;
@@ -796,6 +825,8 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
                         ms->n_live = nl;
                         ms->n_free = nf;
                     }
+                    __syncwarp();
+                    for (uint32_t sx = lane; sx < NS; sx += 32) st_mark[sx] = 0;  // ready for the next step
                 }
             }
             PROF(1)
