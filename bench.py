@@ -220,7 +220,7 @@ def run_ours(args):
         from floria_b200 import shard
 
         unit_ids = np.arange(res.n_blocks, dtype=np.int64) + rank * 1000000
-        return shard.gather_records(unit_ids, res.read_ptr, res.read_ids, res.hap, res.best_ploidy, dev, dst=0)
+        return shard.gather_records(unit_ids, res.read_ptr, res.read_ids, res.hap, res.best_ploidy, dev, dst=0, lazy=True)
 
     def one_pass(fn, steps, timed):
         ev = []

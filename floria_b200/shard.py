@@ -73,10 +73,46 @@ def concat_contigs(contigs, blocks, gap=64):
             np.array(pos_off, np.int64))
 
 
-def gather_records(unit_ids, read_ptr, read_ids, hap, best_ploidy, device, dst=0):
+class GatheredRecords:
+    """The partition records of every rank as received on the destination rank: one byte buffer per rank, parsed on
+    demand (`to_dict`).  Layout of a buffer: int64 n_units, unit_ids[n], best_ploidy[n], read_ptr[n+1], then uint32
+    read_ids[total] and uint8 hap[total]."""
+
+    def __init__(self, bufs):
+        self.bufs = [np.ascontiguousarray(b) for b in bufs]
+
+    @property
+    def nbytes(self):
+        return int(sum(len(b) for b in self.bufs))
+
+    def per_rank(self):
+        """[(unit_ids, best_ploidy, read_ptr, read_ids, hap)] as array views, one tuple per rank"""
+        out = []
+        for b in self.bufs:
+            nu = int(b[:8].view(np.int64)[0])
+            off = 8
+            uids = b[off:off + 8 * nu].view(np.int64); off += 8 * nu
+            bp = b[off:off + 8 * nu].view(np.int64); off += 8 * nu
+            rp = b[off:off + 8 * (nu + 1)].view(np.int64); off += 8 * (nu + 1)
+            tot = int(rp[-1]) if nu else 0
+            rid = b[off:off + 4 * tot].view(np.uint32); off += 4 * tot
+            out.append((uids, bp, rp, rid, b[off:off + tot]))
+        return out
+
+    def to_dict(self):
+        """unit_id -> (best_ploidy, read_ids, hap)"""
+        res = {}
+        for uids, bp, rp, rid, hp in self.per_rank():
+            for k in range(len(uids)):
+                res[int(uids[k])] = (int(bp[k]), rid[rp[k]:rp[k + 1]].copy(), hp[rp[k]:rp[k + 1]].copy())
+        return res
+
+
+def gather_records(unit_ids, read_ptr, read_ids, hap, best_ploidy, device, dst=0, lazy=False):
     """Variable-length gather of per-unit partition records to rank `dst`.
     Every rank passes the records of the units it owns; returns on dst a dict unit_id -> (best_ploidy, read_ids, hap)
-    (None elsewhere).  One all_gather of sizes + one padded gather of the payload."""
+    (a GatheredRecords with lazy=True: the received buffers, parsed on demand), None elsewhere.
+    One all_gather of sizes + one padded gather of the payload into a single [world, max] tensor + one copy to the host."""
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     unit_ids = np.asarray(unit_ids, dtype=np.int64)
@@ -88,28 +124,17 @@ def gather_records(unit_ids, read_ptr, read_ids, hap, best_ploidy, device, dst=0
         bufs = [payload]
     else:
         n = torch.tensor([len(payload)], dtype=torch.int64, device=device)
-        sizes = [torch.zeros_like(n) for _ in range(world)]
-        dist.all_gather(sizes, n)
-        sizes = [int(s.item()) for s in sizes]
+        sizes = torch.zeros(world, dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(sizes, n)
+        sizes = sizes.cpu().tolist()
         mx = max(sizes)
-        rec = torch.zeros(mx, dtype=torch.uint8, device=device)
-        rec[: len(payload)] = torch.from_numpy(payload).to(device)
-        out = [torch.zeros_like(rec) for _ in range(world)] if rank == dst else None
-        dist.gather(rec, out, dst=dst)
+        rec = torch.empty(mx, dtype=torch.uint8, device=device)
+        rec[: len(payload)] = torch.from_numpy(payload).to(device, non_blocking=True)
+        out = torch.empty((world, mx), dtype=torch.uint8, device=device) if rank == dst else None
+        dist.gather(rec, list(out.unbind(0)) if rank == dst else None, dst=dst)
         if rank != dst:
             return None
-        bufs = [o[:s].cpu().numpy() for o, s in zip(out, sizes)]
-    res = {}
-    for b in bufs:
-        b = np.ascontiguousarray(b)
-        nu = int(b[:8].view(np.int64)[0])
-        off = 8
-        uids = b[off:off + 8 * nu].view(np.int64); off += 8 * nu
-        bp = b[off:off + 8 * nu].view(np.int64); off += 8 * nu
-        rp = b[off:off + 8 * (nu + 1)].view(np.int64); off += 8 * (nu + 1)
-        tot = int(rp[-1]) if nu else 0
-        rid = b[off:off + 4 * tot].view(np.uint32); off += 4 * tot
-        hp = b[off:off + tot]
-        for k in range(nu):
-            res[int(uids[k])] = (int(bp[k]), rid[rp[k]:rp[k + 1]].copy(), hp[rp[k]:rp[k + 1]].copy())
-    return res
+        host = out.cpu().numpy()
+        bufs = [host[r, :sizes[r]] for r in range(world)]
+    g = GatheredRecords(bufs)
+    return g if lazy else g.to_dict()
