@@ -8,13 +8,14 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libfloria_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-Wall", "--fmad=false", "-Xptxas", "-v",
 ]
 
 
 def sources():
-    return [os.path.join(CSRC, "fb_lib.cu")]
+    """the translation units: compiled to objects in parallel, then linked into one shared library"""
+    return [os.path.join(CSRC, "fb_lib.cu"), os.path.join(CSRC, "fb_beam_tu.cu")]
 
 
 def stale():
@@ -28,14 +29,27 @@ def stale():
 def build(force=False, verbose=False):
     if not force and not stale():
         return OUT
-    cmd = [NVCC] + FLAGS + ["-o", OUT] + sources()
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-    if res.returncode != 0:
+    objs, procs = [], []
+    for src in sources():
+        obj = os.path.join(HERE, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        procs.append(subprocess.Popen([NVCC] + FLAGS + ["-c", "-o", obj, src], stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True))
+    log, failed = "", False
+    for p in procs:
+        out, err = p.communicate()
+        log += out + err
+        failed |= p.returncode != 0
+    if not failed:
+        res = subprocess.run([NVCC, "-shared", "-o", OUT] + objs, capture_output=True, text=True)
+        log += res.stdout + res.stderr
+        failed = res.returncode != 0
+    if verbose or failed:
+        sys.stderr.write(log)
+    if failed:
         raise RuntimeError("nvcc failed")
     with open(os.path.join(HERE, "build_ptxas.log"), "w") as fh:
-        fh.write(res.stdout + res.stderr)
+        fh.write(log)
     return OUT
 
 

@@ -22,7 +22,7 @@
 #include <vector>
 
 #include "fb_common.cuh"
-#include "fb_kernels.cuh"
+#include "fb_replay.cuh"
 
 // CTA sizes the kernel is instantiated for: 256 threads (one CTA per SM: lowest latency per read step, used when there are
 // fewer instances than SMs can hold) and 128 threads (two CTAs per SM: the dependent chains of two instances interleave,
@@ -106,6 +106,11 @@ struct BeamSmem {
         total = o;
     }
 };
+
+// host entry points of the beam translation unit (fb_beam_tu.cu): the kernel is compiled on its own, in parallel with
+// the rest of the library
+int fb_beam_occupancy(int threads, size_t smem_bytes, int *blocks_per_sm);
+int fb_beam_launch(int threads, unsigned grid, size_t smem_bytes, cudaStream_t stream, const struct BeamParams &bp);
 
 struct BeamJob {
     uint32_t src, dst;

@@ -49,10 +49,8 @@ static int fb_run_beam(fb_ctx *ctx, Engine &e, const fb_params *prm, const BeamT
     const bool small_cta = maxW <= FB_BEAM_THREADS_SMALL && forced != FB_BEAM_THREADS &&
                            (forced == FB_BEAM_THREADS_SMALL || order.size() >= (size_t)ctx->sm_count * 2);
     const int nt = small_cta ? FB_BEAM_THREADS_SMALL : FB_BEAM_THREADS;
-    auto kern = small_cta ? k_beam<FB_BEAM_THREADS_SMALL> : k_beam<FB_BEAM_THREADS>;
-    FB_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     int occ = 1;
-    FB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nt, L.total));
+    FB_CK((cudaError_t)fb_beam_occupancy(nt, L.total, &occ));
     if (occ < 1) occ = 1;
     const uint64_t pool_bytes = (max_pool + 255) & ~255ULL;
     const uint64_t hist_bytes = (((uint64_t)maxR * maxW * 4) + 255) & ~255ULL;
@@ -124,11 +122,11 @@ static int fb_run_beam(fb_ctx *ctx, Engine &e, const fb_params *prm, const BeamT
         bp.prof = d_prof;
     }
     cudaEvent_t e0 = fb_event(ctx);
-    kern<<<(unsigned)n_slots, nt, L.total, ctx->stream>>>(bp);
+    cudaError_t launch_err = (cudaError_t)fb_beam_launch(nt, (unsigned)n_slots, L.total, ctx->stream, bp);
     cudaEvent_t e1 = fb_event(ctx);
     ctx->tim.n_launches++;
     ctx->tim.n_beam_launches++;
-    cudaError_t ce = cudaGetLastError();
+    cudaError_t ce = launch_err;
     if (ce == cudaSuccess) {
         cudaMemcpyAsync(br.cells_beam.data(), d_cells, sizeof(unsigned long long) * n_inst, cudaMemcpyDeviceToHost, ctx->stream);
         cudaMemcpyAsync(br.tap_n.data(), d_tapn, sizeof(unsigned long long) * n_inst, cudaMemcpyDeviceToHost, ctx->stream);
