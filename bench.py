@@ -18,7 +18,6 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import time
 
@@ -42,65 +41,48 @@ def hbm_peak():
 
 
 class ClockSampler:
-    """SM clock / throttle-reason sampler.  Runs NVML in a CHILD PROCESS (started before the timed region, polled every
-    20 ms): an in-process sampler thread was measured to cost ~1 ms per 16 ms step (GIL hand-offs against the thread
-    that launches kernels), and nvidia-smi itself stalls for a second at start-up."""
+    """SM clock / throttle-reason samples of this rank's GPU (NVML, in process), taken BETWEEN the steps of the timed
+    loop: right after a step's synchronize, while the GPU is still at its load clocks, and outside every step's CUDA-event
+    window.  Two concurrent samplers were tried first (a polling thread, then a polling child process): on some hosts
+    their NVML queries stalled the CUDA calls of the measured process for tens of milliseconds (one run: 33.7 ms per step
+    with the sampler against 18.5 ms without, identical kernel times), so nothing polls while a step runs."""
 
-    CHILD = r"""
-import sys, time, pynvml as nv
-nv.nvmlInit()
-h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
-print("max", nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM), flush=True)
-sys.stdin.readline()                      # "go"
-import select
-while True:
-    if select.select([sys.stdin], [], [], float(sys.argv[2]))[0]:
-        break                             # "stop"
-    print(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), int(nv.nvmlDeviceGetCurrentClocksEventReasons(h)), flush=True)
-"""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
                0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, index, period=0.02):
-        self.ok = False
-        self.max_mhz = None
+    def __init__(self, index):
+        self.sm, self.reasons, self.max_mhz, self.ok = [], set(), None, False
         try:
-            # CUDA_VISIBLE_DEVICES remaps CUDA ordinals, not NVML indices
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            import pynvml
+
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")  # remaps CUDA ordinals, not NVML indices
             if vis:
                 index = int(vis.split(",")[index])
-            self.p = subprocess.Popen([sys.executable, "-c", self.CHILD, str(index), str(period)], stdin=subprocess.PIPE,
-                                      stdout=subprocess.PIPE, text=True)
-            line = self.p.stdout.readline().split()
-            if line and line[0] == "max":
-                self.max_mhz = float(line[1])
-                self.ok = True
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
         except Exception as e:  # pragma: no cover
             self.err = str(e)
 
-    def start(self):
-        if self.ok:
-            self.p.stdin.write("go\n")
-            self.p.stdin.flush()
+    def sample(self):
+        if not self.ok:
+            return
+        try:
+            self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+            r = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            for bit, name in self.REASONS.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:  # pragma: no cover
+            pass
 
-    def stop(self):
+    def result(self):
         if not self.ok:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
-        try:
-            out, _ = self.p.communicate("stop\n", timeout=5)
-        except Exception:  # pragma: no cover
-            self.p.kill()
-            out = ""
-        sm, reasons = [], set()
-        for ln in out.splitlines():
-            f = ln.split()
-            if len(f) == 2:
-                sm.append(float(f[0]))
-                for bit, name in self.REASONS.items():
-                    if int(f[1]) & bit:
-                        reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "samples": len(sm),
-                "reasons": sorted(reasons)}
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "samples": len(self.sm), "sampled": "between timed steps", "reasons": sorted(self.reasons)}
 
 
 def make_workload(rank):
@@ -222,7 +204,7 @@ def run_ours(args):
         unit_ids = np.arange(res.n_blocks, dtype=np.int64) + rank * 1000000
         return shard.gather_records(unit_ids, res.read_ptr, res.read_ids, res.hap, res.best_ploidy, dev, dst=0, lazy=True)
 
-    def one_pass(fn, steps, timed):
+    def one_pass(fn, steps, sampler=None):
         ev = []
         cells = 0
         for _ in range(steps):
@@ -239,6 +221,8 @@ def run_ours(args):
                 sys.stderr.write(f"[step] compute {1e3 * (t1 - t0):.2f} ms, gather {1e3 * (t2 - t1):.2f} ms\n")
             e1.record()
             torch.cuda.synchronize()
+            if sampler:
+                sampler.sample()
             ev.append(e0.elapsed_time(e1))
             cells = res.cells
         return ev, cells, res
@@ -246,28 +230,24 @@ def run_ours(args):
     resident = lambda: ctx.phase_blocks_resident(dfr, lo, hi, prm)
     e2e_fn = lambda: ctx.phase_blocks(hfr, lo, hi, prm)
 
-    one_pass(resident, args.warmup, False)
-    one_pass(e2e_fn, min(args.warmup, 3), False)
+    one_pass(resident, args.warmup)
+    one_pass(e2e_fn, min(args.warmup, 3))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # rank 0 samples its GPU's clocks during the timed region (NVML in every rank at once was measured to slow the
-    # host side of all ranks: the queries serialise in the driver)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
-    if sampler:
-        sampler.start()
     t_before = ctx.timings()
-    ev, cells, res = one_pass(resident, args.steps, True)
+    ev, cells, res = one_pass(resident, args.steps, sampler)
     t_after = ctx.timings()
     barrier()
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.result() if sampler else None
     my_ms = sum(ev)
     barrier()
-    ev2, cells2, res2 = one_pass(e2e_fn, args.steps, True)
+    ev2, cells2, res2 = one_pass(e2e_fn, args.steps, sampler)
     barrier()
     my_ms2 = sum(ev2)
 
