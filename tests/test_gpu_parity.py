@@ -227,6 +227,25 @@ def test_beam_cta_sizes_match_oracle(ctx, monkeypatch, cta):
     assert np.array_equal(bits(g.mec_vector), bits(o.mec_vector)) and g.cells == o.cells
 
 
+@pytest.mark.parametrize("cta", [128, 256])
+def test_beam_search_reads_longer_than_the_staging_buffer(ctx, monkeypatch, cta):
+    """k_beam stages a read's planes in shared memory when it spans at most FB_BEAM_RG = 128 groups (2048 SNPs) and
+    reads longer ones from global memory: a contig whose reads span ~2300 of 2600 SNPs takes the second path on almost
+    every step (and mixes both), for both CTA sizes."""
+    monkeypatch.setenv("FB_BEAM_CTA", str(cta))
+    c = synth.make_contig(61, 110, 2600, 2, span_mean=2300)
+    fr = c.frags
+    span = (fr.last.astype(np.int64) - fr.first.astype(np.int64))
+    assert (span > 2100).sum() >= 20 and (span <= 2000).sum() >= 5
+    sel = np.arange(fr.n_reads, dtype=np.uint32)
+    for eps in EPS:
+        prm = default_params(epsilon=eps)
+        oh, osc, _ = oracle.beam_search_phasing(fr, sel, 2, prm)
+        gh, gsc, _ = ctx.beam_search_phasing(fr, sel, 2, prm)
+        assert np.array_equal(gh, oh), f"{int((gh != oh).sum())} assignments differ"
+        assert_f64_identical([gsc], [osc], "beam score")
+
+
 def test_beam_search_small_beam_and_single_read(ctx):
     fr = CASES["edge"]()
     for B in (1, 3):
