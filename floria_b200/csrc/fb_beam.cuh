@@ -16,6 +16,17 @@
 //     they are removed from the hashes and excluded from the equality test.
 // Heap order, `<=` tie behaviour, the width rule (ploidy*B for the first 25 reads), pruning by p - lse > ln(0.01) and
 // the final into_sorted_vec()[0] + parent walk follow the reference line by line (see fb_seq.h for the heap).
+//
+// Anatomy of a step (one read), three CTA-wide synchronisation points:
+//   phase 1  all warps   one warp per live state scores the read (planes from the state, the read's cells from the
+//                        shared-memory staging buffer) and forms its p-value; other warps advance the states' window hashes
+//   phase 2  warp 0      pruning (no exp/log outside the decision band), child scores, compaction, hash fold, duplicate
+//                        classes (exact verification only on a fold match), BinaryHeap pushes/pops, job list
+//            warps 1..   stage the NEXT read's planes in shared memory and sum its delta(read), then wait on named barrier 1
+//   phase 3  warps 1..   materialise the surviving generation's new states, one thread per position, is-max planes by
+//                        ballot -- overlapped with warp 0 writing the next generation's node tables, history, hashes,
+//                        live / free lists (warp 0 only ARRIVES on barrier 1 after publishing the job list)
+// FB_BEAM_PROF=1 accumulates per-phase cycle counts (printed by fb_run_beam); profiles/README.md has the numbers.
 #pragma once
 #include <limits.h>
 
