@@ -41,7 +41,8 @@ def build(force=False, verbose=False):
         log += out + err
         failed |= p.returncode != 0
     if not failed:
-        res = subprocess.run([NVCC, "-shared", "-o", OUT] + objs, capture_output=True, text=True)
+        res = subprocess.run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-pthread", "-o", OUT] + objs,
+                             capture_output=True, text=True)
         log += res.stdout + res.stderr
         failed = res.returncode != 0
     if verbose or failed:
