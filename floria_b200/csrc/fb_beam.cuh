@@ -36,7 +36,8 @@
 #include "fb_replay.cuh"
 
 // CTA sizes the kernel is instantiated for: 256 threads (one CTA per SM: lowest latency per read step, used when there are
-// fewer instances than SMs can hold) and 128 threads (two CTAs per SM: the dependent chains of two instances interleave,
+// fewer instances than SMs can hold) and 128 threads (three CTAs per SM at 168 registers: the dependent chains of
+// several instances interleave; measured 172 vs 186 ms with two CTAs on the configs[4]-shaped batch, 45 vs 56 ms on short reads,
 // used for many-instance work queues such as a batched metagenome)
 #define FB_BEAM_THREADS 256
 #define FB_BEAM_THREADS_SMALL 128
@@ -894,7 +895,7 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT, FB_BEAM_THREADS / NT) k_beam(BeamParams bp) {
+__global__ void __launch_bounds__(NT, NT == FB_BEAM_THREADS ? 1 : 3) k_beam(BeamParams bp) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ int s_work;
     const int tid = threadIdx.x;
