@@ -78,6 +78,18 @@ def test_gather_records_single_process():
     assert res[4][0] == 2 and list(res[4][1]) == [10, 11] and list(res[2][2]) == [0]
 
 
+def test_gather_records_lazy_view():
+    """lazy=True hands back the received buffers (what bench.py times); per_rank() exposes them as array views and
+    to_dict() parses them into the same mapping as the eager call"""
+    g = shard.gather_records([4, 2], [0, 2, 3], [10, 11, 20], [0, 1, 0], [2, 1], torch.device("cpu"), lazy=True)
+    assert isinstance(g, shard.GatheredRecords) and g.nbytes == 8 * (1 + 2 + 2 + 3) + 4 * 3 + 3
+    (uids, bp, rp, rid, hp), = g.per_rank()
+    assert uids.tolist() == [4, 2] and bp.tolist() == [2, 1] and rp.tolist() == [0, 2, 3]
+    assert rid.tolist() == [10, 11, 20] and hp.tolist() == [0, 1, 0]
+    d = g.to_dict()
+    assert d[4][0] == 2 and list(d[4][1]) == [10, 11] and list(d[2][2]) == [0]
+
+
 def _metagenome(n_contigs, n_reads, n_snps):
     from floria_b200 import api, synth
 
