@@ -69,6 +69,18 @@ class FbParts(C.Structure):
     ]
 
 
+class FbBlockPhase(C.Structure):
+    _fields_ = [
+        ("beam_score", C.c_double),
+        ("opt_score", C.c_double),
+        ("n_rounds", C.c_uint32),
+        ("ploidy", C.c_uint32),
+        ("cells_sweep", C.c_uint64),
+        ("cells_hist", C.c_uint64),
+        ("cells_beam", C.c_uint64),
+    ]
+
+
 class FbTimings(C.Structure):
     _fields_ = [
         ("upload_ms", C.c_float),

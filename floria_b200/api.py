@@ -11,6 +11,7 @@ import numpy as np
 
 from ._cdefs import (
     BlockResults,
+    FbBlockPhase,
     FbBlockResults,
     FbFrags,
     FbParams,
@@ -33,6 +34,7 @@ EXPORTS = [
     "fb_init", "fb_destroy", "fb_last_error", "fb_params_default", "fb_last_timings", "fb_stream",
     "fb_frags_upload", "fb_frags_free", "fb_dfrags_bytes", "fb_get_range_with_lengths",
     "fb_find_reads_in_interval", "fb_phase_blocks", "fb_phase_blocks_resident", "fb_free_block_results",
+    "fb_phase_block", "fb_phase_block_resident",
     "fb_score_reads", "fb_hap_block_from_partition", "fb_get_mec_stats_epsilon", "fb_beam_search_phasing",
     "fb_optimize_clustering", "fb_process_reads_for_final_parts", "fb_free_parts", "fb_get_hapq",
     "fb_update_hap_graph",
@@ -77,6 +79,10 @@ def load_library():
     L.fb_phase_blocks_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, u32p, u32p, C.POINTER(FbParams),
                                            C.POINTER(C.POINTER(FbBlockResults))]
     L.fb_free_block_results.argtypes = [C.POINTER(FbBlockResults)]
+    L.fb_phase_block.argtypes = [C.c_void_p, C.POINTER(FbFrags), C.c_uint64, u32p, C.c_uint32, C.POINTER(FbParams), u8p,
+                                 f64p, f64p, C.POINTER(FbBlockPhase)]
+    L.fb_phase_block_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, u32p, C.c_uint32, C.POINTER(FbParams),
+                                          u8p, f64p, f64p, C.POINTER(FbBlockPhase)]
     L.fb_score_reads.argtypes = [C.c_void_p, C.POINTER(FbFrags), C.c_uint64, u32p, u8p, C.c_uint32,
                                  C.POINTER(FbParams), f64p, f64p, i64p, i64p, u32p]
     L.fb_hap_block_from_partition.argtypes = [C.c_void_p, C.POINTER(FbFrags), C.c_uint64, u32p, u8p, C.c_uint32,
@@ -134,6 +140,7 @@ class DeviceFrags:
         self.ctx = ctx
         self.handle = handle
         self.frags = frags
+        self.n_reads = frags.n_reads if frags is not None else None
 
     @property
     def nbytes(self):
@@ -210,6 +217,7 @@ class Context:
                                               ptr(nall8, u8p), ptr(src, u8p), C.byref(out)))
         d = DeviceFrags(self, out, None)
         d.src = src
+        d.n_reads = n_reads
         return d
 
     def bench_sweep_hist(self, dfrags, ploidy, hap, params, iters):
@@ -273,6 +281,29 @@ class Context:
         return res
 
     # ---- fine-grained entry points ----
+    def phase_block(self, frags, sel, ploidy, params):
+        """graph_processing.rs:140-162 for one block at a fixed ploidy: beam_search_phasing -> optimize_clustering ->
+        get_mec_stats_epsilon_no_phred.  `frags` = host Frags (uploaded and packed by the call) or DeviceFrags;
+        sel=None takes every read.  Returns (hap, mec_bases, mec_errors, info dict)."""
+        resident = isinstance(frags, DeviceFrags)
+        if sel is None:
+            n, selp = int(frags.n_reads), None
+        else:
+            sel = np.ascontiguousarray(sel, dtype=np.uint32)
+            n, selp = len(sel), ptr(sel, u32p)
+        hap = np.zeros(max(n, 1), np.uint8)
+        bases = np.zeros(ploidy)
+        errors = np.zeros(ploidy)
+        info = FbBlockPhase()
+        if resident:
+            self._chk(self.L.fb_phase_block_resident(self.h, frags.handle, n, selp, ploidy, C.byref(params),
+                                                     ptr(hap, u8p), ptr(bases, f64p), ptr(errors, f64p), C.byref(info)))
+        else:
+            fs = frags.as_struct()
+            self._chk(self.L.fb_phase_block(self.h, C.byref(fs), n, selp, ploidy, C.byref(params), ptr(hap, u8p),
+                                            ptr(bases, f64p), ptr(errors, f64p), C.byref(info)))
+        return hap[:n], bases, errors, {k: getattr(info, k) for k, _ in FbBlockPhase._fields_}
+
     def score_reads(self, frags, sel, hap, ploidy, params):
         sel = np.ascontiguousarray(sel, dtype=np.uint32)
         hap = np.ascontiguousarray(hap, dtype=np.uint8)

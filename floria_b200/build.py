@@ -15,7 +15,7 @@ FLAGS = [
 
 def sources():
     """the translation units: compiled to objects in parallel, then linked into one shared library"""
-    return [os.path.join(CSRC, "fb_lib.cu"), os.path.join(CSRC, "fb_beam_tu.cu")]
+    return [os.path.join(CSRC, f) for f in ("fb_lib.cu", "fb_beam_tu.cu", "fb_beam_wide_tu.cu")]
 
 
 def stale():

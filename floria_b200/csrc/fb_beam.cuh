@@ -71,6 +71,10 @@ struct BeamParams {
     unsigned long long *tapn_out;   // [n_inst]
     BeamTapDev tap;                 // only meaningful for single-instance calls
     unsigned long long *prof;       // optional [8] cycle counters per phase (FB_BEAM_PROF=1), else NULL
+    // k_beam_wide only (fb_beam_wide.cuh): global workspace of the grid-wide reductions and the grid barrier
+    struct BeamWideAcc *wacc;        // [3][maxNS] per-state partial sums of a step (three step slots)
+    struct BeamWideStep *wstep;      // [3] per-read sums of a step
+    unsigned long long *wbar;        // monotonic arrival counter of the grid barrier
 };
 
 // shared-memory carve-up (same arithmetic on host and device)
@@ -78,7 +82,7 @@ struct BeamSmem {
     uint32_t off_nd_score, off_nd_err, off_nd_ref, off_st_hash, off_sc_same, off_sc_diff, off_st_hi, off_st_mark,
         off_free, off_live, off_ch_score, off_ch_parent, off_ch_part, off_ch_class, off_ch_diff, off_hp_score,
         off_hp_item, off_lut, off_wscr, off_misc, off_job, off_addnew, off_plain, off_sc_pv, off_ch_fold, off_ch_m, off_rq,
-        off_ral, off_rpr, total;
+        off_ral, off_rpr, off_replay, total;
     __host__ __device__ void layout(uint32_t P, uint32_t W, uint32_t NS) {
         uint32_t o = 0;
         auto take = [&](uint32_t bytes) {
@@ -115,6 +119,7 @@ struct BeamSmem {
         off_rq = take(2 * FB_BEAM_RG * 16);   // staged planes of the current / next read (double buffered)
         off_ral = take(2 * FB_BEAM_RG * 4);
         off_rpr = take(2 * FB_BEAM_RG * 2);
+        off_replay = take(NS * 4);  // k_beam_wide: states whose epsilon sum needs the ordered replay
         total = o;
     }
 };
@@ -493,358 +498,15 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
                     }
                 }
             } else {
-                // (a) per node: log-sum-exp, pruning (global_clustering.rs:93-98), child score (:181-208).
-                //     Register arrays with static indexing (guards on j < P) keep the loads independent.
-                for (int n0 = 0; n0 < n_nodes; n0 += 32) {
-                    const int n = n0 + (int)lane;
-                    if (n < n_nodes) {
-                        double pv[P], er[P], df[P];
-#pragma unroll
-                        for (int j = 0; j < P; ++j) {
-                            {
-                                const int s = ND_REF(gen, n, j);
-                                pv[j] = sc_pv[s];
-                                df[j] = sc_diff[s];
-                                er[j] = ND_ERR(gen, n, j);
-                                if (bp.tap.cap) {
-                                    const unsigned long long o = tapn + (unsigned long long)n * P + j;
-                                    if (o < bp.tap.cap) {
-                                        if (bp.tap.same) bp.tap.same[o] = sc_same[s];
-                                        if (bp.tap.diff) bp.tap.diff[o] = df[j];
-                                        if (bp.tap.logp) bp.tap.logp[o] = pv[j];
-                                    }
-                                }
-                            }
-                        }
-                        // utils_frags.rs:250-258 log_sum_exp and the pruning test p[j] - lse > cutoff
-                        // (global_clustering.rs:93-98).  lse = mx + ln(S) with 1 <= S <= P, so p[j] - lse lies in
-                        // [d - ln P, d] for d = p[j] - mx: outside the band cutoff < d <= cutoff + ln P the decision
-                        // needs no exp/log at all (margins of 1e-6 dwarf every rounding error of the full formula, whose
-                        // terms are below 2^40); inside the band the reference formula is evaluated as written.
-                        double mx = pv[0];
-#pragma unroll
-                        for (int j = 1; j < P; ++j) mx = pv[j] > mx ? pv[j] : mx;
-                        const double band_hi = bp.cutoff + ln_p + 1e-6, band_lo = bp.cutoff - 1e-6;
-                        bool need_lse = false;
-#pragma unroll
-                        for (int j = 0; j < P; ++j) {
-                            const double d = pv[j] - mx;
-                            need_lse |= (d > band_lo) && (d <= band_hi);
-                        }
-                        double lse = 0.0;
-                        if (need_lse || !(fabs(mx) < 1e12)) {
-                            double sum = 0.0;
-#pragma unroll
-                            for (int j = 0; j < P; ++j) sum += exp(pv[j] - mx);
-                            lse = mx + log(sum);
-                            need_lse = true;
-                        }
-#pragma unroll
-                        for (int j = 0; j < P; ++j) {
-                            {
-                                double sc = -1.0;  // < 0 marks "pruned" (scores are sums of non-negative terms)
-                                const bool keep = need_lse ? (pv[j] - lse > bp.cutoff) : (pv[j] - mx > band_hi);
-                                if (keep) {
-                                    double mec = 0.0;  // new_error_vec.iter().map(|x| x.1).sum()
-#pragma unroll
-                                    for (int h = 0; h < P; ++h) {
-                                        {
-                                            double e = er[h];
-                                            if (h == j) e = e + df[j];
-                                            mec += e;
-                                        }
-                                    }
-                                    sc = -(-1.0 * mec);  // new_node_score = -score, score = -1.0 * mec
-                                }
-                                ch_score[n * P + j] = sc;  // staging, compacted below
-                            }
-                        }
-                    }
-                }
-                __syncwarp();
-                PROF(6)
-                // (b) compaction in evaluation order (node in heap order, j ascending); the compacted index never exceeds
-                //     the staging index, and every lane reads its staged value before anything of its chunk is written
-                int nc = 0;
-                for (int x0 = 0; x0 < n_nodes * (int)P; x0 += 32) {
-                    const int x = x0 + (int)lane;
-                    double sc = x < n_nodes * (int)P ? ch_score[x] : -1.0;
-                    const bool keep = sc >= 0.0;
-                    const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
-                    __syncwarp();
-                    if (keep) {
-                        const int o = nc + __popc(bal & ((1u << lane) - 1u));
-                        ch_score[o] = sc;
-                        ch_parent[o] = (uint16_t)(x / (int)P);
-                        ch_part[o] = (uint16_t)(x % (int)P);
-                    }
-                    nc += __popc(bal);
-                    __syncwarp();
-                }
-                const unsigned long long delta = ms->delta[par];
-                // (c) one 64-bit fold of each child's tuple of (virtual) state hashes
-                for (int c0 = 0; c0 < nc; c0 += 32) {
-                    const int c = c0 + (int)lane;
-                    if (c < nc) {
-                        const int n1 = ch_parent[c], j1 = ch_part[c];
-                        unsigned long long f = 0;
-                        for (uint32_t i = 0; i < P; ++i)
-                            f += fb_mix64(st_hash[ND_REF(gen, n1, i)] + ((int)i == j1 ? delta : 0ULL) +
-                                          0x632BE59BD9B4E019ULL * (i + 1));
-                        ch_fold[c] = f;
-                        ch_class[c] = (uint16_t)c;
-                    }
-                }
-                __syncwarp();
-                // (d) first earlier child with the same fold (candidate duplicate)
-                unsigned anydup = 0;
-                for (int c0 = 0; c0 < nc; c0 += 32) {
-                    const int c = c0 + (int)lane;
-                    int m = -1;
-                    if (c < nc) {
-                        const unsigned long long f = ch_fold[c];
-                        for (int r = 0; r < c; ++r)
-                            if (ch_fold[r] == f) {
-                                m = r;
-                                break;
-                            }
-                        ch_m[c] = m;
-                    }
-                    anydup |= __ballot_sync(0xFFFFFFFFu, m >= 0);
-                }
-                __syncwarp();
-                // (e) exact equality classes: only children with a fold match need the word-by-word verification
-                if (anydup) {
-                    for (int c = 0; c < nc; ++c) {
-                        if (ch_m[c] < 0) continue;
-                        const int n1 = ch_parent[c], j1 = ch_part[c];
-                        const unsigned long long f = ch_fold[c];
-                        int found = -1;
-                        for (int r = ch_m[c]; r < c && found < 0; ++r) {
-                            if (ch_fold[r] != f || ch_class[r] != r) continue;  // representatives with the same fold
-                            const int n2 = ch_parent[r], j2 = ch_part[r];
-                            bool eq = true;
-                            for (uint32_t i = 0; i < P && eq; ++i) {
-                                const int sA = ND_REF(gen, n1, i), sB = ND_REF(gen, n2, i);
-                                const bool addA = (int)i == j1, addB = (int)i == j2;
-                                if (sA == sB && addA == addB) continue;
-                                if (st_hash[sA] + (addA ? delta : 0ULL) != st_hash[sB] + (addB ? delta : 0ULL)) {
-                                    eq = false;
-                                    break;
-                                }
-                                const unsigned long long *cA = ST_CNT(sA), *cB = ST_CNT(sB);
-                                const int hiA = st_hi[sA], hiB = st_hi[sB];
-                                for (uint32_t p0 = cur_start; p0 < wend; p0 += 32) {
-                                    const uint32_t pos = p0 + lane;
-                                    bool neq = false;
-                                    if (pos < wend) {
-                                        const uint32_t lg = pos >> 4, k = pos & 15;
-                                        unsigned long long A[4], Bw[4];
-#pragma unroll
-                                        for (int a = 0; a < 4; ++a) {
-                                            A[a] = ((int)lg <= hiA) ? cA[(uint64_t)pos * 4 + a] : 0ULL;
-                                            Bw[a] = ((int)lg <= hiB) ? cB[(uint64_t)pos * 4 + a] : 0ULL;
-                                        }
-                                        if ((addA || addB) && lg >= ri.lg0 && lg < ri.lg1) {
-                                            const uint32_t g = ri.gbase + lg;
-                                            const uint32_t pr = bp.fr.present[g];
-                                            if ((pr >> k) & 1u) {
-                                                const uint32_t al = bp.fr.allele[g];
-                                                const uint32_t av = ((al >> k) & 1u) | (((al >> (16 + k)) & 1u) << 1);
-                                                const uint32_t q = qual32[(uint64_t)g * 4 + (k >> 2)];
-                                                const unsigned long long w = lut_s[(q >> (8 * (k & 3))) & 0xFFu];
-#pragma unroll
-                                                for (int a = 0; a < 4; ++a) {
-                                                    if ((uint32_t)a == av) {
-                                                        if (addA) A[a] = (A[a] + w) | FB_PRESENT;
-                                                        if (addB) Bw[a] = (Bw[a] + w) | FB_PRESENT;
-                                                    }
-                                                }
-                                            }
-                                        }
-                                        neq = (A[0] != Bw[0]) | (A[1] != Bw[1]) | (A[2] != Bw[2]) | (A[3] != Bw[3]);
-                                    }
-                                    if (__any_sync(0xFFFFFFFFu, neq)) {
-                                        eq = false;
-                                        break;
-                                    }
-                                }
-                            }
-                            if (eq) found = r;
-                        }
-                        __syncwarp();
-                        if (lane == 0 && found >= 0) ch_class[c] = (uint16_t)found;
-                        __syncwarp();
-                    }
-                }
-                PROF(7)
-                // (f) heap: global_clustering.rs:122-135
-                HeapRef hp;
-                hp.score = hp_score;
-                hp.item = hp_item;
-                hp.len = 0;
-                if (!anydup) {
-                    // no two children can be equal: the `exists` scan is vacuous, lane 0 runs the pushes back to back
-                    if (lane == 0)
-                        for (int c = 0; c < nc; ++c) {
-                            hp.push(ch_score[c], c);
-                            if ((uint32_t)hp.len > width) hp.pop();
-                        }
-                    hp.len = __shfl_sync(0xFFFFFFFFu, hp.len, 0);
-                    __syncwarp();
-                }
-                for (int c = 0; anydup && c < nc; ++c) {
-                    const double sc = ch_score[c];
-                    bool exists = false;
-                    if (anydup) {
-                        const int cls = ch_class[c];
-                        for (int e0 = 0; e0 < hp.len; e0 += 32) {
-                            const int e = e0 + (int)lane;
-                            bool hit = false;
-                            if (e < hp.len) hit = (ch_class[hp_item[e]] == cls) && (hp_score[e] >= sc);
-                            if (__any_sync(0xFFFFFFFFu, hit)) exists = true;
-                        }
-                    }
-                    if (!exists) {
-                        if (lane == 0) {
-                            hp.push(sc, c);
-                            if ((uint32_t)hp.len > width) hp.pop();
-                        }
-                        hp.len = __shfl_sync(0xFFFFFFFFu, hp.len, 0);
-                        __syncwarp();
-                    }
-                }
-                const int len = hp.len;
-                PROF(8)
-                if (bp.prof && tid == 0) { pt[10] += nc; pt[11] += len; }
-                // (g) which states does the next generation need?  (plain / addnew / st_mark are cleared at the end of the
-                //     previous step, off the critical path)
-                for (int x = (int)lane; x < len * (int)P; x += 32) {
-                    const int e = x / (int)P, i = x % (int)P;
-                    const int c = hp_item[e];
-                    if (i != (int)ch_part[c]) plain[ND_REF(gen, ch_parent[c], i)] = 1;
-                }
-                __syncwarp();
-                {
-                    // jobs: one per distinct state that receives the read, created by the first survivor that needs it
-                    // (match_any elects it), in survivor order: copies first [0, nj_copy) taking free ids in that order,
-                    // in-place ones stored from the back of the array
-                    int nj_copy = 0, nj_inpl = 0;
-                    int nfree = ms->n_free;
-                    const unsigned lt = (1u << lane) - 1u;
-                    for (int e0 = 0; e0 < len; e0 += 32) {
-                        const int e = e0 + (int)lane;
-                        int sx = -1;
-                        if (e < len) {
-                            const int c = hp_item[e];
-                            sx = ND_REF(gen, ch_parent[c], ch_part[c]);
-                        }
-                        const bool need = sx >= 0 && addnew[sx] < 0;  // not created by an earlier chunk
-                        __syncwarp();  // every lane has read addnew[] before an elected lane writes it below
-                        const unsigned grp = __match_any_sync(0xFFFFFFFFu, need ? sx : -1 - (int)lane);
-                        const bool leader = need && (int)lane == __ffs(grp) - 1;
-                        const bool cp = leader && plain[sx] != 0;
-                        const unsigned bc = __ballot_sync(0xFFFFFFFFu, cp), bi = __ballot_sync(0xFFFFFFFFu, leader && !cp);
-                        if (leader) {
-                            BeamJob jb;
-                            jb.src = (uint32_t)sx;
-                            jb.src_hi = st_hi[sx];
-                            jb._pad = 0;
-                            if (cp) {
-                                const int d = st_free[nfree - 1 - __popc(bc & lt)];
-                                addnew[sx] = d;
-                                jb.dst = (uint32_t)d;
-                                jobs[nj_copy + __popc(bc & lt)] = jb;
-                            } else {
-                                addnew[sx] = sx;
-                                jb.dst = (uint32_t)sx;
-                                jobs[(int)Wm + 1 - (nj_inpl + __popc(bi & lt))] = jb;
-                            }
-                        }
-                        nj_copy += __popc(bc);
-                        nj_inpl += __popc(bi);
-                        nfree -= __popc(bc);
-                        __syncwarp();
-                    }
-                    if (lane == 0) {
-                        ms->n_free = nfree;
-                        ms->n_jobs_copy = nj_copy;
-                        ms->n_jobs_inplace = nj_inpl;
-                        ms->n_nodes[gen ^ 1] = len;
-                        if (bp.prof) {
-                            pt[13] += nj_copy;
-                            pt[14] += nj_inpl;
-                            pt[15] += n_live;
-                            pt[9] += n_nodes;
-                        }
-                    }
-                }
-                __syncwarp();
-                __threadfence_block();
-                asm volatile("bar.arrive 1, %0;" ::"n"(NT) : "memory");  // releases warps 1..7 into phase 3
-                // next generation's node tables + history (one lane per entry)
-                {
-                    const int ng2 = gen ^ 1;
-                    for (int e = (int)lane; e < len; e += 32) {
-                        const int c = hp_item[e];
-                        const int n = ch_parent[c], j = ch_part[c];
-                        ND_SCORE(ng2, e) = hp_score[e];
-                        for (uint32_t i = 0; i < P; ++i) {
-                            int s = ND_REF(gen, n, i);
-                            double er = ND_ERR(gen, n, i);
-                            if ((int)i == j) {
-                                er = er + sc_diff[s];
-                                s = addnew[s];
-                            }
-                            ND_REF(ng2, e, i) = (uint16_t)s;
-                            ND_ERR(ng2, e, i) = er;
-                            st_mark[s] = 1;
-                        }
-                        hist[(uint64_t)step * Wm + e] = (uint32_t)n | ((uint32_t)j << 16);
-                    }
-                }
-                __syncwarp();
-                for (uint32_t sx = lane; sx < NS; sx += 32) {  // ready for the next step
-                    plain[sx] = 0;
-                    addnew[sx] = -1;
-                }
-                // per-state bookkeeping of the new states (each dst is written once; a copy's dst is never a src)
-                {
-                    const int nj_copy = ms->n_jobs_copy, njt = nj_copy + ms->n_jobs_inplace;
-                    for (int x = (int)lane; x < njt; x += 32) {
-                        const BeamJob jb = x < nj_copy ? jobs[x] : jobs[(int)Wm + 1 - (x - nj_copy)];
-                        const unsigned long long h = st_hash[jb.src] + delta;
-                        __syncwarp(__activemask());
-                        st_hash[jb.dst] = h;
-                        st_hi[jb.dst] = max(jb.src_hi, (int)ri.lg1 - 1);
-                    }
-                }
-                __syncwarp();
-                // free list + live list of the next generation (deterministic order)
-                {
-                    int nl = 0, nf = 0;
-                    for (uint32_t s0 = 0; s0 < NS; s0 += 32) {
-                        const uint32_t s = s0 + lane;
-                        const bool isl = s < NS && st_mark[s];
-                        const unsigned bal = __ballot_sync(0xFFFFFFFFu, isl);
-                        if (isl) live[nl + __popc(bal & ((1u << lane) - 1u))] = (int)s;
-                        nl += __popc(bal);
-                    }
-                    // free list: descending ids so that pops hand out ascending ids
-                    for (int s0 = (int)((NS + 31) / 32) * 32 - 32; s0 >= 0; s0 -= 32) {
-                        const int s = s0 + 31 - (int)lane;  // lane 0 sees the largest id of the chunk
-                        const bool isf = s >= 1 && s < (int)NS && !st_mark[s];
-                        const unsigned bal = __ballot_sync(0xFFFFFFFFu, isf);
-                        if (isf) st_free[nf + __popc(bal & ((1u << lane) - 1u))] = s;
-                        nf += __popc(bal);
-                    }
-                    if (lane == 0) {
-                        ms->n_live = nl;
-                        ms->n_free = nf;
-                    }
-                    __syncwarp();
-                    for (uint32_t sx = lane; sx < NS; sx += 32) st_mark[sx] = 0;  // ready for the next step
-                }
+#define FB_BEAM_POOL_LD(p) (*(p))
+#define FB_BEAM_WRITER true
+#define FB_BEAM_VERIFIED(x)
+#define FB_BEAM_ARRIVE() asm volatile("bar.arrive 1, %0;" ::"n"(NT) : "memory")
+#include "fb_beam_decide.inc"
+#undef FB_BEAM_POOL_LD
+#undef FB_BEAM_WRITER
+#undef FB_BEAM_VERIFIED
+#undef FB_BEAM_ARRIVE
             }
             PROF(1)
             cells += (unsigned long long)n_nodes * rx.nnz;

@@ -1,0 +1,566 @@
+// fb_beam_wide.cuh — beam_search_phasing (global_clustering.rs:10-179) for ONE large instance spread over the whole GPU.
+//
+// k_beam (fb_beam.cuh) gives an instance one CTA: right for thousands of small blocks, hopeless for a block whose reads
+// span tens of thousands of SNPs (the 100k-read x 50k-SNP block of BASELINE.json configs[2]: 3125 groups per read, 1.6 MB
+// of counts per haplotype state).  Here every CTA of a cooperative grid owns an interleaved slice of the SNP axis
+// (chunks of FB_BW_CH groups, chunk c belongs to CTA c mod gridDim.x) of EVERY haplotype state, and a step (one read) is
+//   phase A  every CTA scores its slice of the read against every live state, sums its slice of delta(read) and of
+//            the hash terms that leave the window; the partial sums (exact integers: order-free) are reduced across
+//            the grid with RED atomics into a per-step slot of global memory
+//   -------- ONE grid barrier per step --------
+//   phase B  every CTA forms the p-values of all live states and runs the warp-0 decision section
+//            (fb_beam_decide.inc: pruning, child scores, equality classes, BinaryHeap, next generation) REDUNDANTLY on
+//            identical inputs, so all CTAs hold the same node tables / job list without a broadcast
+//   phase C  every CTA materialises its slice of the surviving generation's new states (copy or in place) and the is-max
+//            planes; the next step's phase A reads only the CTA's own slices, so no barrier is needed here
+// Full-state reads (the ordered epsilon replay of a non-dyadic epsilon, the word-by-word equality check behind a hash
+// match) touch slices that other CTAs update in place in phase C of the same step: steps that execute one add a second
+// grid barrier before phase C.  Both are rare (first reads of a haplotype; states that became equal after the window
+// moved).  Results are bit-identical to k_beam and to the oracle (tests/test_gpu_beam_wide.py).
+#pragma once
+#include "fb_beam.cuh"
+
+#define FB_BW_THREADS 256
+#define FB_BW_WARPS (FB_BW_THREADS / 32)
+#define FB_BW_CH 2  // groups per ownership chunk: 32 positions = 1 KB of counts = one warp pass of the materialisation
+
+struct __align__(8) BeamWideAcc {  // one per (step slot, state)
+    unsigned long long same, emptyw, sub;
+    unsigned int ne_cnt;
+    int last_diff, first_empty;
+    unsigned int _pad;
+};
+struct __align__(8) BeamWideStep {  // one per step slot
+    unsigned long long total, delta;
+};
+
+int fb_beam_wide_max_grid(size_t smem_bytes, int sm_count, int *grid);
+int fb_beam_wide_launch(unsigned grid, size_t smem_bytes, cudaStream_t stream, const struct BeamParams &bp);
+
+__device__ __forceinline__ unsigned long long fb_ld_acquire_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// all threads of all CTAs; `target` = arrivals expected so far (monotonic counter, never reset during a launch)
+__device__ __forceinline__ void fb_grid_barrier(unsigned long long *ctr, unsigned long long target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(ctr) : "memory");
+        while (fb_ld_acquire_u64(ctr) < target) {
+        }
+    }
+    __syncthreads();
+}
+
+// stable_binom_cdf_p_rev (utils_frags.rs:211-248) with its two log terms on the two lanes of a pair (sub = 0 / 1); the
+// operations and their order are those of fb_stable_binom_cdf_p_rev.  Every lane of the warp must call it.
+__device__ __forceinline__ double fb_pvalue_pair(double same_f, double diff_f, uint32_t sub, double eps, double div_factor,
+                                                 bool div_pow2, double inv_div) {
+    const unsigned long long nn = fb_as_usize(same_f + diff_f), kk = fb_as_usize(diff_f);
+    const double n64 = (double)nn, k64 = (double)kk;
+    double a = nn ? k64 / n64 : 0.5;
+    if (a == 1.0) a = 0.9999999;
+    if (a == 0.0) a = 0.0000001;
+    const double x = sub == 0 ? a : (1.0 - a);
+    const double y = sub == 0 ? eps : (1.0 - eps);
+    const double t = x * log(x / y);
+    const double t1 = __shfl_xor_sync(0xFFFFFFFFu, t, 1);
+    double rel_ent = sub == 0 ? t + t1 : t1 + t;  // lane `sub == 0` holds a*ln(a/p), the sum is a*ln(..) + (1-a)*ln(..)
+    if (a < eps) rel_ent = -rel_ent;
+    double pvs = 0.0;
+    if (nn != 0) pvs = (div_pow2 ? -1.0 * n64 * inv_div : -1.0 * n64 / div_factor) * rel_ent;
+    return 1.0 * pvs;
+}
+
+template <int P>
+__device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const int ii, uint8_t *smem, uint8_t *slot,
+                                                   unsigned long long &bar_target) {
+    constexpr int NT = FB_BW_THREADS;
+    constexpr int NW = FB_BW_WARPS;
+    constexpr uint32_t CH = FB_BW_CH;
+    const int tid = threadIdx.x;
+    const uint32_t lane = tid & 31, warp = tid >> 5;
+    const uint32_t G = gridDim.x, cta = blockIdx.x;
+    const bool writer = cta == 0;
+    BeamSmem L;
+    L.layout(bp.maxP, bp.maxW, bp.maxNS);
+    double *nd_score = reinterpret_cast<double *>(smem + L.off_nd_score);     // [2][W]
+    double *nd_err = reinterpret_cast<double *>(smem + L.off_nd_err);         // [2][W][P]
+    uint16_t *nd_ref = reinterpret_cast<uint16_t *>(smem + L.off_nd_ref);     // [2][W][P]
+    unsigned long long *st_hash = reinterpret_cast<unsigned long long *>(smem + L.off_st_hash);
+    double *sc_same = reinterpret_cast<double *>(smem + L.off_sc_same);
+    double *sc_diff = reinterpret_cast<double *>(smem + L.off_sc_diff);
+    double *sc_pv = reinterpret_cast<double *>(smem + L.off_sc_pv);
+    int *st_hi = reinterpret_cast<int *>(smem + L.off_st_hi);
+    int *st_mark = reinterpret_cast<int *>(smem + L.off_st_mark);
+    int *st_free = reinterpret_cast<int *>(smem + L.off_free);
+    int *live = reinterpret_cast<int *>(smem + L.off_live);
+    double *ch_score = reinterpret_cast<double *>(smem + L.off_ch_score);
+    unsigned long long *ch_fold = reinterpret_cast<unsigned long long *>(smem + L.off_ch_fold);
+    int *ch_m = reinterpret_cast<int *>(smem + L.off_ch_m);
+    uint16_t *ch_parent = reinterpret_cast<uint16_t *>(smem + L.off_ch_parent);
+    uint16_t *ch_part = reinterpret_cast<uint16_t *>(smem + L.off_ch_part);
+    uint16_t *ch_class = reinterpret_cast<uint16_t *>(smem + L.off_ch_class);
+    double *hp_score = reinterpret_cast<double *>(smem + L.off_hp_score);
+    int *hp_item = reinterpret_cast<int *>(smem + L.off_hp_item);
+    uint32_t *lut_s = reinterpret_cast<uint32_t *>(smem + L.off_lut);
+    uint32_t *wscr = reinterpret_cast<uint32_t *>(smem + L.off_wscr) + warp * 16;
+    BeamJob *jobs = reinterpret_cast<BeamJob *>(smem + L.off_job);
+    int *addnew = reinterpret_cast<int *>(smem + L.off_addnew);
+    int *plain = reinterpret_cast<int *>(smem + L.off_plain);
+    int *replay = reinterpret_cast<int *>(smem + L.off_replay);
+    struct Misc {
+        unsigned long long delta[2];  // delta(read) of the current step (index = step parity, as in k_beam)
+        int n_nodes[2];
+        int n_live, n_free, n_jobs_copy, n_jobs_inplace;
+        int n_replay, full_reads;  // full_reads: this step read whole states (replay / exact comparison)
+    };
+    Misc *ms = reinterpret_cast<Misc *>(smem + L.off_misc);
+    uint32_t *btbuf = reinterpret_cast<uint32_t *>(smem + L.off_rq);  // backtrack staging (the read staging area of k_beam)
+
+    uint32_t *hist = reinterpret_cast<uint32_t *>(slot + bp.hist_off);
+    const uint32_t *__restrict__ qual32 = reinterpret_cast<const uint32_t *>(bp.fr.qual);
+    const uint8_t *__restrict__ qual8 = reinterpret_cast<const uint8_t *>(bp.fr.qual);
+    const InstDev in = bp.inst[ii];
+    const uint32_t Wmax = P * bp.B;
+    const uint32_t NS = P * bp.B * (P + 1) + 1;
+    const uint32_t npos = in.ng * 16;
+    const uint64_t state_words = ((uint64_t)npos * 4 + in.ng + 1) & ~1ULL;
+    unsigned long long *pool = reinterpret_cast<unsigned long long *>(slot);
+#define ST_CNT(s) (pool + (uint64_t)(s) * state_words)
+#define ST_MASK(s) (reinterpret_cast<uint2 *>(pool + (uint64_t)(s) * state_words + (uint64_t)npos * 4))
+    const uint32_t Wm = bp.maxW;  // smem strides
+    const uint32_t Pm = bp.maxP;
+#define ND_SCORE(g, n) nd_score[(g) * Wm + (n)]
+#define ND_ERR(g, n, h) nd_err[((g) * Wm + (n)) * Pm + (h)]
+#define ND_REF(g, n, h) nd_ref[((g) * Wm + (n)) * Pm + (h)]
+    const RInfo *__restrict__ rinfo = bp.rinfo + in.read_off;
+    const RExtra *__restrict__ rextra = bp.rextra + in.read_off;
+
+    // chunks of CH groups are dealt round-robin to the CTAs: the first chunk >= cA that this CTA owns
+    auto my_first_chunk = [&](uint32_t cA) { return cA + ((cta + G - cA % G) % G); };
+
+    // ---- init: one root node over the empty state (global_clustering.rs:29-47) ---------------------------------------
+    fb_grid_barrier(bp.wbar, bar_target += G);  // the previous instance's readers of the step slots are done
+    for (uint32_t s = tid; s < NS; s += NT) {
+        st_hash[s] = 0;
+        st_hi[s] = -1;
+        st_mark[s] = 0;
+        plain[s] = 0;
+        addnew[s] = -1;
+    }
+    auto zero_slot = [&](uint32_t sl) {  // CTA 0, all threads
+        BeamWideAcc z;
+        z.same = z.emptyw = z.sub = 0;
+        z.ne_cnt = 0;
+        z.last_diff = -1;
+        z.first_empty = INT_MAX;
+        z._pad = 0;
+        for (uint32_t s = tid; s < NS; s += NT) bp.wacc[(uint64_t)sl * bp.maxNS + s] = z;
+        if (tid == 0) {
+            bp.wstep[sl].total = 0;
+            bp.wstep[sl].delta = 0;
+        }
+    };
+    if (writer) {
+        zero_slot(0);
+        zero_slot(1);
+        zero_slot(2);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int nf = 0;
+        for (int s = (int)NS - 1; s >= 1; --s) st_free[nf++] = s;  // pop from the back: 1, 2, 3, ...
+        ms->n_free = nf;
+        ms->n_live = 1;
+        live[0] = 0;
+        ms->n_nodes[0] = 1;
+        ms->n_replay = 0;
+        ms->full_reads = 0;
+        ND_SCORE(0, 0) = 0.0;
+        for (uint32_t h = 0; h < P; ++h) {
+            ND_ERR(0, 0, h) = 0.0;
+            ND_REF(0, 0, h) = 0;
+        }
+    }
+    fb_grid_barrier(bp.wbar, bar_target += G);
+
+    long long pt[24] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tc = clock64();
+#define PROF(i)                                \
+    if (bp.prof && writer && tid == 0) {       \
+        long long n_ = clock64();              \
+        pt[i] += n_ - tc;                      \
+        tc = n_;                               \
+    }
+    const double ln_p = log((double)P);
+    const bool div_pow2 = (fb_f64_bits(bp.div_factor) & 0xFFFFFFFFFFFFFULL) == 0 && bp.div_factor > 1e-300 && bp.div_factor < 1e300;
+    const double inv_div = 1.0 / bp.div_factor;
+    int gen = 0;
+    uint32_t prev_start = 0;  // block-local position0 from which the hashes are valid
+    int gmax = -1;            // last block-local group touched so far
+    unsigned long long cells = 0, tapn = 0;
+    RInfo ri_next = rinfo[0];
+    RExtra rx_next = rextra[0];
+
+    for (uint32_t step = 0; step < in.n_reads; ++step) {
+        const uint32_t width = step < 25 ? Wmax : bp.B;  // global_clustering.rs:50-53
+        const RInfo ri = ri_next;
+        const RExtra rx = rx_next;
+        if (step + 1 < in.n_reads) {  // prefetch the next read's descriptor (consumed next iteration)
+            ri_next = rinfo[step + 1];
+            rx_next = rextra[step + 1];
+        }
+        const uint32_t cur_start = rx.first0;
+        const int par = (int)(step & 1u);
+        const int n_nodes = ms->n_nodes[gen];
+        const int n_live = ms->n_live;
+        const int gmax_new = max(gmax, (int)ri.lg1 - 1);
+        const uint32_t wend = (uint32_t)(gmax_new + 1) * 16u;  // one past the last live window position
+        const uint32_t sl = step % 3u;
+        BeamWideAcc *acc = bp.wacc + (uint64_t)sl * bp.maxNS;
+        BeamWideStep *sacc = bp.wstep + sl;
+
+        // ---- phase A: this CTA's slice of the read against every live state -------------------------------------------
+        if (writer) zero_slot((step + 1) % 3u);  // last read two steps ago, first written after this step's barrier
+        {
+            const uint32_t cA = ri.lg0 / CH, cB = (ri.lg1 - 1) / CH;
+            const uint32_t c0 = my_first_chunk(cA);
+            const uint32_t nmg = c0 <= cB ? ((cB - c0) / G + 1) * CH : 0;  // group slots of my chunks (ends may fall outside the read)
+            const int tiles_g = (int)((nmg + 31) / 32);
+            const int n_tiles = n_live * tiles_g;
+            for (int t = warp; t < n_tiles; t += NW) {
+                const int si = t % n_live, gt = t / n_live;
+                const int s = live[si];
+                const int hi = st_hi[s];
+                const uint32_t gi = (uint32_t)gt * 32 + lane;
+                const uint32_t lg = (c0 + (gi / CH) * G) * CH + gi % CH;
+                const bool valid = gi < nmg && lg >= ri.lg0 && lg < ri.lg1;
+                unsigned long long total = 0, same = 0, emptyw = 0, dl = 0;
+                uint32_t ne_cnt = 0;
+                int last_diff = -1, first_empty = INT_MAX;
+                if (valid) {
+                    const uint32_t g = ri.gbase + lg;
+                    const uint4 q = bp.fr.qual[g];
+                    const uint32_t al = bp.fr.allele[g], pr = bp.fr.present[g];
+                    uint32_t w[16];
+                    fb_group_weights(q, pr, lut_s, w);
+                    if (si == 0) {  // per-read sums, once per group: total weight and delta(read) (see fb_beam.cuh read_delta)
+                        uint32_t tsum = 0;
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) tsum += w[k];
+                        total = tsum;
+#pragma unroll
+                        for (int k = 0; k < 16; ++k)
+                            if ((pr >> k) & 1u) {
+                                const uint32_t av = ((al >> k) & 1u) | (((al >> (16 + k)) & 1u) << 1);
+                                dl += fb_G((in.ag0 + lg) * 16u + k, av) * (unsigned long long)w[k];
+                            }
+                    }
+                    const uint2 m = ((int)lg <= hi) ? __ldcg(ST_MASK(s) + lg) : make_uint2(0u, 0u);
+                    uint32_t sb, ne;
+                    fb_group_masks(al, m, sb, ne);
+                    same = fb_masked_sum(w, sb);
+                    const uint32_t eb = pr & ~ne & 0xFFFFu;
+                    if (eb) {
+                        emptyw = fb_masked_sum(w, eb);
+                        ne_cnt = __popc(eb);
+                        first_empty = (int)(lg * 16u) + __ffs(eb) - 1;
+                    }
+                    const uint32_t db = pr & ne & ~sb & 0xFFFFu;
+                    if (db) last_diff = (int)(lg * 16u) + 31 - __clz(db);
+                }
+                same = fb_warp_sum_u64(same);
+                emptyw = fb_warp_sum_u64(emptyw);
+                ne_cnt = fb_warp_sum_u32(ne_cnt);
+                last_diff = __reduce_max_sync(0xFFFFFFFFu, last_diff);
+                first_empty = __reduce_min_sync(0xFFFFFFFFu, first_empty);
+                if (si == 0) {
+                    total = fb_warp_sum_u64(total);
+                    dl = fb_warp_sum_u64(dl);
+                }
+                if (lane == 0) {
+                    if (same) atomicAdd(&acc[s].same, same);
+                    if (emptyw) atomicAdd(&acc[s].emptyw, emptyw);
+                    if (ne_cnt) atomicAdd(&acc[s].ne_cnt, ne_cnt);
+                    if (last_diff >= 0) atomicMax(&acc[s].last_diff, last_diff);
+                    if (first_empty != INT_MAX) atomicMin(&acc[s].first_empty, first_empty);
+                    if (si == 0) {
+                        if (total) atomicAdd(&sacc->total, total);
+                        if (dl) atomicAdd(&sacc->delta, dl);
+                    }
+                }
+            }
+            // hash terms of the positions [prev_start, cur_start) that leave the window, my slice of every live state
+            if (cur_start > prev_start) {
+                const uint32_t dA = (prev_start >> 4) / CH, dB = ((cur_start - 1) >> 4) / CH;
+                const uint32_t d0 = my_first_chunk(dA);
+                if (d0 <= dB) {
+                    for (int si = warp; si < n_live; si += NW) {
+                        const int s = live[si];
+                        const uint32_t pend = min(cur_start, (uint32_t)(st_hi[s] + 1) * 16u);
+                        unsigned long long sub = 0;
+                        const unsigned long long *c = ST_CNT(s);
+                        for (uint32_t ch = d0; ch <= dB; ch += G) {
+                            // the chunk's 32 positions x 4 alleles, lane = position
+                            const uint32_t pos = ch * CH * 16u + lane;
+                            if (pos >= prev_start && pos < pend) {
+#pragma unroll
+                                for (uint32_t a = 0; a < 4; ++a)
+                                    sub += fb_G(in.ag0 * 16u + pos, a) * (__ldcg(c + (uint64_t)pos * 4 + a) & FB_CNT_MASK);
+                            }
+                        }
+                        sub = fb_warp_sum_u64(sub);
+                        if (lane == 0 && sub) atomicAdd(&acc[s].sub, sub);
+                    }
+                }
+            }
+        }
+        PROF(0)
+        fb_grid_barrier(bp.wbar, bar_target += G);
+        PROF(3)
+
+        // ---- phase B.1 (every CTA, redundantly): scores and p-values of all live states ------------------------------------
+        {
+            const unsigned long long tot_q = __ldcg(&sacc->total);
+            if (tid == 0) ms->delta[par] = __ldcg(&sacc->delta);
+            for (int base = 0; base < n_live; base += NT / 2) {
+                const int si = base + (tid >> 1);
+                const uint32_t sub = tid & 1u;
+                const bool v = si < n_live;
+                const int s = v ? live[si] : 0;
+                const unsigned long long same_q = v ? __ldcg(&acc[s].same) : 0, emptyw = v ? __ldcg(&acc[s].emptyw) : 0;
+                const unsigned long long hsub = v ? __ldcg(&acc[s].sub) : 0;
+                const uint32_t ne_cnt = v ? __ldcg(&acc[s].ne_cnt) : 0;
+                const long long diff_q = v ? (long long)(tot_q - same_q - emptyw) : 0;
+                double diff_f = 0.0;
+                bool need_replay = false;
+                if (ne_cnt == 0)
+                    diff_f = fb_q26_to_f64(diff_q);
+                else if (bp.eps_safe)
+                    diff_f = fb_q26_to_f64(diff_q + (long long)ne_cnt * (long long)(bp.eps * FB_Q26));
+                else if (__ldcg(&acc[s].last_diff) < __ldcg(&acc[s].first_empty))
+                    // every empty position lies right of every diff position: the exact dyadic part followed by ne_cnt
+                    // consecutive `+= epsilon`, evaluated in closed form per binade (fb_add_eps_n)
+                    diff_f = fb_add_eps_n(fb_q26_to_f64(diff_q), bp.eps, ne_cnt);
+                else
+                    need_replay = true;
+                const double same_f = fb_q26_to_f64((long long)same_q);
+                const double pv = fb_pvalue_pair(same_f, diff_f, sub, bp.eps, bp.div_factor, div_pow2, inv_div);
+                if (v && sub == 0) {
+                    sc_same[s] = same_f;
+                    sc_diff[s] = diff_f;
+                    sc_pv[s] = pv;
+                    if (hsub) st_hash[s] -= hsub;
+                    if (need_replay) replay[atomicAdd(&ms->n_replay, 1)] = s;
+                }
+            }
+            __syncthreads();
+            const int n_replay = ms->n_replay;
+            if (n_replay) {
+                // ordered replay over the whole read (utils_frags.rs:33-72 in canonical order); reads planes that other
+                // CTAs own, hence the second grid barrier of this step before phase C
+                const uint32_t g0 = ri.gbase + ri.lg0, g1 = ri.gbase + ri.lg1;
+                for (int x = warp; x < n_replay; x += NW) {
+                    const int s = replay[x];
+                    const double diff_f =
+                        fb_replay_diff_t<32, true>(bp.fr, g0, g1, ST_MASK(s), ri.lg0, st_hi[s], lut_s, bp.eps, wscr);
+                    const double pv = fb_pvalue_pair(sc_same[s], diff_f, lane & 1u, bp.eps, bp.div_factor, div_pow2, inv_div);
+                    if (lane == 0) {
+                        sc_diff[s] = diff_f;
+                        sc_pv[s] = pv;
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    ms->n_replay = 0;
+                    ms->full_reads = 1;
+                }
+                // (the write is ordered before every later read of full_reads by the named barrier / __syncthreads below)
+            }
+        }
+        PROF(4)
+
+        // ---- phase B.2 (warp 0 of every CTA, redundantly): the decision section; the other warps wait for the job list ----
+        if (warp != 0) {
+            asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+        } else {
+#define FB_BEAM_POOL_LD(p) __ldcg(p)
+#define FB_BEAM_WRITER writer
+#define FB_BEAM_VERIFIED(x) \
+    if (lane == 0) ms->full_reads = 1
+#define FB_BEAM_ARRIVE() asm volatile("bar.arrive 1, %0;" ::"n"(NT) : "memory")
+#include "fb_beam_decide.inc"
+#undef FB_BEAM_POOL_LD
+#undef FB_BEAM_WRITER
+#undef FB_BEAM_VERIFIED
+#undef FB_BEAM_ARRIVE
+        }
+        PROF(1)
+        // Steps that read whole states must not overlap another CTA's in-place update of the same step.  full_reads is
+        // written before the job list is published (bar 1) and cleared only after the closing __syncthreads of the
+        // step, and it has the same value in every CTA (the decision section is deterministic).
+        const bool extra = ms->full_reads != 0;
+        if (extra) fb_grid_barrier(bp.wbar, bar_target += G);
+
+        // ---- phase C (all warps but 0, which finishes the bookkeeping in the include above): my slices of the new states ----
+        if (warp != 0) {
+            const int nj_copy = ms->n_jobs_copy, nj_inpl = ms->n_jobs_inplace;
+            const int gs = (int)(cur_start >> 4);
+            for (int pass = 0; pass < 2; ++pass) {
+                const int nj = pass == 0 ? nj_copy : nj_inpl;
+                if (nj == 0) continue;
+                // copies: the whole window [gs, gmax_new]; in place: the read's groups only
+                const int glo = pass == 0 ? gs : (int)ri.lg0;
+                const int ghi = pass == 0 ? gmax_new : (int)ri.lg1 - 1;
+                const uint32_t cA = (uint32_t)glo / CH, cB = (uint32_t)ghi / CH;
+                const uint32_t c0 = my_first_chunk(cA);
+                const int nmc = c0 <= cB ? (int)((cB - c0) / G + 1) : 0;
+                const int total = nj * nmc;  // one warp pass per (job, chunk)
+                for (int x = (int)warp - 1; x < total; x += NW - 1) {
+                    const int jn = x / nmc, kc = x - jn * nmc;
+                    const BeamJob jb = pass == 0 ? jobs[jn] : jobs[(int)Wm + 1 - jn];
+                    const int lg = (int)((c0 + (uint32_t)kc * G) * CH + (lane >> 4));
+                    const uint32_t k = lane & 15u;
+                    const bool act = lg >= glo && lg <= ghi;
+                    bool im0 = false, im1 = false, im2 = false, im3 = false;
+                    if (act) {
+                        const uint64_t pos = (uint64_t)lg * 16 + k;
+                        unsigned long long c0w = 0, c1w = 0, c2w = 0, c3w = 0;
+                        if (lg <= jb.src_hi) {
+                            const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(ST_CNT(jb.src) + pos * 4);
+                            const ulonglong2 v0 = __ldcg(src), v1 = __ldcg(src + 1);
+                            c0w = v0.x;
+                            c1w = v0.y;
+                            c2w = v1.x;
+                            c3w = v1.y;
+                        }
+                        if (lg >= (int)ri.lg0 && lg < (int)ri.lg1) {
+                            const uint32_t g = ri.gbase + (uint32_t)lg;
+                            const uint32_t pr = bp.fr.present[g], al = bp.fr.allele[g];
+                            const uint32_t qb = qual8[(uint64_t)g * 16 + k];
+                            if ((pr >> k) & 1u) {
+                                const uint32_t av = ((al >> k) & 1u) | (((al >> (16 + k)) & 1u) << 1);
+                                const unsigned long long w = lut_s[qb];
+                                if (av == 0) c0w = (c0w + w) | FB_PRESENT;
+                                if (av == 1) c1w = (c1w + w) | FB_PRESENT;
+                                if (av == 2) c2w = (c2w + w) | FB_PRESENT;
+                                if (av == 3) c3w = (c3w + w) | FB_PRESENT;
+                            }
+                        }
+                        ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(ST_CNT(jb.dst) + pos * 4);
+                        dst[0] = make_ulonglong2(c0w, c1w);
+                        dst[1] = make_ulonglong2(c2w, c3w);
+                        const unsigned long long m0 = c0w & FB_CNT_MASK, m1 = c1w & FB_CNT_MASK, m2 = c2w & FB_CNT_MASK,
+                                                 m3 = c3w & FB_CNT_MASK;
+                        unsigned long long mx = m0 > m1 ? m0 : m1;
+                        const unsigned long long my = m2 > m3 ? m2 : m3;
+                        mx = mx > my ? mx : my;
+                        if (mx > 0) {
+                            im0 = m0 == mx;
+                            im1 = m1 == mx;
+                            im2 = m2 == mx;
+                            im3 = m3 == mx;
+                        }
+                    }
+                    const uint32_t sh = lane & 16u;
+                    const uint32_t b0 = (__ballot_sync(0xFFFFFFFFu, im0) >> sh) & 0xFFFFu;
+                    const uint32_t b1 = (__ballot_sync(0xFFFFFFFFu, im1) >> sh) & 0xFFFFu;
+                    const uint32_t b2 = (__ballot_sync(0xFFFFFFFFu, im2) >> sh) & 0xFFFFu;
+                    const uint32_t b3 = (__ballot_sync(0xFFFFFFFFu, im3) >> sh) & 0xFFFFu;
+                    if (act && k == 0) ST_MASK(jb.dst)[lg] = make_uint2(b0 | (b1 << 16), b2 | (b3 << 16));
+                }
+            }
+        }
+        cells += (unsigned long long)n_nodes * rx.nnz;
+        tapn += (unsigned long long)n_nodes * P;
+        gen ^= 1;
+        prev_start = cur_start;
+        gmax = gmax_new;
+        __syncthreads();
+        if (extra && tid == 0) ms->full_reads = 0;  // next read of it is after the next step's grid barrier
+        PROF(2)
+    }
+
+    // ---- global_clustering.rs:149-176: best = into_sorted_vec()[0]; walk the parent pointers (CTA 0, warp 0) ----------
+    if (writer && warp == 0) {
+        const int len = ms->n_nodes[gen];
+        int e = 0;
+        if (lane == 0) {
+            HeapRef hp;
+            hp.score = hp_score;
+            hp.item = hp_item;
+            hp.len = len;
+            for (int x = 0; x < len; ++x) {
+                hp_score[x] = ND_SCORE(gen, x);
+                hp_item[x] = x;
+            }
+            hp.into_sorted();
+            e = hp_item[0];
+            bp.best_out[ii] = hp_score[0];
+            bp.cells_out[ii] = cells;
+            bp.tapn_out[ii] = tapn;
+        }
+        // the history rows are staged in shared memory a batch of steps at a time, so that the dependent walk runs at
+        // shared-memory latency (one L2 round trip per batch instead of one per read)
+        uint8_t *as = bp.assign_out + in.assign_off;
+        const int rows = max(1, (int)(2u * FB_BEAM_RG * 16u / 4u / Wm));
+        for (int hi_step = (int)in.n_reads; hi_step > 0; hi_step -= rows) {
+            const int lo_step = max(0, hi_step - rows);
+            const int n = (hi_step - lo_step) * (int)Wm;
+            __syncwarp();
+            for (int x = (int)lane; x < n; x += 32) btbuf[x] = hist[(uint64_t)lo_step * Wm + x];
+            __syncwarp();
+            if (lane == 0)
+                for (int st = hi_step - 1; st >= lo_step; --st) {
+                    const uint32_t v = btbuf[(st - lo_step) * (int)Wm + e];
+                    as[st] = (uint8_t)(v >> 16);
+                    e = (int)(v & 0xFFFFu);
+                }
+        }
+        if (lane == 0 && bp.prof) {
+            PROF(5)
+            for (int i = 0; i < 12; ++i) atomicAdd(bp.prof + i, (unsigned long long)pt[i]);
+            for (int i = 13; i < 24; ++i) atomicAdd(bp.prof + i, (unsigned long long)pt[i]);
+            atomicAdd(bp.prof + 12, (unsigned long long)in.n_reads);
+        }
+    }
+#undef PROF
+#undef ST_CNT
+#undef ST_MASK
+#undef ND_SCORE
+#undef ND_ERR
+#undef ND_REF
+}
+
+#ifdef FB_BEAM_WIDE_IMPL  // defined by fb_beam_wide_tu.cu only: the kernel is not a template
+// Cooperative launch: every CTA must be resident (the grid barrier spins).  bp.order lists the instances, run one after
+// the other by the whole grid; the scratch is ONE slot (pool + history) sized for the largest of them.
+__global__ void __launch_bounds__(FB_BW_THREADS, 1) k_beam_wide(BeamParams bp) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int tid = threadIdx.x;
+    {
+        BeamSmem L;
+        L.layout(bp.maxP, bp.maxW, bp.maxNS);
+        uint32_t *lut_s = reinterpret_cast<uint32_t *>(smem + L.off_lut);
+        for (int i = tid; i < 256; i += FB_BW_THREADS) lut_s[i] = bp.lut[i];
+    }
+    unsigned long long bar_target = 0;
+    for (int wk = 0; wk < bp.n_work; ++wk) {
+        const int ii = bp.order[wk];
+        __syncthreads();
+        switch (bp.inst[ii].ploidy) {
+            case 2: fb_beam_wide_instance<2>(bp, ii, smem, bp.scratch, bar_target); break;
+            case 3: fb_beam_wide_instance<3>(bp, ii, smem, bp.scratch, bar_target); break;
+            case 4: fb_beam_wide_instance<4>(bp, ii, smem, bp.scratch, bar_target); break;
+            case 5: fb_beam_wide_instance<5>(bp, ii, smem, bp.scratch, bar_target); break;
+            case 6: fb_beam_wide_instance<6>(bp, ii, smem, bp.scratch, bar_target); break;
+            case 7: fb_beam_wide_instance<7>(bp, ii, smem, bp.scratch, bar_target); break;
+            case 8: fb_beam_wide_instance<8>(bp, ii, smem, bp.scratch, bar_target); break;
+            default: break;
+        }
+    }
+}
+#endif  // FB_BEAM_WIDE_IMPL

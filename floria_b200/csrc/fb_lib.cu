@@ -692,6 +692,86 @@ int fb_phase_blocks(fb_ctx *ctx, const fb_frags *fr, uint64_t n_blocks, const ui
     return rc;
 }
 
+// One block at a fixed ploidy on an explicit read list (graph_processing.rs:140-162).
+int fb_phase_block_resident(fb_ctx *ctx, const fb_dfrags *df, uint64_t n_sel, const uint32_t *sel, uint32_t ploidy,
+                            const fb_params *prm, uint8_t *hap_out, double *mec_bases, double *mec_errors,
+                            fb_block_phase *out) {
+    if (!ctx) return FB_ERR_ARG;
+    if (!df || !out) FB_FAIL(FB_ERR_ARG, "null argument");
+    memset(out, 0, sizeof(*out));
+    FB_CK(cudaSetDevice(ctx->device));
+    int rc = fb_check_params(ctx, prm, ploidy);
+    if (rc) return rc;
+    if (ploidy < 1) FB_FAIL(FB_ERR_ARG, "ploidy must be >= 1");
+    ctx->ev_used = 0;
+    cudaEvent_t ev_start = fb_event(ctx);
+    std::vector<uint32_t> reads;
+    if (sel) {
+        if ((rc = fb_check_sel(ctx, df, n_sel, sel))) return rc;
+        reads.assign(sel, sel + n_sel);
+    } else {
+        n_sel = df->n_reads;
+        reads.resize(n_sel);
+        for (uint64_t i = 0; i < n_sel; ++i) reads[i] = (uint32_t)i;
+    }
+    if (n_sel == 0) FB_FAIL(FB_ERR_ARG, "a block needs at least one read");
+    Engine e;
+    e.ctx = ctx;
+    e.df = df;
+    const int b = e.add_block(reads);
+    e.add_instance(b, ploidy);
+    if ((rc = e.finalize_and_upload(prm->epsilon))) return rc;
+    BeamRun br;
+    if ((rc = fb_run_beam(ctx, e, prm, nullptr, br))) return rc;
+    if ((rc = e.run_optimize(prm->num_iter_optimize))) return rc;
+    // get_mec_stats_epsilon_no_phred on the optimized partition: unweighted histogram into the spare buffer
+    if ((rc = e.launch_hist(1, 0, 0, 0, 1))) return rc;
+    if ((rc = e.launch_mec(1, 0))) return rc;
+    cudaEvent_t ev_compute = fb_event(ctx);
+    InstState st;
+    std::vector<double> mec(ploidy * 2);
+    FB_CK(cudaMemcpyAsync(&st, e.d_st, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+    FB_CK(cudaStreamSynchronize(ctx->stream));
+    FB_CK(cudaMemcpyAsync(mec.data(), e.d_mec[st.cur ^ 1], mec.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (hap_out) FB_CK(cudaMemcpyAsync(hap_out, e.d_assign[st.cur], n_sel, cudaMemcpyDeviceToHost, ctx->stream));
+    cudaEvent_t ev_end = fb_event(ctx);
+    FB_CK(cudaStreamSynchronize(ctx->stream));
+    FB_CK(cudaGetLastError());
+    for (uint32_t h = 0; h < ploidy; ++h) {
+        if (mec_bases) mec_bases[h] = mec[h * 2];
+        if (mec_errors) mec_errors[h] = mec[h * 2 + 1];
+    }
+    const uint64_t nnz = e.blocks[b].nnz;
+    out->beam_score = ploidy > 1 ? br.best_score[0] : 0.0;
+    out->opt_score = st.prev_score;
+    out->n_rounds = st.accepted;
+    out->ploidy = ploidy;
+    out->cells_sweep = (uint64_t)st.n_opt_iterate * nnz;
+    out->cells_hist = (uint64_t)(st.n_hist + 1) * nnz;
+    out->cells_beam = ploidy == 1 ? nnz : br.cells_beam[0];
+    ctx->tim.sweep_cells += out->cells_sweep;
+    ctx->tim.hist_cells += out->cells_hist;
+    e.collect_timings();
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev_start, ev_compute);
+    ctx->tim.total_ms += ms;
+    cudaEventElapsedTime(&ms, ev_compute, ev_end);
+    ctx->tim.download_ms += ms;
+    ctx->tim.beam_ms += br.beam_ms;
+    return FB_OK;
+}
+
+int fb_phase_block(fb_ctx *ctx, const fb_frags *fr, uint64_t n_sel, const uint32_t *sel, uint32_t ploidy,
+                   const fb_params *prm, uint8_t *hap_out, double *mec_bases, double *mec_errors, fb_block_phase *out) {
+    if (!ctx) return FB_ERR_ARG;
+    fb_dfrags *df = nullptr;
+    int rc = fb_frags_upload(ctx, fr, &df);
+    if (rc) return rc;
+    rc = fb_phase_block_resident(ctx, df, n_sel, sel, ploidy, prm, hap_out, mec_bases, mec_errors, out);
+    fb_frags_free(ctx, df);
+    return rc;
+}
+
 void fb_free_block_results(fb_block_results *r) {
     if (!r) return;
     free(r->best_ploidy);

@@ -8,7 +8,8 @@
 // Planes of groups beyond `hi` are empty.  Per chunk of 32 groups the lanes are split by ballot into runs of
 // epsilon-free lanes (added as ONE exact integer lump when SeqSum proves that identical to item-by-item addition)
 // and lanes holding epsilon items (replayed item by item).
-template <int L>
+// CG: the planes are read through L2 only (__ldcg), for tables that other CTAs of the running kernel write.
+template <int L, bool CG = false>
 __device__ double fb_replay_diff_t(const DFragsDev &fr, uint32_t g0, uint32_t g1, const uint2 *__restrict__ mh,
                                    uint32_t lg0, int hi, const uint32_t *lut, double eps, uint32_t *wscratch /*16 per team*/) {
     const uint32_t lane = fb_lane() % L;               // lane inside the team
@@ -28,7 +29,7 @@ __device__ double fb_replay_diff_t(const DFragsDev &fr, uint32_t g0, uint32_t g1
             uint32_t pr = fr.present[g];
             fb_group_weights(q, pr, lut, w);
             const uint32_t lg = lg0 + (g - g0);
-            uint2 m = ((int)lg <= hi) ? mh[lg] : make_uint2(0u, 0u);
+            uint2 m = ((int)lg <= hi) ? (CG ? __ldcg(mh + lg) : mh[lg]) : make_uint2(0u, 0u);
             uint32_t same, ne;
             fb_group_masks(al, m, same, ne);
             diffbits = pr & ne & ~same;

@@ -142,6 +142,25 @@ int fb_phase_blocks_resident(fb_ctx *, const fb_dfrags *, uint64_t n_blocks, con
                              const uint32_t *blk_hi, const fb_params *, fb_block_results **out);
 void fb_free_block_results(fb_block_results *);
 
+/* One block at a FIXED ploidy on an explicit read list: the body of the ploidy loop of get_local_hap_blocks
+ * (graph_processing.rs:140-162): beam_search_phasing -> optimize_clustering -> get_mec_stats_epsilon_no_phred.
+ * This is how a block is phased whose reads find_reads_in_interval would drop (spans above 10000 SNPs,
+ * local_clustering.rs:44), e.g. the 100k-read x 50k-SNP roofline block of BASELINE.json.  `sel` = ascending counter_ids
+ * (NULL = every read of the contig).  hap_out [n_sel], mec_bases / mec_errors [ploidy] (the (good, bad) pairs of
+ * graph_processing.rs:156-162) may be NULL. */
+typedef struct {
+    double beam_score;     /* score of the winning beam node */
+    double opt_score;      /* optimize_clustering's returned score */
+    uint32_t n_rounds;     /* accepted opt_iterate rounds */
+    uint32_t ploidy;
+    uint64_t cells_sweep, cells_hist, cells_beam; /* work counters, SURVEY.md section 8d */
+} fb_block_phase;
+int fb_phase_block(fb_ctx *, const fb_frags *, uint64_t n_sel, const uint32_t *sel, uint32_t ploidy, const fb_params *,
+                   uint8_t *hap_out, double *mec_bases, double *mec_errors, fb_block_phase *out);
+int fb_phase_block_resident(fb_ctx *, const fb_dfrags *, uint64_t n_sel, const uint32_t *sel, uint32_t ploidy,
+                            const fb_params *, uint8_t *hap_out, double *mec_bases, double *mec_errors,
+                            fb_block_phase *out);
+
 /* ---- fine-grained entry points (same semantics as the preserved Rust pub fns) ---------------------------------- */
 /* `sel` = ascending counter_ids of the reads of one block; `hap[i]` = haplotype of sel[i] (0..ploidy-1). */
 
