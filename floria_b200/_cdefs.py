@@ -56,6 +56,7 @@ class FbBlockResults(C.Structure):
         ("cells_sweep", C.c_uint64),
         ("cells_hist", C.c_uint64),
         ("cells_beam", C.c_uint64),
+        ("block_cells", u64p),
     ]
 
 
@@ -152,6 +153,7 @@ class BlockResults:
         self.cells_sweep = int(r.cells_sweep)
         self.cells_hist = int(r.cells_hist)
         self.cells_beam = int(r.cells_beam)
+        self.block_cells = np.ctypeslib.as_array(r.block_cells, (max(n, 1),))[:n].copy()
 
     @property
     def cells(self):

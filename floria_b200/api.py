@@ -35,6 +35,8 @@ EXPORTS = [
     "fb_frags_upload", "fb_frags_free", "fb_dfrags_bytes", "fb_get_range_with_lengths",
     "fb_find_reads_in_interval", "fb_phase_blocks", "fb_phase_blocks_resident", "fb_free_block_results",
     "fb_phase_block", "fb_phase_block_resident",
+    "fb_init_multi", "fb_destroy_multi", "fb_multi_size", "fb_multi_ctx", "fb_multi_last_error", "fb_lpt_assign",
+    "fb_contigs_upload", "fb_contigs_free", "fb_phase_contigs_resident", "fb_phase_contigs",
     "fb_score_reads", "fb_hap_block_from_partition", "fb_get_mec_stats_epsilon", "fb_beam_search_phasing",
     "fb_optimize_clustering", "fb_process_reads_for_final_parts", "fb_free_parts", "fb_get_hapq",
     "fb_update_hap_graph",
@@ -100,6 +102,23 @@ def load_library():
                               C.POINTER(FbParams), u8p, f64p, f64p]
     L.fb_update_hap_graph.argtypes = [C.c_void_p, C.POINTER(FbFrags), C.c_uint64, u64p, u64p, u32p, u32p, u32p,
                                       C.POINTER(FbParams), f64p]
+    # several devices in one process
+    i32p = C.POINTER(C.c_int)
+    L.fb_init_multi.argtypes = [C.c_int, i32p, C.POINTER(C.c_void_p)]
+    L.fb_destroy_multi.argtypes = [C.c_void_p]
+    L.fb_multi_size.argtypes = [C.c_void_p]
+    L.fb_multi_ctx.restype = C.c_void_p
+    L.fb_multi_ctx.argtypes = [C.c_void_p, C.c_int]
+    L.fb_multi_last_error.restype = C.c_char_p
+    L.fb_multi_last_error.argtypes = [C.c_void_p]
+    L.fb_lpt_assign.restype = None
+    L.fb_lpt_assign.argtypes = [f64p, C.c_uint64, C.c_uint32, u32p]
+    L.fb_contigs_upload.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(FbFrags), u64p, u32p, u32p, C.POINTER(C.c_void_p)]
+    L.fb_contigs_free.argtypes = [C.c_void_p, C.c_void_p]
+    L.fb_phase_contigs_resident.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(FbParams),
+                                            C.POINTER(C.POINTER(FbBlockResults)), u32p, C.POINTER(C.c_float)]
+    L.fb_phase_contigs.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(FbFrags), u64p, u32p, u32p, C.POINTER(FbParams),
+                                   C.POINTER(C.POINTER(FbBlockResults)), u32p, C.POINTER(C.c_float)]
     # measurement helpers (include/floria_b200_bench.h)
     L.fb_bench_synth_dense.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_double,
                                        C.c_double, u8p, u8p, u8p, C.POINTER(C.c_void_p)]
@@ -133,6 +152,118 @@ def find_reads_in_interval(start, end, frags):
     n = L.fb_find_reads_in_interval(start, end, frags.n_reads, ptr(frags.first, u32p), ptr(frags.last, u32p),
                                     ptr(out, u32p), len(out))
     return out[:n].copy()
+
+
+def contig_cost(frags, n_blocks):
+    """the cost estimate fb_contigs_upload deals contigs to devices by (stored cells, block count as tie-breaker)"""
+    return float(frags.nnz) + 1e-3 * float(n_blocks)
+
+
+def lpt_assign(costs, n_bins):
+    """fb_lpt_assign: deterministic longest-processing-time-first assignment (the library's own, so that ranks of a
+    process-per-GPU job agree with it)"""
+    L = load_library()
+    c = np.ascontiguousarray(costs, dtype=np.float64)
+    owner = np.zeros(max(len(c), 1), np.uint32)
+    L.fb_lpt_assign(ptr(c, f64p), len(c), n_bins, ptr(owner, u32p))
+    return owner[: len(c)].astype(np.int64)
+
+
+class DeviceContigs:
+    def __init__(self, multi, handle, n_contigs):
+        self.multi, self.handle, self.n_contigs = multi, handle, n_contigs
+
+    def free(self):
+        if self.handle:
+            self.multi.L.fb_contigs_free(self.multi.h, self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class MultiContext:
+    """fb_init_multi: several devices driven from this process (one host thread + stream per device inside the
+    library).  phase_contigs deals a contig list to the devices (static LPT queue) and returns per-contig results."""
+
+    def __init__(self, device_ids):
+        self.L = load_library()
+        ids = (C.c_int * len(device_ids))(*device_ids)
+        h = C.c_void_p()
+        rc = self.L.fb_init_multi(len(device_ids), ids, C.byref(h))
+        if rc != 0:
+            raise FloriaB200Error(f"fb_init_multi failed ({rc}): " + self.L.fb_last_error(None).decode())
+        self.h = h
+        self.n_devices = len(device_ids)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.fb_destroy_multi(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise FloriaB200Error(f"floria_b200 error {rc}: " + self.L.fb_multi_last_error(self.h).decode())
+
+    @staticmethod
+    def _pack(contigs, blocks):
+        n = len(contigs)
+        arr = (FbFrags * max(n, 1))()
+        keep = []
+        for k, fr in enumerate(contigs):
+            st = fr.as_struct()
+            keep.append(st)
+            arr[k] = st
+        bp = np.zeros(n + 1, np.uint64)
+        for k, (lo, _) in enumerate(blocks):
+            bp[k + 1] = bp[k] + len(lo)
+        lo = np.concatenate([np.asarray(b[0], np.uint32) for b in blocks]) if n else np.zeros(0, np.uint32)
+        hi = np.concatenate([np.asarray(b[1], np.uint32) for b in blocks]) if n else np.zeros(0, np.uint32)
+        return arr, bp, np.ascontiguousarray(lo), np.ascontiguousarray(hi), keep
+
+    def upload(self, contigs, blocks):
+        arr, bp, lo, hi, keep = self._pack(contigs, blocks)
+        out = C.c_void_p()
+        self._chk(self.L.fb_contigs_upload(self.h, len(contigs), arr, ptr(bp, u64p), ptr(lo, u32p), ptr(hi, u32p),
+                                           C.byref(out)))
+        return DeviceContigs(self, out, len(contigs))
+
+    def _collect(self, n, outs, dev, ms):
+        res = []
+        for k in range(n):
+            res.append(BlockResults(outs[k].contents))
+            self.L.fb_free_block_results(outs[k])
+        return res, dev[:n].astype(np.int64), ms.copy()
+
+    def phase_contigs_resident(self, dcontigs, params):
+        n = dcontigs.n_contigs
+        outs = (C.POINTER(FbBlockResults) * max(n, 1))()
+        dev = np.zeros(max(n, 1), np.uint32)
+        ms = np.zeros(self.n_devices, np.float32)
+        self._chk(self.L.fb_phase_contigs_resident(self.h, dcontigs.handle, C.byref(params), outs, ptr(dev, u32p),
+                                                   ms.ctypes.data_as(C.POINTER(C.c_float))))
+        return self._collect(n, outs, dev, ms)
+
+    def phase_contigs(self, contigs, blocks, params):
+        """contigs: list of Frags; blocks: list of (blk_lo, blk_hi) per contig.  Returns (list of BlockResults in contig
+        order, device index per contig, CUDA-event ms per device)."""
+        arr, bp, lo, hi, keep = self._pack(contigs, blocks)
+        n = len(contigs)
+        outs = (C.POINTER(FbBlockResults) * max(n, 1))()
+        dev = np.zeros(max(n, 1), np.uint32)
+        ms = np.zeros(self.n_devices, np.float32)
+        self._chk(self.L.fb_phase_contigs(self.h, n, arr, ptr(bp, u64p), ptr(lo, u32p), ptr(hi, u32p), C.byref(params),
+                                          outs, ptr(dev, u32p), ms.ctypes.data_as(C.POINTER(C.c_float))))
+        return self._collect(n, outs, dev, ms)
 
 
 class DeviceFrags:

@@ -172,6 +172,7 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
         unsigned long long delta[2];  // delta(read) of the current / next read (step parity)
         int n_nodes[2];
         int n_live, n_free, n_jobs_copy, n_jobs_inplace;
+        int hw;  // high-water mark of the state ids handed out so far (ids >= hw are free and untouched)
     };
     Misc *ms = reinterpret_cast<Misc *>(smem + L.off_misc);
     uint4 *rq = reinterpret_cast<uint4 *>(smem + L.off_rq);            // [2][FB_BEAM_RG]
@@ -208,9 +209,8 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
         }
         __syncthreads();
         if (tid == 0) {
-            int nf = 0;
-            for (int s = (int)NS - 1; s >= 1; --s) st_free[nf++] = s;  // pop from the back: 1, 2, 3, ...
-            ms->n_free = nf;
+            ms->n_free = 0;  // explicit free stack (ids below hw); state 0 is the root's empty state
+            ms->hw = 1;
             ms->n_live = 1;
             live[0] = 0;
             ms->n_nodes[0] = 1;
@@ -502,11 +502,13 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
 #define FB_BEAM_WRITER true
 #define FB_BEAM_VERIFIED(x)
 #define FB_BEAM_ARRIVE() asm volatile("bar.arrive 1, %0;" ::"n"(NT) : "memory")
+#define FB_BEAM_ARRIVE2()
 #include "fb_beam_decide.inc"
 #undef FB_BEAM_POOL_LD
 #undef FB_BEAM_WRITER
 #undef FB_BEAM_VERIFIED
 #undef FB_BEAM_ARRIVE
+#undef FB_BEAM_ARRIVE2
             }
             PROF(1)
             cells += (unsigned long long)n_nodes * rx.nnz;

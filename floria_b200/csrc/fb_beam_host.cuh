@@ -264,12 +264,13 @@ static int fb_run_beam(fb_ctx *ctx, Engine &e, const fb_params *prm, const BeamT
             const double steps = (double)std::max<unsigned long long>(h[12], 1);
             fprintf(stderr,
                     "[k_beam_wide prof] %.3f ms (both kernels), %d instances on a grid of %d CTAs, %.0f steps; CTA 0 cycles/step: "
-                    "phaseA(slice scoring + REDs) %.0f | grid barrier %.0f | p-values %.0f | warp0: lse %.0f "
-                    "compact+fold+dups+classes %.0f heap %.0f nextgen %.0f | phaseC wait+closing sync %.0f | children/step %.1f "
-                    "survivors/step %.1f copyjobs/step %.2f inplace/step %.2f live states/step %.2f nodes/step %.2f | backtrack total %.0f\n",
-                    br.beam_ms, (int)order_w.size(), grid_w, steps, h[0] / steps, h[3] / steps, h[4] / steps, h[6] / steps,
-                    h[7] / steps, h[8] / steps, h[1] / steps, h[2] / steps, h[10] / steps, h[11] / steps, h[13] / steps,
-                    h[14] / steps, h[15] / steps, h[9] / steps, (double)h[5]);
+                    "warp 0: bookkeeping after the live list %.0f | grid barrier %.0f | p-values %.0f | lse %.0f "
+                    "compact+fold+dups+classes %.0f heap %.0f (jobs + live list: rest) || warp 1: phase A %.0f | stage next read + "
+                    "phase C %.0f | waiting for warp 0 %.0f || children/step %.1f survivors/step %.1f copyjobs/step %.2f "
+                    "inplace/step %.2f live states/step %.2f nodes/step %.2f | backtrack total %.0f\n",
+                    br.beam_ms, (int)order_w.size(), grid_w, steps, h[1] / steps, h[3] / steps, h[4] / steps, h[6] / steps,
+                    h[7] / steps, h[8] / steps, h[0] / steps, h[2] / steps, h[20] / steps, h[10] / steps, h[11] / steps,
+                    h[13] / steps, h[14] / steps, h[15] / steps, h[9] / steps, (double)h[5]);
         }
     }
     cleanup();

@@ -115,9 +115,13 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
         unsigned long long delta[2];  // delta(read) of the current step (index = step parity, as in k_beam)
         int n_nodes[2];
         int n_live, n_free, n_jobs_copy, n_jobs_inplace;
+        int hw;  // high-water mark of the state ids handed out so far
         int n_replay, full_reads;  // full_reads: this step read whole states (replay / exact comparison)
     };
     Misc *ms = reinterpret_cast<Misc *>(smem + L.off_misc);
+    uint4 *rq = reinterpret_cast<uint4 *>(smem + L.off_rq);          // [2 * FB_BEAM_RG] this CTA's groups of the staged read
+    uint32_t *ral = reinterpret_cast<uint32_t *>(smem + L.off_ral);
+    uint16_t *rpr = reinterpret_cast<uint16_t *>(smem + L.off_rpr);
     uint32_t *btbuf = reinterpret_cast<uint32_t *>(smem + L.off_rq);  // backtrack staging (the read staging area of k_beam)
 
     uint32_t *hist = reinterpret_cast<uint32_t *>(slot + bp.hist_off);
@@ -151,29 +155,28 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
         plain[s] = 0;
         addnew[s] = -1;
     }
-    auto zero_slot = [&](uint32_t sl) {  // CTA 0, all threads
+    auto zero_slot = [&](uint32_t sl, int t0, int nt) {  // CTA 0, threads [t0, t0 + nt)
         BeamWideAcc z;
         z.same = z.emptyw = z.sub = 0;
         z.ne_cnt = 0;
         z.last_diff = -1;
         z.first_empty = INT_MAX;
         z._pad = 0;
-        for (uint32_t s = tid; s < NS; s += NT) bp.wacc[(uint64_t)sl * bp.maxNS + s] = z;
-        if (tid == 0) {
+        for (int s = tid - t0; s >= 0 && s < (int)NS; s += nt) bp.wacc[(uint64_t)sl * bp.maxNS + s] = z;
+        if (tid == t0) {
             bp.wstep[sl].total = 0;
             bp.wstep[sl].delta = 0;
         }
     };
     if (writer) {
-        zero_slot(0);
-        zero_slot(1);
-        zero_slot(2);
+        zero_slot(0, 0, NT);
+        zero_slot(1, 0, NT);
+        zero_slot(2, 0, NT);
     }
     __syncthreads();
     if (tid == 0) {
-        int nf = 0;
-        for (int s = (int)NS - 1; s >= 1; --s) st_free[nf++] = s;  // pop from the back: 1, 2, 3, ...
-        ms->n_free = nf;
+        ms->n_free = 0;  // explicit free stack (ids below hw); state 0 is the root's empty state
+        ms->hw = 1;
         ms->n_live = 1;
         live[0] = 0;
         ms->n_nodes[0] = 1;
@@ -187,7 +190,10 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
     }
     fb_grid_barrier(bp.wbar, bar_target += G);
 
-    long long pt[24] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    // profile counters of thread 0 (FB_BEAM_PROF=1) live in shared memory: 24 64-bit registers would cost the kernel spills
+    __shared__ long long pt[24];
+    if (tid < 24) pt[tid] = 0;
+    __syncthreads();
     long long tc = clock64();
 #define PROF(i)                                \
     if (bp.prof && writer && tid == 0) {       \
@@ -195,6 +201,8 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
         pt[i] += n_ - tc;                      \
         tc = n_;                               \
     }
+    long long pa = 0, pc = 0, pw = 0;  // CTA 0, warp 1: cycles in phase A, phase C, and waiting for warp 0
+    const bool prof1 = bp.prof && writer && tid == 32;
     const double ln_p = log((double)P);
     const bool div_pow2 = (fb_f64_bits(bp.div_factor) & 0xFFFFFFFFFFFFFULL) == 0 && bp.div_factor > 1e-300 && bp.div_factor < 1e300;
     const double inv_div = 1.0 / bp.div_factor;
@@ -204,6 +212,60 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
     unsigned long long cells = 0, tapn = 0;
     RInfo ri_next = rinfo[0];
     RExtra rx_next = rextra[0];
+
+    // This CTA's groups of a read, staged in shared memory one step ahead (by the warps that idle while warp 0 runs the
+    // decision section) together with the read-only sums of the step: total weight and delta(read) = sum of
+    // G(pos, allele) * weight (see fb_beam.cuh), both reduced over the grid into the step's slot.
+    constexpr uint32_t STG = 2 * FB_BEAM_RG;  // staging capacity in groups
+    auto my_groups = [&](const RInfo &r, uint32_t &c0) {
+        const uint32_t cA = r.lg0 / CH, cB = (r.lg1 - 1) / CH;
+        c0 = my_first_chunk(cA);
+        return c0 <= cB ? ((cB - c0) / G + 1) * CH : 0u;  // group slots of my chunks (the ends may fall outside the read)
+    };
+    auto stage_read = [&](const RInfo &r, uint32_t slot_idx) {  // warps 1..NW-1
+        uint32_t c0;
+        const uint32_t nmg = my_groups(r, c0);
+        // the planes of my groups -> shared memory (one thread per group) ...
+        for (uint32_t gi = (uint32_t)tid - 32; gi < min(nmg, STG); gi += NT - 32) {
+            const uint32_t lg = (c0 + (gi / CH) * G) * CH + gi % CH;
+            uint4 q = make_uint4(~0u, ~0u, ~0u, ~0u);
+            uint32_t al = 0, pr = 0;
+            if (lg >= r.lg0 && lg < r.lg1) {
+                const uint32_t g = r.gbase + lg;
+                q = bp.fr.qual[g];
+                al = bp.fr.allele[g];
+                pr = bp.fr.present[g];
+            }
+            rq[gi] = q;
+            ral[gi] = al;
+            rpr[gi] = (uint16_t)pr;
+        }
+        // ... and the per-read sums, one thread per cell (the position hash fb_G is the expensive part)
+        unsigned long long total = 0, dl = 0;
+        for (uint32_t x = (uint32_t)tid - 32; x < nmg * 16u; x += NT - 32) {
+            const uint32_t gi = x >> 4, k = x & 15u;
+            const uint32_t lg = (c0 + (gi / CH) * G) * CH + gi % CH;
+            if (lg >= r.lg0 && lg < r.lg1) {
+                const uint32_t g = r.gbase + lg;
+                const uint32_t pr = bp.fr.present[g];
+                if ((pr >> k) & 1u) {
+                    const uint32_t al = bp.fr.allele[g];
+                    const unsigned long long w = lut_s[qual8[(uint64_t)g * 16 + k]];
+                    const uint32_t av = ((al >> k) & 1u) | (((al >> (16 + k)) & 1u) << 1);
+                    total += w;
+                    dl += fb_G((in.ag0 + lg) * 16u + k, av) * w;
+                }
+            }
+        }
+        total = fb_warp_sum_u64(total);
+        dl = fb_warp_sum_u64(dl);
+        if (lane == 0) {
+            if (total) atomicAdd(&bp.wstep[slot_idx].total, total);
+            if (dl) atomicAdd(&bp.wstep[slot_idx].delta, dl);
+        }
+    };
+    if (warp != 0) stage_read(ri_next, 0);
+    __syncthreads();
 
     for (uint32_t step = 0; step < in.n_reads; ++step) {
         const uint32_t width = step < 25 ? Wmax : bp.B;  // global_clustering.rs:50-53
@@ -215,51 +277,48 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
         }
         const uint32_t cur_start = rx.first0;
         const int par = (int)(step & 1u);
-        const int n_nodes = ms->n_nodes[gen];
-        const int n_live = ms->n_live;
         const int gmax_new = max(gmax, (int)ri.lg1 - 1);
         const uint32_t wend = (uint32_t)(gmax_new + 1) * 16u;  // one past the last live window position
         const uint32_t sl = step % 3u;
         BeamWideAcc *acc = bp.wacc + (uint64_t)sl * bp.maxNS;
         BeamWideStep *sacc = bp.wstep + sl;
 
-        // ---- phase A: this CTA's slice of the read against every live state -------------------------------------------
-        if (writer) zero_slot((step + 1) % 3u);  // last read two steps ago, first written after this step's barrier
-        {
-            const uint32_t cA = ri.lg0 / CH, cB = (ri.lg1 - 1) / CH;
-            const uint32_t c0 = my_first_chunk(cA);
-            const uint32_t nmg = c0 <= cB ? ((cB - c0) / G + 1) * CH : 0;  // group slots of my chunks (ends may fall outside the read)
+        // ---- phase A (warps 1..; warp 0 is still closing the previous step's bookkeeping): this CTA's slice of the
+        //      read against every live state ------------------------------------------------------------------------------
+        if (warp != 0) {
+            long long q0 = 0;
+            if (prof1) q0 = clock64();
+            const int n_live = ms->n_live;
+            if (writer) zero_slot((step + 1) % 3u, 32, NT - 32);  // last read two steps ago, first written after this step's barrier
+            uint32_t c0;
+            const uint32_t nmg = my_groups(ri, c0);
             const int tiles_g = (int)((nmg + 31) / 32);
             const int n_tiles = n_live * tiles_g;
-            for (int t = warp; t < n_tiles; t += NW) {
+            for (int t = (int)warp - 1; t < n_tiles; t += NW - 1) {
                 const int si = t % n_live, gt = t / n_live;
                 const int s = live[si];
                 const int hi = st_hi[s];
                 const uint32_t gi = (uint32_t)gt * 32 + lane;
                 const uint32_t lg = (c0 + (gi / CH) * G) * CH + gi % CH;
                 const bool valid = gi < nmg && lg >= ri.lg0 && lg < ri.lg1;
-                unsigned long long total = 0, same = 0, emptyw = 0, dl = 0;
-                uint32_t ne_cnt = 0;
+                uint32_t same = 0, emptyw = 0, ne_cnt = 0;  // per lane: at most 16 weights of 2^26
                 int last_diff = -1, first_empty = INT_MAX;
                 if (valid) {
-                    const uint32_t g = ri.gbase + lg;
-                    const uint4 q = bp.fr.qual[g];
-                    const uint32_t al = bp.fr.allele[g], pr = bp.fr.present[g];
+                    const uint2 m = ((int)lg <= hi) ? __ldcg(ST_MASK(s) + lg) : make_uint2(0u, 0u);
+                    uint4 q;
+                    uint32_t al, pr;
+                    if (gi < STG) {
+                        q = rq[gi];
+                        al = ral[gi];
+                        pr = rpr[gi];
+                    } else {
+                        const uint32_t g = ri.gbase + lg;
+                        q = bp.fr.qual[g];
+                        al = bp.fr.allele[g];
+                        pr = bp.fr.present[g];
+                    }
                     uint32_t w[16];
                     fb_group_weights(q, pr, lut_s, w);
-                    if (si == 0) {  // per-read sums, once per group: total weight and delta(read) (see fb_beam.cuh read_delta)
-                        uint32_t tsum = 0;
-#pragma unroll
-                        for (int k = 0; k < 16; ++k) tsum += w[k];
-                        total = tsum;
-#pragma unroll
-                        for (int k = 0; k < 16; ++k)
-                            if ((pr >> k) & 1u) {
-                                const uint32_t av = ((al >> k) & 1u) | (((al >> (16 + k)) & 1u) << 1);
-                                dl += fb_G((in.ag0 + lg) * 16u + k, av) * (unsigned long long)w[k];
-                            }
-                    }
-                    const uint2 m = ((int)lg <= hi) ? __ldcg(ST_MASK(s) + lg) : make_uint2(0u, 0u);
                     uint32_t sb, ne;
                     fb_group_masks(al, m, sb, ne);
                     same = fb_masked_sum(w, sb);
@@ -272,25 +331,25 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
                     const uint32_t db = pr & ne & ~sb & 0xFFFFu;
                     if (db) last_diff = (int)(lg * 16u) + 31 - __clz(db);
                 }
-                same = fb_warp_sum_u64(same);
-                emptyw = fb_warp_sum_u64(emptyw);
-                ne_cnt = fb_warp_sum_u32(ne_cnt);
-                last_diff = __reduce_max_sync(0xFFFFFFFFu, last_diff);
-                first_empty = __reduce_min_sync(0xFFFFFFFFu, first_empty);
-                if (si == 0) {
-                    total = fb_warp_sum_u64(total);
-                    dl = fb_warp_sum_u64(dl);
+                // warp sums of values below 2^30 as two 16-bit halves (each REDUX result fits 32 bits)
+                const unsigned long long same_w = (unsigned long long)__reduce_add_sync(0xFFFFFFFFu, same & 0xFFFFu) +
+                                                  ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, same >> 16) << 16);
+                ne_cnt = __reduce_add_sync(0xFFFFFFFFu, ne_cnt);
+                unsigned long long emptyw_w = 0;
+                if (ne_cnt) {
+                    emptyw_w = (unsigned long long)__reduce_add_sync(0xFFFFFFFFu, emptyw & 0xFFFFu) +
+                               ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, emptyw >> 16) << 16);
+                    first_empty = __reduce_min_sync(0xFFFFFFFFu, first_empty);
                 }
+                if (!bp.eps_safe) last_diff = __reduce_max_sync(0xFFFFFFFFu, last_diff);  // only the epsilon order needs it
                 if (lane == 0) {
-                    if (same) atomicAdd(&acc[s].same, same);
-                    if (emptyw) atomicAdd(&acc[s].emptyw, emptyw);
-                    if (ne_cnt) atomicAdd(&acc[s].ne_cnt, ne_cnt);
-                    if (last_diff >= 0) atomicMax(&acc[s].last_diff, last_diff);
-                    if (first_empty != INT_MAX) atomicMin(&acc[s].first_empty, first_empty);
-                    if (si == 0) {
-                        if (total) atomicAdd(&sacc->total, total);
-                        if (dl) atomicAdd(&sacc->delta, dl);
+                    if (same_w) atomicAdd(&acc[s].same, same_w);
+                    if (ne_cnt) {
+                        atomicAdd(&acc[s].ne_cnt, ne_cnt);
+                        if (emptyw_w) atomicAdd(&acc[s].emptyw, emptyw_w);
+                        atomicMin(&acc[s].first_empty, first_empty);
                     }
+                    if (!bp.eps_safe && last_diff >= 0) atomicMax(&acc[s].last_diff, last_diff);
                 }
             }
             // hash terms of the positions [prev_start, cur_start) that leave the window, my slice of every live state
@@ -298,14 +357,13 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
                 const uint32_t dA = (prev_start >> 4) / CH, dB = ((cur_start - 1) >> 4) / CH;
                 const uint32_t d0 = my_first_chunk(dA);
                 if (d0 <= dB) {
-                    for (int si = warp; si < n_live; si += NW) {
+                    for (int si = (int)warp - 1; si < n_live; si += NW - 1) {
                         const int s = live[si];
                         const uint32_t pend = min(cur_start, (uint32_t)(st_hi[s] + 1) * 16u);
                         unsigned long long sub = 0;
                         const unsigned long long *c = ST_CNT(s);
                         for (uint32_t ch = d0; ch <= dB; ch += G) {
-                            // the chunk's 32 positions x 4 alleles, lane = position
-                            const uint32_t pos = ch * CH * 16u + lane;
+                            const uint32_t pos = ch * CH * 16u + lane;  // the chunk's 32 positions, lane = position
                             if (pos >= prev_start && pos < pend) {
 #pragma unroll
                                 for (uint32_t a = 0; a < 4; ++a)
@@ -317,10 +375,13 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
                     }
                 }
             }
+            if (prof1) pa += clock64() - q0;
         }
-        PROF(0)
+        PROF(1)  // warp 0: the bookkeeping that follows the previous step's live list (overlaps phase A)
         fb_grid_barrier(bp.wbar, bar_target += G);
         PROF(3)
+        const int n_nodes = ms->n_nodes[gen];
+        const int n_live = ms->n_live;
 
         // ---- phase B.1 (every CTA, redundantly): scores and p-values of all live states ------------------------------------
         {
@@ -378,35 +439,32 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
                     ms->n_replay = 0;
                     ms->full_reads = 1;
                 }
-                // (the write is ordered before every later read of full_reads by the named barrier / __syncthreads below)
             }
         }
         PROF(4)
 
-        // ---- phase B.2 (warp 0 of every CTA, redundantly): the decision section; the other warps wait for the job list ----
+        // ---- phase B.2 / C ---------------------------------------------------------------------------------------------------
+        // warp 0 of every CTA runs the decision section (redundantly, identical inputs); the other warps stage the next
+        // read, wait for the job list (named barrier 1), materialise this CTA's slices of the new states, wait for the
+        // next step's live list (named barrier 2) and go straight into the next step's phase A.
+        // Steps that read whole states (replay / exact comparison: full_reads, same value in every CTA) must not
+        // overlap another CTA's in-place update of the same step: all CTAs meet at a second grid barrier first.
         if (warp != 0) {
+            long long q0 = 0;
+            if (prof1) q0 = clock64();
+            if (step + 1 < in.n_reads) stage_read(ri_next, (step + 1) % 3u);
+            if (prof1) {
+                const long long n_ = clock64();
+                pc += n_ - q0;
+                q0 = n_;
+            }
             asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
-        } else {
-#define FB_BEAM_POOL_LD(p) __ldcg(p)
-#define FB_BEAM_WRITER writer
-#define FB_BEAM_VERIFIED(x) \
-    if (lane == 0) ms->full_reads = 1
-#define FB_BEAM_ARRIVE() asm volatile("bar.arrive 1, %0;" ::"n"(NT) : "memory")
-#include "fb_beam_decide.inc"
-#undef FB_BEAM_POOL_LD
-#undef FB_BEAM_WRITER
-#undef FB_BEAM_VERIFIED
-#undef FB_BEAM_ARRIVE
-        }
-        PROF(1)
-        // Steps that read whole states must not overlap another CTA's in-place update of the same step.  full_reads is
-        // written before the job list is published (bar 1) and cleared only after the closing __syncthreads of the
-        // step, and it has the same value in every CTA (the decision section is deterministic).
-        const bool extra = ms->full_reads != 0;
-        if (extra) fb_grid_barrier(bp.wbar, bar_target += G);
-
-        // ---- phase C (all warps but 0, which finishes the bookkeeping in the include above): my slices of the new states ----
-        if (warp != 0) {
+            if (ms->full_reads) fb_grid_barrier(bp.wbar, bar_target += G);
+            if (prof1) {
+                const long long n_ = clock64();
+                pw += n_ - q0;
+                q0 = n_;
+            }
             const int nj_copy = ms->n_jobs_copy, nj_inpl = ms->n_jobs_inplace;
             const int gs = (int)(cur_start >> 4);
             for (int pass = 0; pass < 2; ++pass) {
@@ -419,38 +477,53 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
                 const uint32_t c0 = my_first_chunk(cA);
                 const int nmc = c0 <= cB ? (int)((cB - c0) / G + 1) : 0;
                 const int total = nj * nmc;  // one warp pass per (job, chunk)
-                for (int x = (int)warp - 1; x < total; x += NW - 1) {
+                // two passes in flight per warp: the loads of both are issued before either is finished
+                struct CItem {
+                    uint32_t src, dst;
+                    int src_hi, lg;
+                    bool act, in_read;
+                    ulonglong2 v0, v1;
+                    uint32_t pr, al, qb;
+                };
+                const uint32_t k = lane & 15u;
+                auto c_load = [&](int x, CItem &it) {
                     const int jn = x / nmc, kc = x - jn * nmc;
                     const BeamJob jb = pass == 0 ? jobs[jn] : jobs[(int)Wm + 1 - jn];
-                    const int lg = (int)((c0 + (uint32_t)kc * G) * CH + (lane >> 4));
-                    const uint32_t k = lane & 15u;
-                    const bool act = lg >= glo && lg <= ghi;
+                    it.src = jb.src;
+                    it.dst = jb.dst;
+                    it.src_hi = jb.src_hi;
+                    it.lg = (int)((c0 + (uint32_t)kc * G) * CH + (lane >> 4));
+                    it.act = it.lg >= glo && it.lg <= ghi;
+                    it.in_read = it.act && it.lg >= (int)ri.lg0 && it.lg < (int)ri.lg1;
+                    it.v0 = make_ulonglong2(0ULL, 0ULL);
+                    it.v1 = it.v0;
+                    it.pr = it.al = it.qb = 0;
+                    if (it.act && it.lg <= it.src_hi) {
+                        const ulonglong2 *src =
+                            reinterpret_cast<const ulonglong2 *>(ST_CNT(it.src) + ((uint64_t)it.lg * 16 + k) * 4);
+                        it.v0 = __ldcg(src);
+                        it.v1 = __ldcg(src + 1);
+                    }
+                    if (it.in_read) {
+                        const uint32_t g = ri.gbase + (uint32_t)it.lg;
+                        it.pr = bp.fr.present[g];
+                        it.al = bp.fr.allele[g];
+                        it.qb = qual8[(uint64_t)g * 16 + k];
+                    }
+                };
+                auto c_finish = [&](const CItem &it) {
                     bool im0 = false, im1 = false, im2 = false, im3 = false;
-                    if (act) {
-                        const uint64_t pos = (uint64_t)lg * 16 + k;
-                        unsigned long long c0w = 0, c1w = 0, c2w = 0, c3w = 0;
-                        if (lg <= jb.src_hi) {
-                            const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(ST_CNT(jb.src) + pos * 4);
-                            const ulonglong2 v0 = __ldcg(src), v1 = __ldcg(src + 1);
-                            c0w = v0.x;
-                            c1w = v0.y;
-                            c2w = v1.x;
-                            c3w = v1.y;
+                    if (it.act) {
+                        unsigned long long c0w = it.v0.x, c1w = it.v0.y, c2w = it.v1.x, c3w = it.v1.y;
+                        if (it.in_read && ((it.pr >> k) & 1u)) {
+                            const uint32_t av = ((it.al >> k) & 1u) | (((it.al >> (16 + k)) & 1u) << 1);
+                            const unsigned long long w = lut_s[it.qb];
+                            if (av == 0) c0w = (c0w + w) | FB_PRESENT;
+                            if (av == 1) c1w = (c1w + w) | FB_PRESENT;
+                            if (av == 2) c2w = (c2w + w) | FB_PRESENT;
+                            if (av == 3) c3w = (c3w + w) | FB_PRESENT;
                         }
-                        if (lg >= (int)ri.lg0 && lg < (int)ri.lg1) {
-                            const uint32_t g = ri.gbase + (uint32_t)lg;
-                            const uint32_t pr = bp.fr.present[g], al = bp.fr.allele[g];
-                            const uint32_t qb = qual8[(uint64_t)g * 16 + k];
-                            if ((pr >> k) & 1u) {
-                                const uint32_t av = ((al >> k) & 1u) | (((al >> (16 + k)) & 1u) << 1);
-                                const unsigned long long w = lut_s[qb];
-                                if (av == 0) c0w = (c0w + w) | FB_PRESENT;
-                                if (av == 1) c1w = (c1w + w) | FB_PRESENT;
-                                if (av == 2) c2w = (c2w + w) | FB_PRESENT;
-                                if (av == 3) c3w = (c3w + w) | FB_PRESENT;
-                            }
-                        }
-                        ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(ST_CNT(jb.dst) + pos * 4);
+                        ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(ST_CNT(it.dst) + ((uint64_t)it.lg * 16 + k) * 4);
                         dst[0] = make_ulonglong2(c0w, c1w);
                         dst[1] = make_ulonglong2(c2w, c3w);
                         const unsigned long long m0 = c0w & FB_CNT_MASK, m1 = c1w & FB_CNT_MASK, m2 = c2w & FB_CNT_MASK,
@@ -470,18 +543,55 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
                     const uint32_t b1 = (__ballot_sync(0xFFFFFFFFu, im1) >> sh) & 0xFFFFu;
                     const uint32_t b2 = (__ballot_sync(0xFFFFFFFFu, im2) >> sh) & 0xFFFFu;
                     const uint32_t b3 = (__ballot_sync(0xFFFFFFFFu, im3) >> sh) & 0xFFFFu;
-                    if (act && k == 0) ST_MASK(jb.dst)[lg] = make_uint2(b0 | (b1 << 16), b2 | (b3 << 16));
+                    if (it.act && k == 0) ST_MASK(it.dst)[it.lg] = make_uint2(b0 | (b1 << 16), b2 | (b3 << 16));
+                };
+                for (int x = (int)warp - 1; x < total; x += 2 * (NW - 1)) {
+                    CItem ia, ib;
+                    c_load(x, ia);
+                    const bool two = x + (NW - 1) < total;  // warp-uniform
+                    if (two) c_load(x + (NW - 1), ib);
+                    c_finish(ia);
+                    if (two) c_finish(ib);
                 }
             }
+            if (prof1) {
+                const long long n_ = clock64();
+                pc += n_ - q0;
+                q0 = n_;
+            }
+            asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory");  // the next step's live list
+            if (prof1) pw += clock64() - q0;
+        } else {
+#define FB_BEAM_POOL_LD(p) __ldcg(p)
+#define FB_BEAM_WRITER writer
+#define FB_BEAM_VERIFIED(x) \
+    if (lane == 0) ms->full_reads = 1
+#define FB_BEAM_ARRIVE()                                              \
+    asm volatile("bar.arrive 1, %0;" ::"n"(NT) : "memory");           \
+    if (ms->full_reads) {                                             \
+        fb_grid_barrier(bp.wbar, bar_target += G);                    \
+        if (lane == 0) ms->full_reads = 0;                            \
+    }
+#define FB_BEAM_ARRIVE2() asm volatile("bar.arrive 2, %0;" ::"n"(NT) : "memory")
+#include "fb_beam_decide.inc"
+#undef FB_BEAM_POOL_LD
+#undef FB_BEAM_WRITER
+#undef FB_BEAM_VERIFIED
+#undef FB_BEAM_ARRIVE
+#undef FB_BEAM_ARRIVE2
         }
         cells += (unsigned long long)n_nodes * rx.nnz;
         tapn += (unsigned long long)n_nodes * P;
         gen ^= 1;
         prev_start = cur_start;
         gmax = gmax_new;
-        __syncthreads();
-        if (extra && tid == 0) ms->full_reads = 0;  // next read of it is after the next step's grid barrier
-        PROF(2)
+        // no closing barrier: the next step's grid barrier orders warp 0's bookkeeping before anything that reads it
+    }
+    __syncthreads();
+    if (prof1) {
+        atomicAdd(bp.prof + 0, (unsigned long long)pa);
+        atomicAdd(bp.prof + 2, (unsigned long long)pc);
+        atomicAdd(bp.prof + 20, (unsigned long long)pw);
     }
 
     // ---- global_clustering.rs:149-176: best = into_sorted_vec()[0]; walk the parent pointers (CTA 0, warp 0) ----------

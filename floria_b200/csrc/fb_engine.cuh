@@ -30,6 +30,8 @@ struct fb_ctx {
     int sm_count = 148;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
+    FbCache cache;           // device memory of this context (free list is per context: see fb_cache.cuh)
+    bool hist_attr = false;  // cudaFuncSetAttribute(k_hist) done on this context's device
 };
 
 struct fb_dfrags {
@@ -82,7 +84,7 @@ template <class T>
 static int fb_dalloc(fb_ctx *ctx, T **p, size_t n) {
     *p = nullptr;
     if (n == 0) n = 1;
-    FB_CK(FbCache::get().alloc((void **)p, n * sizeof(T)));
+    FB_CK(ctx->cache.alloc((void **)p, n * sizeof(T)));
     return FB_OK;
 }
 template <class T>
@@ -376,10 +378,9 @@ struct Engine {
             k_hist_zero<<<dim3(64, (unsigned)n), 256, 0, ctx->stream>>>(a);
             ctx->tim.n_launches++;
         }
-        static bool hist_attr = false;
-        if (!hist_attr) {
+        if (!ctx->hist_attr) {  // function attributes are per device
             FB_CK(cudaFuncSetAttribute(k_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_HIST_SMEM));
-            hist_attr = true;
+            ctx->hist_attr = true;
         }
         k_hist<<<(unsigned)ctas, FB_HIST_THREADS, FB_HIST_SMEM, ctx->stream>>>(a);
         cudaEvent_t e1 = fb_event(ctx);

@@ -83,7 +83,8 @@ void fb_destroy(fb_ctx *ctx) {
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     cudaFree(ctx->d_lut);
     cudaFree(ctx->d_n_active);
-    FbCache::get().trim(ctx->device);
+    ctx->cache.trim();
+    FbCacheRegistry::get().orphan(&ctx->cache);
     if (ctx->h_n_active) cudaFreeHost(ctx->h_n_active);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -602,6 +603,7 @@ int fb_phase_blocks_resident(fb_ctx *ctx, const fb_dfrags *df, uint64_t n_blocks
     r->mec_vector = (double *)calloc(n_blocks * mp + 1, sizeof(double));
     r->expected_errors = (double *)calloc(n_blocks * mp + 1, sizeof(double));
     r->read_ptr = (uint64_t *)calloc(n_blocks + 1, sizeof(uint64_t));
+    r->block_cells = (uint64_t *)calloc(n_blocks + 1, sizeof(uint64_t));
     uint64_t tot = 0;
     for (uint64_t j = 0; j < n_blocks; ++j) {
         r->read_ptr[j] = tot;
@@ -635,9 +637,12 @@ int fb_phase_blocks_resident(fb_ctx *ctx, const fb_dfrags *df, uint64_t n_blocks
                 num_alleles += bad;
             }
             expected[ploidy - 1] = num_alleles * epsilon;  // :196
-            r->cells_sweep += (uint64_t)s.n_opt_iterate * b.nnz;
-            r->cells_hist += (uint64_t)(s.n_hist + 1) * b.nnz;
-            r->cells_beam += ploidy == 1 ? b.nnz : br.cells_beam[ii];
+            const uint64_t cs = (uint64_t)s.n_opt_iterate * b.nnz, ch = (uint64_t)(s.n_hist + 1) * b.nnz;
+            const uint64_t cb = ploidy == 1 ? b.nnz : br.cells_beam[ii];
+            r->cells_sweep += cs;
+            r->cells_hist += ch;
+            r->cells_beam += cb;
+            r->block_cells[j] += cs + ch + cb;
             if (ploidy > 1) {
                 const double thr = fb_mec_threshold(ploidy, epsilon, prm->ploidy_sensitivity);
                 if ((mec_vector[ploidy - 1] / mec_vector[ploidy - 2]) < thr) {
@@ -781,6 +786,7 @@ void fb_free_block_results(fb_block_results *r) {
     free(r->read_ptr);
     free(r->read_ids);
     free(r->hap);
+    free(r->block_cells);
     free(r);
 }
 
@@ -1259,4 +1265,5 @@ int fb_update_hap_graph(fb_ctx *ctx, const fb_frags *fr, uint64_t n_cols, const 
 
 }  // extern "C"
 
+#include "fb_multi.cuh"
 #include "fb_bench.cuh"

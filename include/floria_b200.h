@@ -87,6 +87,7 @@ typedef struct {
     /* work counters: stored cells visited by scoring / histogram passes and beam steps,
        counted only for the ploidies the reference loop would evaluate */
     uint64_t cells_sweep, cells_hist, cells_beam;
+    uint64_t *block_cells;     /* [n_blocks] the three counters summed, per block (lets a batched call be split again) */
 } fb_block_results;
 
 /* Result of fb_process_reads_for_final_parts. */
@@ -114,6 +115,36 @@ void fb_params_default(fb_params *);
 int fb_last_timings(const fb_ctx *, fb_timings *out);
 /* stream the library launches on (a cudaStream_t), so callers can bracket it with their own events */
 void *fb_stream(const fb_ctx *);
+
+/* ---- several devices in one host process (fb_init(n_devices, device_ids)) ------------- */
+/* Contigs are independent units (src/bin/floria.rs:229 loops over them; graph_processing.rs:345-362 over their
+ * blocks), so a contig list is dealt to the devices by a static longest-processing-time-first queue and every device
+ * phases its share in ONE batched call (its contigs concatenated along the SNP axis), driven by one host thread per
+ * device.  The results come back to the caller's process in contig order: no collective is needed when one process
+ * owns all devices.  (One process per GPU, e.g. under torchrun: every rank opens fb_init_multi(1, {local_rank}),
+ * calls fb_lpt_assign to learn its share and gathers the partition records with NCCL, see floria_b200/shard.py.) */
+typedef struct fb_multi fb_multi;
+typedef struct fb_dcontigs fb_dcontigs; /* a contig list resident in the HBM of the devices that own its contigs */
+int fb_init_multi(int n_devices, const int *device_ids, fb_multi **out);
+void fb_destroy_multi(fb_multi *);
+int fb_multi_size(const fb_multi *);
+fb_ctx *fb_multi_ctx(fb_multi *, int i);
+const char *fb_multi_last_error(const fb_multi *);
+/* deterministic LPT: units by descending cost (ties by index) onto the least loaded bin (first minimum) */
+void fb_lpt_assign(const double *costs, uint64_t n_units, uint32_t n_bins, uint32_t *owner_out);
+/* blk_ptr [n_contigs+1] indexes blk_lo / blk_hi (1-based SNP ranges in each contig's own coordinates) */
+int fb_contigs_upload(fb_multi *, uint64_t n_contigs, const fb_frags *contigs, const uint64_t *blk_ptr,
+                      const uint32_t *blk_lo, const uint32_t *blk_hi, fb_dcontigs **out);
+void fb_contigs_free(fb_multi *, fb_dcontigs *);
+/* out [n_contigs]: one fb_block_results per contig (free each with fb_free_block_results), identical to what
+ * fb_phase_blocks returns for that contig alone (except that cells_beam carries the sum of the three work counters: a
+ * batched call only knows their per-block sum, block_cells); device_of [n_contigs] and device_ms [n_devices] (CUDA-event time of
+ * each device's batch) may be NULL */
+int fb_phase_contigs_resident(fb_multi *, const fb_dcontigs *, const fb_params *, fb_block_results **out,
+                              uint32_t *device_of, float *device_ms);
+int fb_phase_contigs(fb_multi *, uint64_t n_contigs, const fb_frags *contigs, const uint64_t *blk_ptr,
+                     const uint32_t *blk_lo, const uint32_t *blk_hi, const fb_params *, fb_block_results **out,
+                     uint32_t *device_of, float *device_ms);
 
 /* ---- data movement ------------------------------------------------------------------------- */
 /* Validates (sorted by Frag::cmp, allele <= 3, pos within [first,last]) and packs the CSR reads into

@@ -1410,6 +1410,7 @@ int orc_phase_blocks(const fb_frags *fr, uint64_t n_blocks, const uint32_t *blk_
     r->mec_vector = (double *)calloc(n_blocks * mp + 1, sizeof(double));
     r->expected_errors = (double *)calloc(n_blocks * mp + 1, sizeof(double));
     r->read_ptr = (uint64_t *)calloc(n_blocks + 1, sizeof(uint64_t));
+    r->block_cells = (uint64_t *)calloc(n_blocks + 1, sizeof(uint64_t));
     uint64_t tot = 0;
     for (uint64_t j = 0; j < n_blocks; ++j) {
         r->read_ptr[j] = tot;
@@ -1433,6 +1434,7 @@ int orc_phase_blocks(const fb_frags *fr, uint64_t n_blocks, const uint32_t *blk_
         r->cells_sweep += b.cells_sweep;
         r->cells_hist += b.cells_hist;
         r->cells_beam += b.cells_beam;
+        r->block_cells[j] = b.cells_sweep + b.cells_hist + b.cells_beam;
     }
     *out = r;
     return 0;
@@ -1447,6 +1449,7 @@ void orc_free_block_results(fb_block_results *r) {
     free(r->read_ptr);
     free(r->read_ids);
     free(r->hap);
+    free(r->block_cells);
     free(r);
 }
 
