@@ -126,6 +126,11 @@ def load_library():
                                       C.POINTER(C.c_float), C.POINTER(C.c_float), u64p]
     L.fb_bench_block_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, u8p, C.POINTER(FbParams), u64p, u64p, i64p,
                                         i64p, u32p]
+    L.fb_bench_export_csr.argtypes = [C.c_void_p, C.c_void_p, u64p, u32p, u32p, u32p, u8p, u8p]
+    L.fb_dfrags_nnz.restype = C.c_uint64
+    L.fb_dfrags_nnz.argtypes = [C.c_void_p]
+    L.fb_dfrags_n_reads.restype = C.c_uint64
+    L.fb_dfrags_n_reads.argtypes = [C.c_void_p]
     L.fb_bench_download_planes.argtypes = [C.c_void_p, C.c_void_p, u64p, u8p, u32p, C.POINTER(C.c_uint16)]
     _lib = L
     return L
@@ -350,6 +355,26 @@ class Context:
         d.src = src
         d.n_reads = n_reads
         return d
+
+    def bench_export_csr(self, dfrags, alloc=None):
+        """host CSR (a Frags) of a resident contig; alloc(nbytes) -> uint8 numpy array lets the caller supply pinned memory"""
+        from .frags import Frags
+
+        alloc = alloc or (lambda n: np.zeros(max(n, 1), np.uint8))
+        R = int(self.L.fb_dfrags_n_reads(dfrags.handle))
+        nnz = int(self.L.fb_dfrags_nnz(dfrags.handle))
+        row_ptr = alloc(8 * (R + 1))[: 8 * (R + 1)].view(np.uint64)
+        first = alloc(4 * R)[: 4 * R].view(np.uint32)
+        last = alloc(4 * R)[: 4 * R].view(np.uint32)
+        pos = alloc(4 * nnz)[: 4 * nnz].view(np.uint32)
+        allele = alloc(nnz)[:nnz]
+        qual = alloc(nnz)[:nnz]
+        self._chk(self.L.fb_bench_export_csr(self.h, dfrags.handle, ptr(row_ptr, u64p), ptr(first, u32p),
+                                             ptr(last, u32p), ptr(pos, u32p), ptr(allele, u8p), ptr(qual, u8p)))
+        f = Frags.__new__(Frags)
+        f.row_ptr, f.pos, f.allele, f.qual, f.first, f.last = row_ptr, pos, allele, qual, first, last
+        f.n_reads, f.nnz = R, nnz
+        return f
 
     def bench_sweep_hist(self, dfrags, ploidy, hap, params, iters):
         hap = np.ascontiguousarray(hap, np.uint8)

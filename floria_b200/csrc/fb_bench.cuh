@@ -199,6 +199,104 @@ int fb_bench_block_tables(fb_ctx *ctx, const fb_dfrags *df, uint32_t ploidy, con
     return rc;
 }
 
+// warp per read: the packed planes of a read back into CSR cells (ascending positions)
+__global__ void k_unpack_csr(DFragsDev fr, uint64_t r0, uint64_t r1, const uint64_t *__restrict__ row_ptr /*[r1-r0+1], relative*/,
+                             uint32_t *__restrict__ pos, uint8_t *__restrict__ allele, uint8_t *__restrict__ qual) {
+    const uint64_t r = r0 + (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= r1) return;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t g0 = fr.gptr[r], ng = fr.gnum[r], gs = fr.gstart[r];
+    uint64_t o = row_ptr[r - r0];
+    const uint8_t *q8 = reinterpret_cast<const uint8_t *>(fr.qual);
+    for (uint32_t b = 0; b < ng; b += 32) {
+        const uint32_t x = b + lane;
+        const uint32_t pr = x < ng ? fr.present[g0 + x] : 0u;
+        const uint32_t n = __popc(pr);
+        uint32_t pre = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, pre, d);
+            if ((int)lane >= d) pre += t;
+        }
+        const uint32_t tot = __shfl_sync(0xFFFFFFFFu, pre, 31);
+        if (n) {
+            const uint32_t al = fr.allele[g0 + x];
+            uint64_t w = o + pre - n;
+            for (uint32_t bits = pr; bits;) {
+                const int k = __ffs(bits) - 1;
+                bits &= bits - 1;
+                pos[w] = (gs + x) * 16u + (uint32_t)k + 1u;
+                allele[w] = (uint8_t)(((al >> k) & 1u) | (((al >> (16 + k)) & 1u) << 1));
+                qual[w] = q8[(uint64_t)(g0 + x) * 16 + k];
+                ++w;
+            }
+        }
+        o += tot;
+    }
+}
+
+// Host CSR of a resident contig (the form a floria host would hand to fb_phase_block / fb_phase_blocks): row_ptr
+// [n_reads+1], first / last [n_reads], pos / allele / qual [nnz]; the destination buffers may be pinned.  Used by bench.py
+// to obtain HOST buffers of the 100k x 50k block for the end-to-end leg without a minutes-long host-side generator.
+int fb_bench_export_csr(fb_ctx *ctx, const fb_dfrags *df, uint64_t *row_ptr, uint32_t *first, uint32_t *last,
+                        uint32_t *pos, uint8_t *allele, uint8_t *qual) {
+    if (!ctx) return FB_ERR_ARG;
+    if (!df || !row_ptr || !first || !last || !pos || !allele || !qual) FB_FAIL(FB_ERR_ARG, "null argument");
+    FB_CK(cudaSetDevice(ctx->device));
+    const uint64_t R = df->n_reads;
+    row_ptr[0] = 0;
+    for (uint64_t i = 0; i < R; ++i) {
+        row_ptr[i + 1] = row_ptr[i] + df->h_nnz[i];
+        first[i] = df->h_first[i];
+        last[i] = df->h_last[i];
+    }
+    const uint64_t chunk_cells = 256ull << 20;  // cells per device staging chunk (1.5 GB of temporaries)
+    uint64_t *d_row = nullptr;
+    uint32_t *d_pos = nullptr;
+    uint8_t *d_al = nullptr, *d_q = nullptr;
+    int rc = FB_OK;
+    auto cleanup = [&]() {
+        fb_cache_free(d_row);
+        fb_cache_free(d_pos);
+        fb_cache_free(d_al);
+        fb_cache_free(d_q);
+    };
+    std::vector<uint64_t> rel;
+    uint64_t cap_cells = 0, cap_rows = 0;
+    for (uint64_t r0 = 0; r0 < R;) {
+        uint64_t r1 = r0 + 1;
+        while (r1 < R && row_ptr[r1 + 1] - row_ptr[r0] <= chunk_cells) ++r1;
+        const uint64_t cells = row_ptr[r1] - row_ptr[r0], rows = r1 - r0;
+        if (cells > cap_cells || rows > cap_rows) {
+            cleanup();
+            cap_cells = std::max(cells, chunk_cells);
+            cap_rows = std::max<uint64_t>(rows, 1 << 16);
+            if ((rc = fb_dalloc(ctx, &d_row, cap_rows + 1)) || (rc = fb_dalloc(ctx, &d_pos, cap_cells)) ||
+                (rc = fb_dalloc(ctx, &d_al, cap_cells)) || (rc = fb_dalloc(ctx, &d_q, cap_cells))) {
+                cleanup();
+                return rc;
+            }
+        }
+        rel.resize(rows + 1);
+        for (uint64_t i = 0; i <= rows; ++i) rel[i] = row_ptr[r0 + i] - row_ptr[r0];
+        cudaMemcpyAsync(d_row, rel.data(), (rows + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
+        k_unpack_csr<<<(unsigned)((rows + 7) / 8), 256, 0, ctx->stream>>>(df->dev(), r0, r1, d_row, d_pos, d_al, d_q);
+        cudaMemcpyAsync(pos + row_ptr[r0], d_pos, cells * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(allele + row_ptr[r0], d_al, cells, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(qual + row_ptr[r0], d_q, cells, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+        if (ce == cudaSuccess) ce = cudaGetLastError();
+        if (ce != cudaSuccess) {
+            ctx->err = std::string("fb_bench_export_csr: ") + cudaGetErrorString(ce);
+            cleanup();
+            return FB_ERR_CUDA;
+        }
+        r0 = r1;
+    }
+    cleanup();
+    return FB_OK;
+}
+
 int fb_bench_download_planes(fb_ctx *ctx, const fb_dfrags *df, uint64_t *n_groups, uint8_t *qual, uint32_t *allele,
                              uint16_t *present) {
     if (!ctx) return FB_ERR_ARG;

@@ -255,6 +255,8 @@ void fb_frags_free(fb_ctx *ctx, fb_dfrags *df) {
 }
 
 uint64_t fb_dfrags_bytes(const fb_dfrags *df) { return df ? df->bytes : 0; }
+uint64_t fb_dfrags_nnz(const fb_dfrags *df) { return df ? df->nnz : 0; }
+uint64_t fb_dfrags_n_reads(const fb_dfrags *df) { return df ? df->n_reads : 0; }
 
 // ======================================================================================================================
 // host-side helpers

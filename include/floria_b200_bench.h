@@ -32,6 +32,14 @@ int fb_bench_sweep_hist(fb_ctx *, const fb_dfrags *df, uint32_t ploidy, const ui
 int fb_bench_block_tables(fb_ctx *, const fb_dfrags *df, uint32_t ploidy, const uint8_t *hap, const fb_params *,
                           uint64_t *n_pos, uint64_t *counts, int64_t *same_q26, int64_t *diff_q26, uint32_t *n_empty);
 
+/* The host CSR (fb_frags layout) of a resident contig: row_ptr [n_reads+1], first / last [n_reads], pos / allele / qual
+ * [nnz] (query nnz with fb_dfrags_nnz).  bench.py builds the HOST buffers of the end-to-end leg from the device-generated
+ * block this way. */
+int fb_bench_export_csr(fb_ctx *, const fb_dfrags *df, uint64_t *row_ptr, uint32_t *first, uint32_t *last, uint32_t *pos,
+                        uint8_t *allele, uint8_t *qual);
+uint64_t fb_dfrags_nnz(const fb_dfrags *);
+uint64_t fb_dfrags_n_reads(const fb_dfrags *);
+
 /* Debug/test: copy the packed planes of a resident contig back to the host (any pointer may be NULL). */
 int fb_bench_download_planes(fb_ctx *, const fb_dfrags *df, uint64_t *n_groups, uint8_t *qual /*[16*ng]*/,
                              uint32_t *allele /*[ng]*/, uint16_t *present /*[ng]*/);

@@ -11,6 +11,7 @@ import numpy as np
 
 from floria_b200._cdefs import (
     BlockResults,
+    FbBlockPhase,
     FbBlockResults,
     FbFrags,
     FbParams,
@@ -180,6 +181,23 @@ def optimize_clustering(frags, sel, hap_in, ploidy, params):
                                        C.c_uint32(ploidy), C.byref(params), ptr(hap, u8p), C.byref(score),
                                        C.byref(nr)))
     return hap, score.value, int(nr.value)
+
+
+def phase_block(frags, sel, ploidy, params):
+    """mirror of api.Context.phase_block: beam -> optimize -> no-phred MEC of one block at a fixed ploidy"""
+    if sel is None:
+        n, selp = frags.n_reads, None
+    else:
+        sel = _sel(sel)
+        n, selp = len(sel), ptr(sel, u32p)
+    hap = np.zeros(max(n, 1), np.uint8)
+    bases = np.zeros(ploidy)
+    errors = np.zeros(ploidy)
+    info = FbBlockPhase()
+    fs = frags.as_struct()
+    _chk(lib().orc_phase_block(C.byref(fs), C.c_uint64(n), selp, C.c_uint32(ploidy), C.byref(params), ptr(hap, u8p),
+                               ptr(bases, f64p), ptr(errors, f64p), C.byref(info)))
+    return hap[:n], bases, errors, {k: getattr(info, k) for k, _ in FbBlockPhase._fields_}
 
 
 def phase_blocks(frags, blk_lo, blk_hi, params, n_threads=1):

@@ -1379,6 +1379,61 @@ int orc_optimize_clustering(const fb_frags *fr, uint64_t n_sel, const uint32_t *
     return 0;
 }
 
+// graph_processing.rs:140-162 for one block at a fixed ploidy on an explicit read list (mirror of fb_phase_block):
+// beam_search_phasing -> optimize_clustering -> get_mec_stats_epsilon_no_phred, with the work counters of SURVEY.md 8d.
+int orc_phase_block(const fb_frags *fr, uint64_t n_sel, const uint32_t *sel, uint32_t ploidy, const fb_params *prm,
+                    uint8_t *hap_out, double *mec_bases, double *mec_errors, fb_block_phase *out) {
+    std::vector<Frag> frags;
+    if (!build_frags(fr, frags)) return 1;
+    WeightScope ws(prm);
+    std::vector<uint32_t> all;
+    if (!sel) {
+        n_sel = frags.size();
+        all.resize(n_sel);
+        for (uint64_t i = 0; i < n_sel; ++i) all[i] = (uint32_t)i;
+        sel = all.data();
+    }
+    std::vector<const Frag *> reads;
+    uint64_t nnz_block = 0;
+    for (uint64_t i = 0; i < n_sel; ++i) {
+        reads.push_back(&frags[sel[i]]);
+        nnz_block += frags[sel[i]].positions.size();
+    }
+    BeamCounters bc;
+    double best = 0.0;
+    auto bs = beam_search_phasing(std::vector<FragSet>(ploidy), reads, prm->epsilon, prm->div_factor,
+                                  prm->prob_cutoff_ln, prm->max_number_solns, &best, nullptr, &bc);
+    std::vector<FragSet> optimized_part;
+    OptCounters oc;
+    const double s = optimize_clustering(std::move(bs.second), prm->epsilon, prm->num_iter_optimize, &optimized_part,
+                                         nullptr, &oc);
+    auto binom_vec = get_mec_stats_epsilon_no_phred(optimized_part, prm->epsilon);
+    oc.n_hist++;
+    for (uint32_t h = 0; h < ploidy; ++h) {
+        if (mec_bases) mec_bases[h] = binom_vec[h].first;
+        if (mec_errors) mec_errors[h] = binom_vec[h].second;
+    }
+    if (hap_out) {
+        for (uint64_t i = 0; i < n_sel; ++i) hap_out[i] = 255;
+        for (size_t h = 0; h < optimized_part.size(); ++h)
+            for (const Frag *f : optimized_part[h]) {
+                const uint32_t *it = std::lower_bound(sel, sel + n_sel, (uint32_t)f->counter_id);
+                hap_out[it - sel] = (uint8_t)h;
+            }
+    }
+    if (out) {
+        memset(out, 0, sizeof(*out));
+        out->beam_score = ploidy > 1 ? best : 0.0;
+        out->opt_score = s;
+        out->n_rounds = (uint32_t)oc.n_accepted;
+        out->ploidy = ploidy;
+        out->cells_sweep = oc.n_opt_iterate * nnz_block;
+        out->cells_hist = oc.n_hist * nnz_block;
+        out->cells_beam = bc.cells_beam;
+    }
+    return 0;
+}
+
 int orc_phase_blocks(const fb_frags *fr, uint64_t n_blocks, const uint32_t *blk_lo, const uint32_t *blk_hi,
                      const fb_params *prm, uint32_t n_threads, fb_block_results **out) {
     std::vector<Frag> frags;

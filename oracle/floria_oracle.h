@@ -48,6 +48,9 @@ int orc_beam_search_phasing(const fb_frags *, uint64_t n_sel, const uint32_t *se
 int orc_optimize_clustering(const fb_frags *, uint64_t n_sel, const uint32_t *sel, const uint8_t *hap_in,
                             uint32_t ploidy, const fb_params *, uint8_t *hap_out, double *score,
                             uint32_t *n_rounds);
+/* mirror of fb_phase_block (sel == NULL: every read) */
+int orc_phase_block(const fb_frags *, uint64_t n_sel, const uint32_t *sel, uint32_t ploidy, const fb_params *,
+                    uint8_t *hap_out, double *mec_bases, double *mec_errors, fb_block_phase *out);
 /* n_threads workers over blocks, mirroring rayon's par_iter (graph_processing.rs:345-362). */
 int orc_phase_blocks(const fb_frags *, uint64_t n_blocks, const uint32_t *blk_lo, const uint32_t *blk_hi,
                      const fb_params *, uint32_t n_threads, fb_block_results **out);
