@@ -28,7 +28,7 @@ from ._cdefs import (
 )
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfloria_b200.so")
+LIB_PATH = os.environ.get("FB_LIB") or os.path.join(_HERE, "libfloria_b200.so")  # FB_LIB: A/B builds
 
 EXPORTS = [
     "fb_init", "fb_destroy", "fb_last_error", "fb_params_default", "fb_last_timings", "fb_stream",
