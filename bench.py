@@ -482,6 +482,8 @@ def run_ours(args):
     torch.set_num_threads(1)  # the hot path is on the GPU; N ranks share the host cores with their planning threads
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if not os.environ.get("FB_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL_DEBUG=VERSION/INFO prints to stdout: the line printed here must be the only one
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     sampler = ClockSampler(local_rank) if rank == 0 else None
