@@ -282,9 +282,11 @@ struct Engine {
         done_off.push_back(tot_done);
         tot_done += (uint64_t)tiles * ploidy;
         tile_counts.push_back((uint64_t)tiles * ploidy * splits);
+        // k_select packs a move as read | j << 24 | i << 28 and sorts over a power-of-two capacity held in 32 bits:
+        // blocks beyond 2^24 reads are refused by the callers (fb_limits_ok), so neither can overflow here
         uint64_t maxm = (uint64_t)in.n_reads * (ploidy > 1 ? ploidy - 1 : 1);
         uint32_t cap = 1;
-        while (cap < maxm) cap <<= 1;
+        while (cap < maxm && cap < (1u << 31)) cap <<= 1;
         moves_off.push_back(tot_moves);
         moves_cap.push_back(cap);
         tot_moves += cap;
@@ -299,6 +301,10 @@ struct Engine {
     std::vector<uint64_t> tile_counts;
 
     int finalize_and_upload(double eps_) {
+        {
+            std::string why;
+            if (!limits_ok(why)) FB_FAIL(FB_ERR_LIMIT, "%s", why.c_str());
+        }
         eps = eps_;
         eps_safe = fb_eps_is_safe(eps_);
         int n = (int)inst.size();
@@ -337,6 +343,20 @@ struct Engine {
     }
 
     int n_inst() const { return (int)inst.size(); }
+    // capacity limits of the instance kernels: k_select's 24-bit read index, 4-bit haplotype fields
+    bool limits_ok(std::string &why) const {
+        for (const InstDev &in : inst) {
+            if (in.n_reads >= (1u << 24)) {
+                why = "a block holds " + std::to_string(in.n_reads) + " reads; the move selection supports fewer than 2^24 per block";
+                return false;
+            }
+            if (in.ploidy > 15) {
+                why = "ploidy above 15";
+                return false;
+            }
+        }
+        return true;
+    }
 
     int launch_sizes(int which) {
         int n = n_inst();

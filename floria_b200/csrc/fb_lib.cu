@@ -497,8 +497,12 @@ int fb_beam_search_phasing(fb_ctx *ctx, const fb_frags *fr, uint64_t n_sel, cons
     double *d_ts = nullptr, *d_td = nullptr, *d_tp = nullptr;
     if (tap_cap) {
         if ((rc = fb_dalloc(ctx, &d_ts, tap_cap)) || (rc = fb_dalloc(ctx, &d_td, tap_cap)) ||
-            (rc = fb_dalloc(ctx, &d_tp, tap_cap)))
+            (rc = fb_dalloc(ctx, &d_tp, tap_cap))) {
+            fb_cache_free(d_ts);  // every early return releases what was allocated
+            fb_cache_free(d_td);
+            fb_cache_free(d_tp);
             return rc;
+        }
         tap.same = d_ts;
         tap.diff = d_td;
         tap.logp = d_tp;

@@ -234,7 +234,10 @@ int fb_process_reads_for_final_parts(fb_ctx *, const fb_frags *, uint64_t n_part
                                      const fb_params *, fb_parts **out);
 void fb_free_parts(fb_parts *);
 
-/* part_block_manip.rs:517-620 get_hapq. hapq/rel_err are [n_parts]. */
+/* part_block_manip.rs:517-620 get_hapq. hapq/rel_err are [n_parts].
+ * Order dependence (declared): get_errors_cov_from_frags compares every allele count with the RUNNING SUM of the
+ * position (utils_frags.rs:616-624), so at sites with three or more alleles `rel_err` / `avg_err` depend on the hash
+ * iteration order of the real binary; this library uses ascending allele order (HAPQ itself is not affected). */
 int fb_get_hapq(fb_ctx *, const fb_frags *, uint64_t n_parts, const uint64_t *part_ptr, const uint32_t *part_reads,
                 const uint32_t *range_lo, const uint32_t *range_hi, const uint64_t *snp_to_genome_pos,
                 uint64_t n_snps, const fb_params *, uint8_t *hapq, double *rel_err, double *avg_err);
