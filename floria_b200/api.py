@@ -39,7 +39,8 @@ EXPORTS = [
     "fb_contigs_upload", "fb_contigs_free", "fb_phase_contigs_resident", "fb_phase_contigs",
     "fb_score_reads", "fb_hap_block_from_partition", "fb_get_mec_stats_epsilon", "fb_beam_search_phasing",
     "fb_optimize_clustering", "fb_process_reads_for_final_parts", "fb_free_parts", "fb_get_hapq",
-    "fb_update_hap_graph",
+    "fb_update_hap_graph", "fb_process_reads_for_final_parts_resident", "fb_get_hapq_resident",
+    "fb_update_hap_graph_resident",
 ]
 
 _lib = None
@@ -102,6 +103,12 @@ def load_library():
                               C.POINTER(FbParams), u8p, f64p, f64p]
     L.fb_update_hap_graph.argtypes = [C.c_void_p, C.POINTER(FbFrags), C.c_uint64, u64p, u64p, u32p, u32p, u32p,
                                       C.POINTER(FbParams), f64p]
+    L.fb_process_reads_for_final_parts_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, u64p, u32p, u32p, u32p,
+                                                            C.POINTER(FbParams), C.POINTER(C.POINTER(FbParts))]
+    L.fb_get_hapq_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, u64p, u32p, u32p, u32p, u64p, C.c_uint64,
+                                       C.POINTER(FbParams), u8p, f64p, f64p]
+    L.fb_update_hap_graph_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, u64p, u64p, u32p, u32p, u32p,
+                                               C.POINTER(FbParams), f64p]
     # several devices in one process
     i32p = C.POINTER(C.c_int)
     L.fb_init_multi.argtypes = [C.c_int, i32p, C.POINTER(C.c_void_p)]
@@ -530,10 +537,15 @@ class Context:
         rl = np.ascontiguousarray(range_lo, np.uint32)
         rh = np.ascontiguousarray(range_hi, np.uint32)
         out = C.POINTER(FbParts)()
-        fs = frags.as_struct()
-        self._chk(self.L.fb_process_reads_for_final_parts(self.h, C.byref(fs), len(pp) - 1, ptr(pp, u64p),
-                                                          ptr(pr, u32p), ptr(rl, u32p), ptr(rh, u32p),
-                                                          C.byref(params), C.byref(out)))
+        if isinstance(frags, DeviceFrags):  # contig already resident in HBM
+            self._chk(self.L.fb_process_reads_for_final_parts_resident(self.h, frags.handle, len(pp) - 1, ptr(pp, u64p),
+                                                                       ptr(pr, u32p), ptr(rl, u32p), ptr(rh, u32p),
+                                                                       C.byref(params), C.byref(out)))
+        else:
+            fs = frags.as_struct()
+            self._chk(self.L.fb_process_reads_for_final_parts(self.h, C.byref(fs), len(pp) - 1, ptr(pp, u64p),
+                                                              ptr(pr, u32p), ptr(rl, u32p), ptr(rh, u32p),
+                                                              C.byref(params), C.byref(out)))
         res = Parts(out.contents)
         self.L.fb_free_parts(out)
         return res
@@ -548,10 +560,15 @@ class Context:
         hapq = np.zeros(max(n, 1), np.uint8)
         rel = np.zeros(max(n, 1))
         avg = C.c_double(0)
-        fs = frags.as_struct()
-        self._chk(self.L.fb_get_hapq(self.h, C.byref(fs), n, ptr(pp, u64p), ptr(pr, u32p), ptr(rl, u32p),
-                                     ptr(rh, u32p), ptr(g, u64p), len(g), C.byref(params), ptr(hapq, u8p),
-                                     ptr(rel, f64p), C.byref(avg)))
+        if isinstance(frags, DeviceFrags):
+            self._chk(self.L.fb_get_hapq_resident(self.h, frags.handle, n, ptr(pp, u64p), ptr(pr, u32p), ptr(rl, u32p),
+                                                  ptr(rh, u32p), ptr(g, u64p), len(g), C.byref(params), ptr(hapq, u8p),
+                                                  ptr(rel, f64p), C.byref(avg)))
+        else:
+            fs = frags.as_struct()
+            self._chk(self.L.fb_get_hapq(self.h, C.byref(fs), n, ptr(pp, u64p), ptr(pr, u32p), ptr(rl, u32p),
+                                         ptr(rh, u32p), ptr(g, u64p), len(g), C.byref(params), ptr(hapq, u8p),
+                                         ptr(rel, f64p), C.byref(avg)))
         return hapq[:n], rel[:n], avg.value
 
     def update_hap_graph(self, frags, col_ptr, node_ptr, node_reads, node_lo, node_hi, params):
@@ -563,8 +580,13 @@ class Context:
         n_cols = len(cp) - 1
         tot = sum(int(cp[i + 1] - cp[i]) * int(cp[i + 2] - cp[i + 1]) for i in range(n_cols - 1))
         out = np.zeros(max(tot, 1))
-        fs = frags.as_struct()
-        self._chk(self.L.fb_update_hap_graph(self.h, C.byref(fs), n_cols, ptr(cp, u64p), ptr(npt, u64p),
-                                             ptr(nr, u32p), ptr(nl, u32p), ptr(nh, u32p), C.byref(params),
-                                             ptr(out, f64p)))
+        if isinstance(frags, DeviceFrags):
+            self._chk(self.L.fb_update_hap_graph_resident(self.h, frags.handle, n_cols, ptr(cp, u64p), ptr(npt, u64p),
+                                                          ptr(nr, u32p), ptr(nl, u32p), ptr(nh, u32p), C.byref(params),
+                                                          ptr(out, f64p)))
+        else:
+            fs = frags.as_struct()
+            self._chk(self.L.fb_update_hap_graph(self.h, C.byref(fs), n_cols, ptr(cp, u64p), ptr(npt, u64p),
+                                                 ptr(nr, u32p), ptr(nl, u32p), ptr(nh, u32p), C.byref(params),
+                                                 ptr(out, f64p)))
         return out[:tot]

@@ -254,10 +254,10 @@ static int fb_run_beam(fb_ctx *ctx, Engine &e, const fb_params *prm, const BeamT
             fprintf(stderr,
                     "[k_beam prof] %.3f ms (both kernels), %d instances on %llu CTAs, %.0f steps; cycles/step: phase1(score) %.0f | warp0: lse %.0f "
                     "compact+fold+dups+classes %.0f heap %.0f nextgen %.0f | phase3(copy) %.0f | children/step %.1f survivors/step %.1f "
-                    "copyjobs/step %.2f inplace/step %.2f live states/step %.2f nodes/step %.2f | backtrack total %.0f\n",
+                    "copyjobs/step %.2f inplace/step %.2f live states/step %.2f nodes/step %.2f | uniform steps %.1f %% | backtrack total %.0f\n",
                     br.beam_ms, (int)order_n.size(), (unsigned long long)slots_n, steps, h[0] / steps, h[6] / steps, h[7] / steps,
                     h[8] / steps, h[1] / steps, h[2] / steps, h[10] / steps, h[11] / steps, h[13] / steps, h[14] / steps,
-                    h[15] / steps, h[9] / steps, (double)h[5]);
+                    h[15] / steps, h[9] / steps, 100.0 * h[21] / steps, (double)h[5]);
         }
         if (!order_w.empty()) {
             const unsigned long long *h = hh + 24;
@@ -267,10 +267,10 @@ static int fb_run_beam(fb_ctx *ctx, Engine &e, const fb_params *prm, const BeamT
                     "warp 0: bookkeeping after the live list %.0f | grid barrier %.0f | p-values %.0f | lse %.0f "
                     "compact+fold+dups+classes %.0f heap %.0f (jobs + live list: rest) || warp 1: phase A %.0f | stage next read + "
                     "phase C %.0f | waiting for warp 0 %.0f || children/step %.1f survivors/step %.1f copyjobs/step %.2f "
-                    "inplace/step %.2f live states/step %.2f nodes/step %.2f | backtrack total %.0f\n",
+                    "inplace/step %.2f live states/step %.2f nodes/step %.2f | uniform steps %.1f %% | backtrack total %.0f\n",
                     br.beam_ms, (int)order_w.size(), grid_w, steps, h[1] / steps, h[3] / steps, h[4] / steps, h[6] / steps,
                     h[7] / steps, h[8] / steps, h[0] / steps, h[2] / steps, h[20] / steps, h[10] / steps, h[11] / steps,
-                    h[13] / steps, h[14] / steps, h[15] / steps, h[9] / steps, (double)h[5]);
+                    h[13] / steps, h[14] / steps, h[15] / steps, h[9] / steps, 100.0 * h[21] / steps, (double)h[5]);
         }
     }
     cleanup();

@@ -222,35 +222,72 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
         c0 = my_first_chunk(cA);
         return c0 <= cB ? ((cB - c0) / G + 1) * CH : 0u;  // group slots of my chunks (the ends may fall outside the read)
     };
-    auto stage_read = [&](const RInfo &r, uint32_t slot_idx) {  // warps 1..NW-1
+    // The loads of a read's planes are ISSUED one step ahead, at the top of phase A (prefetch_issue: registers), so that
+    // their DRAM latency hides behind phase A, the grid barrier and the p-values; they are COMMITTED to the shared-memory
+    // staging buffer while warp 0 runs the decision section (prefetch_commit), where the per-read sums are formed too.
+    // (scalars and a macro rather than arrays captured by a lambda: the prefetched values must stay in registers, a trip
+    // through local memory would wait for the loads right where they are issued)
+    uint4 pf_q0 = make_uint4(~0u, ~0u, ~0u, ~0u), pf_q1 = pf_q0;
+    uint32_t pf_al0 = 0, pf_al1 = 0, pf_pr0 = 0, pf_pr1 = 0;
+#define FB_BW_PREFETCH_ONE(r_, gi_, q_, al_, pr_, c0_, nmg_)                          \
+    {                                                                                \
+        q_ = make_uint4(~0u, ~0u, ~0u, ~0u);                                         \
+        al_ = 0;                                                                     \
+        pr_ = 0;                                                                     \
+        if ((gi_) < (nmg_)) {                                                        \
+            const uint32_t lg_ = ((c0_) + ((gi_) / CH) * G) * CH + (gi_) % CH;       \
+            if (lg_ >= (r_).lg0 && lg_ < (r_).lg1) {                                 \
+                const uint32_t g_ = (r_).gbase + lg_;                                \
+                q_ = bp.fr.qual[g_];                                                 \
+                al_ = bp.fr.allele[g_];                                              \
+                pr_ = bp.fr.present[g_];                                             \
+            }                                                                        \
+        }                                                                            \
+    }
+#define FB_BW_PREFETCH_ISSUE(r_)                                                                        \
+    {                                                                                                   \
+        uint32_t c0_;                                                                                   \
+        const uint32_t nmg_ = min(my_groups(r_, c0_), STG);                                             \
+        FB_BW_PREFETCH_ONE(r_, (uint32_t)tid - 32u, pf_q0, pf_al0, pf_pr0, c0_, nmg_)                   \
+        FB_BW_PREFETCH_ONE(r_, (uint32_t)tid - 32u + (uint32_t)(NT - 32), pf_q1, pf_al1, pf_pr1, c0_, nmg_) \
+    }
+    auto prefetch_commit = [&](const RInfo &r, uint32_t slot_idx) {  // warps 1..NW-1
         uint32_t c0;
-        const uint32_t nmg = my_groups(r, c0);
-        // the planes of my groups -> shared memory (one thread per group) ...
-        for (uint32_t gi = (uint32_t)tid - 32; gi < min(nmg, STG); gi += NT - 32) {
-            const uint32_t lg = (c0 + (gi / CH) * G) * CH + gi % CH;
-            uint4 q = make_uint4(~0u, ~0u, ~0u, ~0u);
-            uint32_t al = 0, pr = 0;
-            if (lg >= r.lg0 && lg < r.lg1) {
-                const uint32_t g = r.gbase + lg;
-                q = bp.fr.qual[g];
-                al = bp.fr.allele[g];
-                pr = bp.fr.present[g];
+        const uint32_t nmg = my_groups(r, c0), nst = min(nmg, STG);
+        {
+            const uint32_t gi0 = (uint32_t)tid - 32, gi1 = gi0 + (uint32_t)(NT - 32);
+            if (gi0 < nst) {
+                rq[gi0] = pf_q0;
+                ral[gi0] = pf_al0;
+                rpr[gi0] = (uint16_t)pf_pr0;
             }
-            rq[gi] = q;
-            ral[gi] = al;
-            rpr[gi] = (uint16_t)pr;
+            if (gi1 < nst) {
+                rq[gi1] = pf_q1;
+                ral[gi1] = pf_al1;
+                rpr[gi1] = (uint16_t)pf_pr1;
+            }
         }
-        // ... and the per-read sums, one thread per cell (the position hash fb_G is the expensive part)
+        asm volatile("bar.sync 3, %0;" ::"n"(NT - 32) : "memory");  // warps 1..NW-1 only
+        // the per-read sums, one thread per cell (the position hash fb_G is the expensive part)
         unsigned long long total = 0, dl = 0;
+        const uint8_t *rq8 = reinterpret_cast<const uint8_t *>(rq);
         for (uint32_t x = (uint32_t)tid - 32; x < nmg * 16u; x += NT - 32) {
             const uint32_t gi = x >> 4, k = x & 15u;
             const uint32_t lg = (c0 + (gi / CH) * G) * CH + gi % CH;
             if (lg >= r.lg0 && lg < r.lg1) {
-                const uint32_t g = r.gbase + lg;
-                const uint32_t pr = bp.fr.present[g];
+                uint32_t pr, al, qb;
+                if (gi < nst) {
+                    pr = rpr[gi];
+                    al = ral[gi];
+                    qb = rq8[gi * 16 + k];
+                } else {  // beyond the staging capacity (reads of more than 256 x gridDim groups): straight from global memory
+                    const uint32_t g = r.gbase + lg;
+                    pr = bp.fr.present[g];
+                    al = bp.fr.allele[g];
+                    qb = qual8[(uint64_t)g * 16 + k];
+                }
                 if ((pr >> k) & 1u) {
-                    const uint32_t al = bp.fr.allele[g];
-                    const unsigned long long w = lut_s[qual8[(uint64_t)g * 16 + k]];
+                    const unsigned long long w = lut_s[qb];
                     const uint32_t av = ((al >> k) & 1u) | (((al >> (16 + k)) & 1u) << 1);
                     total += w;
                     dl += fb_G((in.ag0 + lg) * 16u + k, av) * w;
@@ -264,7 +301,10 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
             if (dl) atomicAdd(&bp.wstep[slot_idx].delta, dl);
         }
     };
-    if (warp != 0) stage_read(ri_next, 0);
+    if (warp != 0) {
+        FB_BW_PREFETCH_ISSUE(ri_next)
+        prefetch_commit(ri_next, 0);
+    }
     __syncthreads();
 
     for (uint32_t step = 0; step < in.n_reads; ++step) {
@@ -289,6 +329,7 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
             long long q0 = 0;
             if (prof1) q0 = clock64();
             const int n_live = ms->n_live;
+            if (step + 1 < in.n_reads) FB_BW_PREFETCH_ISSUE(ri_next)  // consumed in this step's phase B.2
             if (writer) zero_slot((step + 1) % 3u, 32, NT - 32);  // last read two steps ago, first written after this step's barrier
             uint32_t c0;
             const uint32_t nmg = my_groups(ri, c0);
@@ -452,7 +493,7 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
         if (warp != 0) {
             long long q0 = 0;
             if (prof1) q0 = clock64();
-            if (step + 1 < in.n_reads) stage_read(ri_next, (step + 1) % 3u);
+            if (step + 1 < in.n_reads) prefetch_commit(ri_next, (step + 1) % 3u);
             if (prof1) {
                 const long long n_ = clock64();
                 pc += n_ - q0;
@@ -638,6 +679,8 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
         }
     }
 #undef PROF
+#undef FB_BW_PREFETCH_ONE
+#undef FB_BW_PREFETCH_ISSUE
 #undef ST_CNT
 #undef ST_MASK
 #undef ND_SCORE

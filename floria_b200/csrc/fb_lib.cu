@@ -876,21 +876,21 @@ static void fb_separate_broken_haplogroups(const fb_dfrags *df, std::vector<std:
 
 extern "C" {
 
-int fb_process_reads_for_final_parts(fb_ctx *ctx, const fb_frags *fr, uint64_t n_parts, const uint64_t *part_ptr,
-                                     const uint32_t *part_reads, const uint32_t *range_lo, const uint32_t *range_hi,
-                                     const fb_params *prm, fb_parts **out) {
+int fb_process_reads_for_final_parts_resident(fb_ctx *ctx, const fb_dfrags *df, uint64_t n_parts,
+                                              const uint64_t *part_ptr, const uint32_t *part_reads,
+                                              const uint32_t *range_lo, const uint32_t *range_hi, const fb_params *prm,
+                                              fb_parts **out) {
     if (!ctx) return FB_ERR_ARG;
-    if (!fr || !out || (n_parts && (!part_ptr || !range_lo || !range_hi))) FB_FAIL(FB_ERR_ARG, "null argument");
+    if (!df || !out || (n_parts && (!part_ptr || !range_lo || !range_hi))) FB_FAIL(FB_ERR_ARG, "null argument");
     *out = nullptr;
     FB_CK(cudaSetDevice(ctx->device));
     ctx->ev_used = 0;
     int rc = fb_check_params(ctx, prm, 1);
     if (rc) return rc;
-    Single s;
-    s.ctx = ctx;
-    if ((rc = fb_frags_upload(ctx, fr, &s.df))) return rc;
-    s.own_df = true;
-    Engine &e = s.eng;
+    struct {
+        const fb_dfrags *df;
+    } s{df};
+    Engine e;
     e.ctx = ctx;
     e.df = s.df;
     std::vector<std::vector<uint32_t>> parts;
@@ -986,6 +986,18 @@ int fb_process_reads_for_final_parts(fb_ctx *ctx, const fb_frags *fr, uint64_t n
     return FB_OK;
 }
 
+int fb_process_reads_for_final_parts(fb_ctx *ctx, const fb_frags *fr, uint64_t n_parts, const uint64_t *part_ptr,
+                                     const uint32_t *part_reads, const uint32_t *range_lo, const uint32_t *range_hi,
+                                     const fb_params *prm, fb_parts **out) {
+    if (!ctx) return FB_ERR_ARG;
+    fb_dfrags *df = nullptr;
+    int rc = fb_frags_upload(ctx, fr, &df);
+    if (rc) return rc;
+    rc = fb_process_reads_for_final_parts_resident(ctx, df, n_parts, part_ptr, part_reads, range_lo, range_hi, prm, out);
+    fb_frags_free(ctx, df);
+    return rc;
+}
+
 void fb_free_parts(fb_parts *r) {
     if (!r) return;
     free(r->part_ptr);
@@ -999,7 +1011,21 @@ int fb_get_hapq(fb_ctx *ctx, const fb_frags *fr, uint64_t n_parts, const uint64_
                 const uint32_t *range_lo, const uint32_t *range_hi, const uint64_t *snp_to_genome_pos, uint64_t n_snps,
                 const fb_params *prm, uint8_t *hapq, double *rel_err, double *avg_err) {
     if (!ctx) return FB_ERR_ARG;
-    if (!fr || (n_parts && (!part_ptr || !range_lo || !range_hi || !hapq || !rel_err)) || !snp_to_genome_pos || !avg_err)
+    fb_dfrags *df = nullptr;
+    int rc = fb_frags_upload(ctx, fr, &df);
+    if (rc) return rc;
+    rc = fb_get_hapq_resident(ctx, df, n_parts, part_ptr, part_reads, range_lo, range_hi, snp_to_genome_pos, n_snps, prm, hapq,
+                              rel_err, avg_err);
+    fb_frags_free(ctx, df);
+    return rc;
+}
+
+int fb_get_hapq_resident(fb_ctx *ctx, const fb_dfrags *df, uint64_t n_parts, const uint64_t *part_ptr,
+                         const uint32_t *part_reads, const uint32_t *range_lo, const uint32_t *range_hi,
+                         const uint64_t *snp_to_genome_pos, uint64_t n_snps, const fb_params *prm, uint8_t *hapq,
+                         double *rel_err, double *avg_err) {
+    if (!ctx) return FB_ERR_ARG;
+    if (!df || (n_parts && (!part_ptr || !range_lo || !range_hi || !hapq || !rel_err)) || !snp_to_genome_pos || !avg_err)
         FB_FAIL(FB_ERR_ARG, "null argument");
     FB_CK(cudaSetDevice(ctx->device));
     ctx->ev_used = 0;
@@ -1008,11 +1034,10 @@ int fb_get_hapq(fb_ctx *ctx, const fb_frags *fr, uint64_t n_parts, const uint64_
     for (uint64_t i = 0; i < n_parts; ++i)
         if (range_lo[i] < 1 || range_hi[i] > n_snps || range_lo[i] > range_hi[i])
             FB_FAIL(FB_ERR_ARG, "part %llu: snp range outside snp_to_genome_pos", (unsigned long long)i);
-    Single s;
-    s.ctx = ctx;
-    if ((rc = fb_frags_upload(ctx, fr, &s.df))) return rc;
-    s.own_df = true;
-    Engine &e = s.eng;
+    struct {
+        const fb_dfrags *df;
+    } s{df};
+    Engine e;
     e.ctx = ctx;
     e.df = s.df;
     std::vector<std::vector<uint32_t>> parts;
@@ -1153,17 +1178,28 @@ int fb_update_hap_graph(fb_ctx *ctx, const fb_frags *fr, uint64_t n_cols, const 
                         const uint64_t *node_ptr, const uint32_t *node_reads, const uint32_t *node_lo,
                         const uint32_t *node_hi, const fb_params *prm, double *out_weights) {
     if (!ctx) return FB_ERR_ARG;
-    if (!fr || !col_ptr || !node_ptr || !node_lo || !node_hi || !out_weights) FB_FAIL(FB_ERR_ARG, "null argument");
+    fb_dfrags *df = nullptr;
+    int rc = fb_frags_upload(ctx, fr, &df);
+    if (rc) return rc;
+    rc = fb_update_hap_graph_resident(ctx, df, n_cols, col_ptr, node_ptr, node_reads, node_lo, node_hi, prm, out_weights);
+    fb_frags_free(ctx, df);
+    return rc;
+}
+
+int fb_update_hap_graph_resident(fb_ctx *ctx, const fb_dfrags *df, uint64_t n_cols, const uint64_t *col_ptr,
+                                 const uint64_t *node_ptr, const uint32_t *node_reads, const uint32_t *node_lo,
+                                 const uint32_t *node_hi, const fb_params *prm, double *out_weights) {
+    if (!ctx) return FB_ERR_ARG;
+    if (!df || !col_ptr || !node_ptr || !node_lo || !node_hi || !out_weights) FB_FAIL(FB_ERR_ARG, "null argument");
     FB_CK(cudaSetDevice(ctx->device));
     ctx->ev_used = 0;
     int rc = fb_check_params(ctx, prm, 1);
     if (rc) return rc;
     const uint64_t n_nodes = col_ptr[n_cols];
-    Single s;
-    s.ctx = ctx;
-    if ((rc = fb_frags_upload(ctx, fr, &s.df))) return rc;
-    s.own_df = true;
-    Engine &e = s.eng;
+    struct {
+        const fb_dfrags *df;
+    } s{df};
+    Engine e;
     e.ctx = ctx;
     e.df = s.df;
     std::vector<std::vector<uint32_t>> nodes;

@@ -233,6 +233,19 @@ int fb_process_reads_for_final_parts(fb_ctx *, const fb_frags *, uint64_t n_part
                                      const uint32_t *part_reads, const uint32_t *range_lo, const uint32_t *range_hi,
                                      const fb_params *, fb_parts **out);
 void fb_free_parts(fb_parts *);
+/* The three contig-level calls with the contig already resident in HBM (fb_frags_upload once per contig; a pipeline
+ * fb_phase_blocks_resident -> fb_update_hap_graph_resident -> fb_process_reads_for_final_parts_resident ->
+ * fb_get_hapq_resident packs the reads once instead of four times). */
+int fb_process_reads_for_final_parts_resident(fb_ctx *, const fb_dfrags *, uint64_t n_parts, const uint64_t *part_ptr,
+                                              const uint32_t *part_reads, const uint32_t *range_lo,
+                                              const uint32_t *range_hi, const fb_params *, fb_parts **out);
+int fb_get_hapq_resident(fb_ctx *, const fb_dfrags *, uint64_t n_parts, const uint64_t *part_ptr,
+                         const uint32_t *part_reads, const uint32_t *range_lo, const uint32_t *range_hi,
+                         const uint64_t *snp_to_genome_pos, uint64_t n_snps, const fb_params *, uint8_t *hapq,
+                         double *rel_err, double *avg_err);
+int fb_update_hap_graph_resident(fb_ctx *, const fb_dfrags *, uint64_t n_cols, const uint64_t *col_ptr,
+                                 const uint64_t *node_ptr, const uint32_t *node_reads, const uint32_t *node_lo,
+                                 const uint32_t *node_hi, const fb_params *, double *out_weights);
 
 /* part_block_manip.rs:517-620 get_hapq. hapq/rel_err are [n_parts].
  * Order dependence (declared): get_errors_cov_from_frags compares every allele count with the RUNNING SUM of the

@@ -91,3 +91,36 @@ def test_final_parts_random_overlapping_sets(ctx):
     gh, grel, gavg = ctx.get_hapq(c.frags, g.part_ptr, g.read_ids, g.range_lo, g.range_hi, c.snp_to_genome_pos, prm)
     assert np.array_equal(gh, oh)
     assert np.array_equal(grel.view(np.uint64), orel.view(np.uint64))
+
+
+def test_resident_contig_pipeline_packs_once(ctx):
+    """fb_frags_upload once, then phase_blocks_resident -> update_hap_graph_resident -> process_reads_for_final_parts_resident
+    -> get_hapq_resident on the same device-resident contig: identical to the host-buffer entry points"""
+    c = synth.make_contig(54, 400, 360, 3, span_mean=60)
+    prm = default_params(epsilon=0.04, max_ploidy=4, block_length=10000)
+    lo, hi = api.get_range_with_lengths(c.snp_to_genome_pos, 10000, 10000 // 3, 0.0005)
+    d = ctx.upload(c.frags)
+    r = ctx.phase_blocks_resident(d, lo, hi, prm)
+    h = ctx.phase_blocks(c.frags, lo, hi, prm)
+    assert np.array_equal(r.hap, h.hap) and np.array_equal(r.best_ploidy, h.best_ploidy)
+    ptr, reads, rlo, rhi, col_ptr, node_lo, node_hi = [0], [], [], [], [0], [], []
+    for j in range(r.n_blocks):
+        ids = r.read_ids[r.read_ptr[j]:r.read_ptr[j + 1]]
+        hp = r.hap[r.read_ptr[j]:r.read_ptr[j + 1]]
+        for k in range(int(r.best_ploidy[j])):
+            reads.extend(ids[hp == k].tolist())
+            ptr.append(len(reads))
+            rlo.append(int(lo[j]))
+            rhi.append(int(hi[j]))
+        col_ptr.append(len(ptr) - 1)
+    w_res = ctx.update_hap_graph(d, col_ptr, ptr, reads, rlo, rhi, prm)
+    w_host = ctx.update_hap_graph(c.frags, col_ptr, ptr, reads, rlo, rhi, prm)
+    assert np.array_equal(w_res, w_host)
+    p_res = ctx.process_reads_for_final_parts(d, ptr, reads, rlo, rhi, prm)
+    p_host = ctx.process_reads_for_final_parts(c.frags, ptr, reads, rlo, rhi, prm)
+    same_parts(p_res, p_host)
+    q_res = ctx.get_hapq(d, p_res.part_ptr, p_res.read_ids, p_res.range_lo, p_res.range_hi, c.snp_to_genome_pos, prm)
+    q_host = ctx.get_hapq(c.frags, p_host.part_ptr, p_host.read_ids, p_host.range_lo, p_host.range_hi, c.snp_to_genome_pos, prm)
+    assert np.array_equal(q_res[0], q_host[0]) and np.array_equal(q_res[1].view(np.uint64), q_host[1].view(np.uint64))
+    assert q_res[2] == q_host[2]
+    d.free()
