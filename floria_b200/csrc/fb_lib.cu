@@ -550,57 +550,18 @@ int fb_phase_blocks_resident(fb_ctx *ctx, const fb_dfrags *df, uint64_t n_blocks
     cudaEvent_t ev_start = fb_event(ctx);
     const bool hprof = getenv("FB_HOST_PROF") != nullptr;
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    double tp[8] = {now(), 0, 0, 0, 0, 0, 0, 0};
+    double tp[6] = {0, 0, 0, 0, 0, 0};  // plan | finalize+upload | beam | optimize | final hist/mec + download | stopping rule
+    double t_last = now();
+    auto lap = [&](int k) {
+        const double t = now();
+        tp[k] += t - t_last;
+        t_last = t;
+    };
 
-    Engine e;
-    e.ctx = ctx;
-    e.df = df;
-    std::vector<int> blk_index(n_blocks, -1);          // block j -> engine block
-    std::vector<int> first_inst(n_blocks, -1);         // block j -> its ploidy-1 instance
-    std::vector<uint32_t> reads;
-    for (uint64_t j = 0; j < n_blocks; ++j) {
-        fb_find_reads(df, blk_lo[j], blk_hi[j], reads);  // graph_processing.rs:121-126
-        if (reads.empty()) continue;                     // :129-131 -> None
-        int b = e.add_block(reads);
-        blk_index[j] = b;
-        for (uint32_t p = 1; p <= mp; ++p) {
-            int ii = e.add_instance(b, p);
-            if (p == 1) first_inst[j] = ii;
-        }
-    }
-    tp[1] = now();
-    if ((rc = e.finalize_and_upload(prm->epsilon))) return rc;
-    tp[2] = now();
+    // graph_processing.rs:121-131: the reads of every block; blocks without reads return None
+    std::vector<std::vector<uint32_t>> block_reads(n_blocks);
+    for (uint64_t j = 0; j < n_blocks; ++j) fb_find_reads(df, blk_lo[j], blk_hi[j], block_reads[j]);
 
-    // beam_search_phasing for every instance with ploidy > 1 (ploidy 1: every read lands in haplotype 0)
-    BeamRun br;
-    if ((rc = fb_run_beam(ctx, e, prm, nullptr, br))) return rc;
-    tp[3] = now();
-    // optimize_clustering
-    if ((rc = e.run_optimize(prm->num_iter_optimize))) return rc;
-    tp[4] = now();
-    // get_mec_stats_epsilon_no_phred on the optimized partition: unweighted histogram into the spare buffer
-    if ((rc = e.launch_hist(1, 0, 0, 0, 1))) return rc;
-    if ((rc = e.launch_mec(1, 0))) return rc;
-    cudaEvent_t ev_compute = fb_event(ctx);
-
-    const int n_inst = e.n_inst();
-    std::vector<InstState> st(n_inst);
-    std::vector<double> mec0(e.tot_mec * 2), mec1(e.tot_mec * 2);
-    std::vector<uint8_t> as0(e.tot_assign), as1(e.tot_assign);
-    if (n_inst) {
-        FB_CK(cudaMemcpyAsync(st.data(), e.d_st, sizeof(InstState) * n_inst, cudaMemcpyDeviceToHost, ctx->stream));
-        FB_CK(cudaMemcpyAsync(mec0.data(), e.d_mec[0], mec0.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        FB_CK(cudaMemcpyAsync(mec1.data(), e.d_mec[1], mec1.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        FB_CK(cudaMemcpyAsync(as0.data(), e.d_assign[0], as0.size(), cudaMemcpyDeviceToHost, ctx->stream));
-        FB_CK(cudaMemcpyAsync(as1.data(), e.d_assign[1], as1.size(), cudaMemcpyDeviceToHost, ctx->stream));
-    }
-    cudaEvent_t ev_end = fb_event(ctx);
-    FB_CK(cudaStreamSynchronize(ctx->stream));
-    FB_CK(cudaGetLastError());
-    tp[5] = now();
-
-    // ---- the ploidy loop and stopping rule of get_local_hap_blocks (graph_processing.rs:132-252), on the host -------------
     fb_block_results *r = (fb_block_results *)calloc(1, sizeof(fb_block_results));
     r->n_blocks = n_blocks;
     r->max_ploidy = mp;
@@ -613,82 +574,179 @@ int fb_phase_blocks_resident(fb_ctx *ctx, const fb_dfrags *df, uint64_t n_blocks
     uint64_t tot = 0;
     for (uint64_t j = 0; j < n_blocks; ++j) {
         r->read_ptr[j] = tot;
-        if (blk_index[j] >= 0) tot += e.blocks[blk_index[j]].reads.size();
+        tot += block_reads[j].size();
     }
     r->read_ptr[n_blocks] = tot;
     r->read_ids = (uint32_t *)calloc(tot + 1, sizeof(uint32_t));
     r->hap = (uint8_t *)calloc(tot + 1, 1);
+    for (uint64_t j = 0; j < n_blocks; ++j)
+        if (!block_reads[j].empty())
+            memcpy(r->read_ids + r->read_ptr[j], block_reads[j].data(), block_reads[j].size() * sizeof(uint32_t));
+    auto fail = [&](int code) {
+        fb_free_block_results(r);
+        return code;
+    };
+
+    // ---- the ploidy loop of get_local_hap_blocks (graph_processing.rs:132-252), in WAVES ----------------------------------
+    // The reference evaluates ploidy 1, 2, ... for a block until its stopping rule breaks the loop.  Running every ploidy of
+    // every block speculatively keeps the GPU full but wastes the ploidies beyond the break (on the mixed-ploidy metagenome of
+    // BASELINE.json configs[4]: 35 % of the beam-search and optimize work, and the highest ploidies are the expensive ones).
+    // The loop therefore advances in waves: the first wave carries ploidies 1..FB_PLOIDY_WAVE (default 3) of every block,
+    // every later wave ONE more ploidy of the blocks whose loop is still running; the stopping rule is applied between waves
+    // on the host.  Only the ploidies the reference would evaluate are counted in the work counters, as before.
+    const char *wenv = getenv("FB_PLOIDY_WAVE");
+    uint32_t wave0 = wenv ? (uint32_t)atoi(wenv) : 3u;
+    if (wave0 == 0 || wave0 > mp) wave0 = mp;  // 0: everything in one wave (round-1 behaviour)
     const double epsilon = prm->epsilon;
+    std::vector<uint8_t> running(n_blocks, 0);
+    std::vector<std::vector<uint8_t>> hap_prev(n_blocks);  // partition of the last evaluated ploidy (the break may fall back to it)
+    uint64_t n_running = 0;
+    for (uint64_t j = 0; j < n_blocks; ++j)
+        if (!block_reads[j].empty()) {
+            running[j] = 1;
+            ++n_running;
+        }
+    lap(0);
+    float download_ms = 0.f;
     uint64_t sweep_cells_all = 0, hist_cells_all = 0;
-    for (uint64_t j = 0; j < n_blocks; ++j) {
-        if (blk_index[j] < 0) continue;
-        const BlockPlan &b = e.blocks[blk_index[j]];
-        double *mec_vector = r->mec_vector + j * mp;
-        double *expected = r->expected_errors + j * mp;
-        uint32_t best_ploidy = 1;
-        for (uint32_t ploidy = 1; ploidy <= mp; ++ploidy) {
-            const int ii = first_inst[j] + (int)(ploidy - 1);
-            const InstDev &in = e.inst[ii];
-            const InstState &s = st[ii];
-            best_ploidy = ploidy;
-            r->ploidies_run[j] += 1;
-            // the no-phred stats were written to the buffer opposite to the accepted one
-            const std::vector<double> &mec = (s.cur ^ 1) == 0 ? mec0 : mec1;
-            double num_alleles = 0.0;
-            for (uint32_t h = 0; h < ploidy; ++h) {
-                const double good = mec[((uint64_t)in.mec_off + h) * 2 + 0];
-                const double bad = mec[((uint64_t)in.mec_off + h) * 2 + 1];
-                mec_vector[ploidy - 1] += bad;  // :159
-                num_alleles += good;
-                num_alleles += bad;
+    for (uint32_t p_lo = 1; p_lo <= mp && n_running; ) {
+        const uint32_t p_hi = p_lo == 1 ? wave0 : p_lo;  // inclusive
+        Engine e;
+        e.ctx = ctx;
+        e.df = df;
+        std::vector<int> first_inst(n_blocks, -1), blk_index(n_blocks, -1);
+        for (uint64_t j = 0; j < n_blocks; ++j) {
+            if (!running[j]) continue;
+            const int b = e.add_block(block_reads[j]);
+            blk_index[j] = b;
+            for (uint32_t p = p_lo; p <= p_hi; ++p) {
+                const int ii = e.add_instance(b, p);
+                if (p == p_lo) first_inst[j] = ii;
             }
-            expected[ploidy - 1] = num_alleles * epsilon;  // :196
-            const uint64_t cs = (uint64_t)s.n_opt_iterate * b.nnz, ch = (uint64_t)(s.n_hist + 1) * b.nnz;
-            const uint64_t cb = ploidy == 1 ? b.nnz : br.cells_beam[ii];
-            r->cells_sweep += cs;
-            r->cells_hist += ch;
-            r->cells_beam += cb;
-            r->block_cells[j] += cs + ch + cb;
-            if (ploidy > 1) {
-                const double thr = fb_mec_threshold(ploidy, epsilon, prm->ploidy_sensitivity);
-                if ((mec_vector[ploidy - 1] / mec_vector[ploidy - 2]) < thr) {
-                } else if (prm->stopping_heuristic) {
-                    best_ploidy -= 1;
-                    break;
+        }
+        lap(0);
+        if ((rc = e.finalize_and_upload(prm->epsilon))) return fail(rc);
+        lap(1);
+        // beam_search_phasing for every instance with ploidy > 1 (ploidy 1: every read lands in haplotype 0)
+        BeamRun br;
+        if ((rc = fb_run_beam(ctx, e, prm, nullptr, br))) return fail(rc);
+        lap(2);
+        if ((rc = e.run_optimize(prm->num_iter_optimize))) return fail(rc);
+        lap(3);
+        // get_mec_stats_epsilon_no_phred on the optimized partition: unweighted histogram into the spare buffer
+        if ((rc = e.launch_hist(1, 0, 0, 0, 1))) return fail(rc);
+        if ((rc = e.launch_mec(1, 0))) return fail(rc);
+        cudaEvent_t ev_compute = fb_event(ctx);
+        const int n_inst = e.n_inst();
+        std::vector<InstState> st(n_inst);
+        std::vector<double> mec0(e.tot_mec * 2), mec1(e.tot_mec * 2);
+        std::vector<uint8_t> as0(e.tot_assign), as1(e.tot_assign);
+        if (n_inst) {
+            cudaError_t ce = cudaMemcpyAsync(st.data(), e.d_st, sizeof(InstState) * n_inst, cudaMemcpyDeviceToHost, ctx->stream);
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(mec0.data(), e.d_mec[0], mec0.size() * 8, cudaMemcpyDeviceToHost, ctx->stream);
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(mec1.data(), e.d_mec[1], mec1.size() * 8, cudaMemcpyDeviceToHost, ctx->stream);
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(as0.data(), e.d_assign[0], as0.size(), cudaMemcpyDeviceToHost, ctx->stream);
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(as1.data(), e.d_assign[1], as1.size(), cudaMemcpyDeviceToHost, ctx->stream);
+            if (ce != cudaSuccess) {
+                ctx->err = std::string("fb_phase_blocks: ") + cudaGetErrorString(ce);
+                return fail(FB_ERR_CUDA);
+            }
+        }
+        cudaEvent_t ev_end = fb_event(ctx);
+        cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+        if (ce == cudaSuccess) ce = cudaGetLastError();
+        if (ce != cudaSuccess) {
+            ctx->err = std::string("fb_phase_blocks: ") + cudaGetErrorString(ce);
+            return fail(FB_ERR_CUDA);
+        }
+        lap(4);
+        {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev_compute, ev_end);
+            download_ms += ms;
+        }
+        // ---- the loop body and stopping rule for the ploidies of this wave (graph_processing.rs:132-252), on the host ----
+        for (uint64_t j = 0; j < n_blocks; ++j) {
+            if (!running[j]) continue;
+            const BlockPlan &b = e.blocks[blk_index[j]];
+            double *mec_vector = r->mec_vector + j * mp;
+            double *expected = r->expected_errors + j * mp;
+            const uint64_t o = r->read_ptr[j];
+            bool broke = false;
+            uint32_t best_ploidy = 0;
+            for (uint32_t ploidy = p_lo; ploidy <= p_hi; ++ploidy) {
+                const int ii = first_inst[j] + (int)(ploidy - p_lo);
+                const InstDev &in = e.inst[ii];
+                const InstState &s = st[ii];
+                best_ploidy = ploidy;
+                r->ploidies_run[j] += 1;
+                // the no-phred stats were written to the buffer opposite to the accepted one
+                const std::vector<double> &mec = (s.cur ^ 1) == 0 ? mec0 : mec1;
+                double num_alleles = 0.0;
+                for (uint32_t h = 0; h < ploidy; ++h) {
+                    const double good = mec[((uint64_t)in.mec_off + h) * 2 + 0];
+                    const double bad = mec[((uint64_t)in.mec_off + h) * 2 + 1];
+                    mec_vector[ploidy - 1] += bad;  // :159
+                    num_alleles += good;
+                    num_alleles += bad;
                 }
-                if (mec_vector[ploidy - 1] < expected[ploidy - 1]) break;
-            } else {
-                if (mec_vector[ploidy - 1] < expected[ploidy - 1]) break;
+                expected[ploidy - 1] = num_alleles * epsilon;  // :196
+                const uint64_t cs = (uint64_t)s.n_opt_iterate * b.nnz, ch = (uint64_t)(s.n_hist + 1) * b.nnz;
+                const uint64_t cb = ploidy == 1 ? b.nnz : br.cells_beam[ii];
+                r->cells_sweep += cs;
+                r->cells_hist += ch;
+                r->cells_beam += cb;
+                r->block_cells[j] += cs + ch + cb;
+                bool fall_back = false;
+                if (ploidy > 1) {
+                    const double thr = fb_mec_threshold(ploidy, epsilon, prm->ploidy_sensitivity);
+                    if ((mec_vector[ploidy - 1] / mec_vector[ploidy - 2]) < thr) {
+                    } else if (prm->stopping_heuristic) {
+                        best_ploidy -= 1;
+                        fall_back = true;
+                        broke = true;
+                    }
+                    if (!broke && mec_vector[ploidy - 1] < expected[ploidy - 1]) broke = true;
+                } else {
+                    if (mec_vector[ploidy - 1] < expected[ploidy - 1]) broke = true;
+                }
+                if (!fall_back) {  // this ploidy's partition is the current candidate
+                    const std::vector<uint8_t> &as = s.cur == 0 ? as0 : as1;
+                    hap_prev[j].assign(as.begin() + in.assign_off, as.begin() + in.assign_off + b.reads.size());
+                }
+                if (broke) break;
+            }
+            if (broke || p_hi == mp) {  // loop finished: `best_ploidy` and its partition (hap_prev holds it in both cases)
+                r->best_ploidy[j] = best_ploidy;
+                if (!hap_prev[j].empty()) memcpy(r->hap + o, hap_prev[j].data(), hap_prev[j].size());
+                running[j] = 0;
+                --n_running;
+                std::vector<uint8_t>().swap(hap_prev[j]);
             }
         }
-        r->best_ploidy[j] = best_ploidy;
-        const int ib = first_inst[j] + (int)(best_ploidy - 1);
-        const std::vector<uint8_t> &as = st[ib].cur == 0 ? as0 : as1;
-        const uint64_t o = r->read_ptr[j];
-        for (size_t k = 0; k < b.reads.size(); ++k) {
-            r->read_ids[o + k] = b.reads[k];
-            r->hap[o + k] = as[e.inst[ib].assign_off + k];
+        for (int ii = 0; ii < n_inst; ++ii) {
+            const uint64_t nnz = e.blocks[e.inst[ii].block].nnz;
+            sweep_cells_all += (uint64_t)st[ii].n_opt_iterate * nnz;
+            hist_cells_all += (uint64_t)(st[ii].n_hist + 1) * nnz;
         }
-    }
-    for (int ii = 0; ii < n_inst; ++ii) {
-        const uint64_t nnz = e.blocks[e.inst[ii].block].nnz;
-        sweep_cells_all += (uint64_t)st[ii].n_opt_iterate * nnz;
-        hist_cells_all += (uint64_t)(st[ii].n_hist + 1) * nnz;
+        e.collect_timings();
+        ctx->tim.beam_ms += br.beam_ms;
+        lap(5);
+        p_lo = p_hi + 1;
     }
     ctx->tim.sweep_cells += sweep_cells_all;
     ctx->tim.hist_cells += hist_cells_all;
-    e.collect_timings();
+    cudaEvent_t ev_done = fb_event(ctx);
+    FB_CK(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
-    cudaEventElapsedTime(&ms, ev_start, ev_compute);
-    ctx->tim.total_ms += ms;
-    cudaEventElapsedTime(&ms, ev_compute, ev_end);
-    ctx->tim.download_ms += ms;
-    ctx->tim.beam_ms += br.beam_ms;
+    cudaEventElapsedTime(&ms, ev_start, ev_done);
+    ctx->tim.total_ms += ms - download_ms;
+    ctx->tim.download_ms += download_ms;
     *out = r;
     if (hprof)
         fprintf(stderr, "[fb_phase_blocks_resident host ms] plan %.2f | finalize+upload %.2f | beam (launch..sync) %.2f | optimize %.2f | "
                         "final hist/mec + download %.2f | stopping rule + results %.2f\n",
-                tp[1] - tp[0], tp[2] - tp[1], tp[3] - tp[2], tp[4] - tp[3], tp[5] - tp[4], now() - tp[5]);
+                tp[0], tp[1], tp[2], tp[3], tp[4], tp[5]);
     return FB_OK;
 }
 

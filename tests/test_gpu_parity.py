@@ -346,3 +346,22 @@ def test_encode_linearity_property_at_scale(ctx):
         w_empty = tot - (sq[:, h] + dq[:, h]) * 2.0 ** -26
         assert np.all(w_empty >= 0)
         assert np.all((ne[:, h] == 0) <= (w_empty == 0))
+
+
+@pytest.mark.parametrize("wave", [0, 1, 2, 3])
+def test_phase_blocks_ploidy_waves_match_oracle(ctx, monkeypatch, wave):
+    """the ploidy loop advances in waves on the device (first wave: ploidies 1..FB_PLOIDY_WAVE, then one ploidy per wave for
+    the blocks whose stopping rule has not fired); every schedule must give the oracle's result, counters included"""
+    monkeypatch.setenv("FB_PLOIDY_WAVE", str(wave))
+    for seed, truth, mp in ((71, 2, 5), (72, 4, 6), (73, 1, 4)):
+        c = synth.make_contig(seed, 320, 280, truth, span_mean=70)
+        prm = default_params(epsilon=0.04, max_ploidy=mp)
+        lo, hi = api.get_range_with_lengths(c.snp_to_genome_pos, 6000, 2000, 0.0005)
+        g = ctx.phase_blocks(c.frags, lo, hi, prm)
+        o = oracle.phase_blocks(c.frags, lo, hi, prm, n_threads=4)
+        _compare_block_results(g, o)
+        assert len(set(g.ploidies_run.tolist())) > 1 or mp <= 2, "the inputs should stop at different ploidies"
+    prm = default_params(epsilon=0.04, max_ploidy=5, stopping_heuristic=0)
+    c = synth.make_contig(74, 200, 200, 2, span_mean=60)
+    lo, hi = api.get_range_with_lengths(c.snp_to_genome_pos, 6000, 2000, 0.0005)
+    _compare_block_results(ctx.phase_blocks(c.frags, lo, hi, prm), oracle.phase_blocks(c.frags, lo, hi, prm, n_threads=4))
