@@ -6,6 +6,7 @@
 #include "fb_beam_wide.cuh"
 #include "fb_engine.cuh"
 #include <stdlib.h>
+#include <chrono>
 
 struct BeamRun {
     std::vector<unsigned long long> cells_beam, tap_n;
@@ -27,7 +28,8 @@ static void fb_beam_split(const fb_ctx *ctx, const Engine &e, std::vector<int> &
         const InstDev &in = e.inst[i];
         if (in.ploidy < 2 || in.n_reads == 0) continue;  // ploidy 1: every read lands in haplotype 0
         uint64_t g = 0;
-        for (uint32_t r = 0; r < in.n_reads; ++r) g += e.rinfo[in.read_off + r].lg1 - e.rinfo[in.read_off + r].lg0;
+        const std::vector<RInfo> &hr = e.host_rinfo();
+        for (uint32_t r = 0; r < in.n_reads; ++r) g += hr[in.read_off + r].lg1 - hr[in.read_off + r].lg0;
         const double g_mean = (double)g / in.n_reads;
         if (forced == 1 || (forced != 0 && g_mean >= 192.0)) {
             cand.push_back(i);
@@ -50,6 +52,10 @@ static void fb_beam_split(const fb_ctx *ctx, const Engine &e, std::vector<int> &
 }
 
 static int fb_run_beam(fb_ctx *ctx, Engine &e, const fb_params *prm, const BeamTapDev *tap, BeamRun &br) {
+    const bool hprof = getenv("FB_HOST_PROF") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_enter = now();
+    double t_split = 0, t_alloc = 0;
     const int n_inst = e.n_inst();
     br.cells_beam.assign(n_inst, 0);
     br.tap_n.assign(n_inst, 0);
@@ -60,6 +66,7 @@ static int fb_run_beam(fb_ctx *ctx, Engine &e, const fb_params *prm, const BeamT
     fb_beam_split(ctx, e, order_n, order_w);
     br.n_narrow = (int)order_n.size();
     br.n_wide = (int)order_w.size();
+    t_split = now();
     if (order_n.empty() && order_w.empty()) return FB_OK;
 
     unsigned long long *d_cells = nullptr, *d_tapn = nullptr, *d_prof = nullptr;
@@ -92,10 +99,16 @@ static int fb_run_beam(fb_ctx *ctx, Engine &e, const fb_params *prm, const BeamT
         }
         cudaMemsetAsync(d_prof, 0, 48 * 8, ctx->stream);
     }
-    size_t free_b = 0, total_b = 0;
-    FB_CK(cudaMemGetInfo(&free_b, &total_b));
+    // memory budget of the scratch slots: what was free when the context was opened minus what this context holds now
+    // (cudaMemGetInfo itself costs 1-50 ms per call on a context with many allocations: measured, profiles/README.md)
+    size_t free_b = ctx->mem_free_at_init > ctx->cache.live_bytes ? ctx->mem_free_at_init - ctx->cache.live_bytes : 0;
+    if (free_b == 0) {
+        size_t total_b = 0;
+        FB_CK(cudaMemGetInfo(&free_b, &total_b));
+    }
     const uint64_t budget = (uint64_t)(free_b * 0.85);
 
+    t_alloc = now();
     cudaEvent_t e0 = fb_event(ctx);
     cudaError_t launch_err = cudaSuccess;
     uint64_t slots_n = 0;
@@ -243,6 +256,9 @@ static int fb_run_beam(fb_ctx *ctx, Engine &e, const fb_params *prm, const BeamT
         return FB_ERR_CUDA;
     }
     cudaEventElapsedTime(&br.beam_ms, e0, e1);
+    if (hprof)
+        fprintf(stderr, "[fb_run_beam host ms] split %.2f | result buffers %.2f | scratch + launch + sync %.2f (kernels %.2f)\n",
+                t_split - t_enter, t_alloc - t_split, now() - t_alloc, br.beam_ms);
     if (prof) {
         unsigned long long hh[48];
         cudaMemcpy(hh, d_prof, 48 * 8, cudaMemcpyDeviceToHost);

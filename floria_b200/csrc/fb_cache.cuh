@@ -33,6 +33,8 @@ struct FbCacheRegistry {
 
 struct FbCache {
     std::mutex mu;
+    size_t live_bytes = 0;  // handed out and not yet released (cudaMemGetInfo costs tens of ms on a busy context: callers
+                            // budget against the device total minus this figure instead)
     std::multimap<size_t, void *> free_blocks;
     cudaError_t alloc(void **p, size_t bytes) {
         if (bytes == 0) bytes = 1;
@@ -44,6 +46,7 @@ struct FbCache {
                 *p = it->second;
                 const size_t sz = it->first;
                 free_blocks.erase(it);
+                live_bytes += sz;
                 std::lock_guard<std::mutex> g2(FbCacheRegistry::get().mu);
                 FbCacheRegistry::get().live[*p] = std::make_pair(this, sz);
                 return cudaSuccess;
@@ -55,6 +58,10 @@ struct FbCache {
             cudaGetLastError();
             e = cudaMalloc(p, bytes);
             if (e != cudaSuccess) return e;
+        }
+        {
+            std::lock_guard<std::mutex> g(mu);
+            live_bytes += bytes;
         }
         std::lock_guard<std::mutex> g2(FbCacheRegistry::get().mu);
         FbCacheRegistry::get().live[*p] = std::make_pair(this, bytes);
@@ -88,4 +95,5 @@ static inline void fb_cache_free(void *p) {
     }
     std::lock_guard<std::mutex> g(owner->mu);
     owner->free_blocks.insert(std::make_pair(sz, p));
+    owner->live_bytes -= sz < owner->live_bytes ? sz : owner->live_bytes;
 }

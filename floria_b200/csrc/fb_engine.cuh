@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/floria_b200.h"
@@ -28,6 +29,7 @@ struct fb_ctx {
     int *d_n_active = nullptr;
     int *h_n_active = nullptr;  // pinned
     int sm_count = 148;
+    size_t mem_free_at_init = 0;  // cudaMemGetInfo at fb_init (free bytes of the device when the context was opened)
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     FbCache cache;           // device memory of this context (free list is per context: see fb_cache.cuh)
@@ -129,14 +131,69 @@ static void fb_find_reads(const fb_dfrags *df, uint32_t start, uint32_t end, std
 
 // ---- the batched plan -------------------------------------------------------------------------------------------------
 struct BlockPlan {
-    std::vector<uint32_t> reads;  // counter_ids ascending
+    std::vector<uint32_t> reads;  // counter_ids ascending (may be left empty when the caller keeps the list: n_reads counts)
+    uint32_t n_reads = 0;
     uint32_t ag0 = 0, ng = 0;
     uint64_t nnz = 0;
     uint32_t read_off = 0;
 };
 
+// a block planned once (read selection, extents, per-read descriptors) and appended to the engine of every ploidy wave
+struct PlannedBlock {
+    BlockPlan plan;
+    std::vector<RInfo> ri;
+    std::vector<RExtra> rx;
+};
+static void fb_plan_block(const fb_dfrags *df, std::vector<uint32_t> &&reads, PlannedBlock &pb) {
+    BlockPlan &b = pb.plan;
+    b.reads = std::move(reads);
+    b.n_reads = (uint32_t)b.reads.size();
+    b.nnz = 0;
+    uint32_t gmin = 0xFFFFFFFFu, gmax = 0;
+    for (uint32_t r : b.reads) {
+        uint32_t g0 = df->h_gstart[r];
+        uint32_t g1 = g0 + df->h_gnum[r];
+        gmin = std::min(gmin, g0);
+        gmax = std::max(gmax, g1);
+        b.nnz += df->h_nnz[r];
+    }
+    if (b.reads.empty()) {
+        gmin = 0;
+        gmax = 0;
+    }
+    b.ag0 = gmin;
+    b.ng = gmax - gmin;
+    b.read_off = 0;
+    pb.ri.resize(b.reads.size());
+    pb.rx.resize(b.reads.size());
+    for (size_t k = 0; k < b.reads.size(); ++k) {
+        const uint32_t r = b.reads[k];
+        RInfo &ri = pb.ri[k];
+        ri.rid = r;
+        ri.lg0 = df->h_gstart[r] - gmin;
+        ri.lg1 = ri.lg0 + df->h_gnum[r];
+        ri.gbase = df->h_gptr[r] - ri.lg0;
+        pb.rx[k].first0 = (df->h_first[r] - 1u) - gmin * 16u;
+        pb.rx[k].nnz = df->h_nnz[r];
+    }
+}
+
+// per-read descriptors of a whole contig's blocks, built and uploaded once and shared by the engines of all ploidy waves
+struct SharedReads {
+    std::vector<RInfo> rinfo;
+    std::vector<RExtra> rextra;
+    RInfo *d_rinfo = nullptr;
+    RExtra *d_rextra = nullptr;
+    ~SharedReads() {
+        fb_cache_free(d_rinfo);
+        fb_cache_free(d_rextra);
+    }
+};
+
 struct Engine {
     fb_ctx *ctx = nullptr;
+    const SharedReads *shared = nullptr;  // when set: blocks reference its descriptors (add_shared) and nothing is copied
+    const std::vector<RInfo> &host_rinfo() const { return shared ? shared->rinfo : rinfo; }
     const fb_dfrags *df = nullptr;
     std::vector<BlockPlan> blocks;
     std::vector<InstDev> inst;
@@ -184,11 +241,11 @@ struct Engine {
         d_mec_chunks = nullptr;
         fb_cache_free(d_moves_off);
         fb_cache_free(d_moves_cap);
-        fb_cache_free(d_rinfo);
+        if (!shared) fb_cache_free(d_rinfo);
         fb_cache_free(d_hist_splits);
         fb_cache_free(d_done_off);
         fb_cache_free(d_done);
-        fb_cache_free(d_rextra);
+        if (!shared) fb_cache_free(d_rextra);
         for (int b = 0; b < 2; ++b) {
             fb_cache_free(d_assign[b]);
             fb_cache_free(d_cnt[b]);
@@ -218,35 +275,26 @@ struct Engine {
 
     // add a block given its (ascending) read list; returns block index
     int add_block(const std::vector<uint32_t> &reads) {
+        PlannedBlock pb;
+        fb_plan_block(df, std::vector<uint32_t>(reads), pb);
+        return add_planned(pb);
+    }
+    // a block whose descriptors sit at `read_off` of the shared arrays (the read list stays with the caller)
+    int add_shared(const BlockPlan &plan, uint32_t read_off) {
         BlockPlan b;
-        b.reads = reads;
-        uint32_t gmin = 0xFFFFFFFFu, gmax = 0;
-        for (uint32_t r : reads) {
-            uint32_t g0 = df->h_gstart[r];
-            uint32_t g1 = g0 + df->h_gnum[r];
-            gmin = std::min(gmin, g0);
-            gmax = std::max(gmax, g1);
-            b.nnz += df->h_nnz[r];
-        }
-        if (reads.empty()) {
-            gmin = 0;
-            gmax = 0;
-        }
-        b.ag0 = gmin;
-        b.ng = gmax - gmin;
+        b.n_reads = plan.n_reads;
+        b.ag0 = plan.ag0;
+        b.ng = plan.ng;
+        b.nnz = plan.nnz;
+        b.read_off = read_off;
+        blocks.push_back(std::move(b));
+        return (int)blocks.size() - 1;
+    }
+    int add_planned(const PlannedBlock &pb) {
+        BlockPlan b = pb.plan;
         b.read_off = (uint32_t)rinfo.size();
-        for (uint32_t r : reads) {
-            RInfo ri;
-            ri.rid = r;
-            ri.lg0 = df->h_gstart[r] - gmin;
-            ri.lg1 = ri.lg0 + df->h_gnum[r];
-            ri.gbase = df->h_gptr[r] - ri.lg0;
-            rinfo.push_back(ri);
-            RExtra rx;
-            rx.first0 = (df->h_first[r] - 1u) - gmin * 16u;
-            rx.nnz = df->h_nnz[r];
-            rextra.push_back(rx);
-        }
+        rinfo.insert(rinfo.end(), pb.ri.begin(), pb.ri.end());
+        rextra.insert(rextra.end(), pb.rx.begin(), pb.rx.end());
         blocks.push_back(std::move(b));
         return (int)blocks.size() - 1;
     }
@@ -256,7 +304,7 @@ struct Engine {
         memset(&in, 0, sizeof(in));
         in.block = (uint32_t)block;
         in.ploidy = ploidy;
-        in.n_reads = (uint32_t)b.reads.size();
+        in.n_reads = b.n_reads;
         in.ng = b.ng;
         in.ag0 = b.ag0;
         in.read_off = b.read_off;
@@ -325,11 +373,17 @@ struct Engine {
         if ((rc = fb_dalloc(ctx, &d_mec_chunks, (size_t)std::max<uint64_t>(mec_chunk_prefix.back(), 1)))) return rc;
         if ((rc = fb_upload(ctx, &d_moves_off, moves_off))) return rc;
         if ((rc = fb_upload(ctx, &d_moves_cap, moves_cap))) return rc;
-        if ((rc = fb_upload(ctx, &d_rinfo, rinfo))) return rc;
+        if (shared)
+            d_rinfo = shared->d_rinfo;
+        else if ((rc = fb_upload(ctx, &d_rinfo, rinfo)))
+            return rc;
         if ((rc = fb_upload(ctx, &d_hist_splits, hist_splits))) return rc;
         if ((rc = fb_upload(ctx, &d_done_off, done_off))) return rc;
         if ((rc = fb_dalloc(ctx, &d_done, tot_done))) return rc;
-        if ((rc = fb_upload(ctx, &d_rextra, rextra))) return rc;
+        if (shared)
+            d_rextra = shared->d_rextra;
+        else if ((rc = fb_upload(ctx, &d_rextra, rextra)))
+            return rc;
         for (int b = 0; b < 2; ++b) {
             if ((rc = fb_dalloc(ctx, &d_assign[b], tot_assign))) return rc;
             if ((rc = fb_dalloc(ctx, &d_cnt[b], tot_cnt))) return rc;
@@ -473,8 +527,9 @@ struct Engine {
         // lanes per read: a whole warp for long reads, teams of 8 / 2 lanes when the reads span few 16-SNP groups
         if (sweep_team == 0) {
             uint64_t g = 0;
-            for (const RInfo &r : rinfo) g += r.lg1 - r.lg0;
-            const double avg = rinfo.empty() ? 32.0 : (double)g / (double)rinfo.size();
+            const std::vector<RInfo> &hr = host_rinfo();
+            for (const RInfo &r : hr) g += r.lg1 - r.lg0;
+            const double avg = hr.empty() ? 32.0 : (double)g / (double)hr.size();
             sweep_team = avg > 12.0 ? 32 : (avg > 2.5 ? 8 : 2);
             if (getenv("FB_SWEEP_TEAM")) sweep_team = atoi(getenv("FB_SWEEP_TEAM"));
         }

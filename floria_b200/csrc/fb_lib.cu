@@ -72,6 +72,10 @@ int fb_init(int device, fb_ctx **out) {
         return FB_ERR_CUDA;
     }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) ctx->mem_free_at_init = free_b;
+    }
     *out = ctx;
     return FB_OK;
 }
@@ -558,9 +562,51 @@ int fb_phase_blocks_resident(fb_ctx *ctx, const fb_dfrags *df, uint64_t n_blocks
         t_last = t;
     };
 
-    // graph_processing.rs:121-131: the reads of every block; blocks without reads return None
-    std::vector<std::vector<uint32_t>> block_reads(n_blocks);
-    for (uint64_t j = 0; j < n_blocks; ++j) fb_find_reads(df, blk_lo[j], blk_hi[j], block_reads[j]);
+    // graph_processing.rs:121-131: the reads of every block; blocks without reads return None.  Planned once (read
+    // selection, extents, per-read descriptors), by a few host threads, and appended to the engine of every ploidy wave.
+    std::vector<PlannedBlock> planned(n_blocks);
+    {
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const uint64_t nt = std::max<uint64_t>(1, std::min<uint64_t>(std::min<unsigned>(4u, hw), n_blocks / 256));
+        auto work = [&](uint64_t t) {
+            std::vector<uint32_t> reads;
+            for (uint64_t j = n_blocks * t / nt; j < n_blocks * (t + 1) / nt; ++j) {
+                fb_find_reads(df, blk_lo[j], blk_hi[j], reads);
+                fb_plan_block(df, std::move(reads), planned[j]);
+                reads = std::vector<uint32_t>();
+            }
+        };
+        std::vector<std::thread> th;
+        for (uint64_t t = 1; t < nt; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto &x : th) x.join();
+    }
+    auto block_reads = [&](uint64_t j) -> const std::vector<uint32_t> & { return planned[j].plan.reads; };
+    // the per-read descriptors of all blocks, concatenated and uploaded once
+    SharedReads shared;
+    std::vector<uint32_t> shared_off(n_blocks + 1, 0);
+    {
+        uint64_t tot_r = 0;
+        for (uint64_t j = 0; j < n_blocks; ++j) {
+            shared_off[j] = (uint32_t)tot_r;
+            tot_r += planned[j].ri.size();
+        }
+        if (tot_r >= (1ull << 32)) {
+            ctx->err = "more than 2^32 (block, read) pairs in one call";
+            return FB_ERR_LIMIT;
+        }
+        shared_off[n_blocks] = (uint32_t)tot_r;
+        shared.rinfo.resize(tot_r);
+        shared.rextra.resize(tot_r);
+        for (uint64_t j = 0; j < n_blocks; ++j) {
+            if (planned[j].ri.empty()) continue;
+            memcpy(shared.rinfo.data() + shared_off[j], planned[j].ri.data(), planned[j].ri.size() * sizeof(RInfo));
+            memcpy(shared.rextra.data() + shared_off[j], planned[j].rx.data(), planned[j].rx.size() * sizeof(RExtra));
+            std::vector<RInfo>().swap(planned[j].ri);
+            std::vector<RExtra>().swap(planned[j].rx);
+        }
+        if ((rc = fb_upload(ctx, &shared.d_rinfo, shared.rinfo)) || (rc = fb_upload(ctx, &shared.d_rextra, shared.rextra))) return rc;
+    }
 
     fb_block_results *r = (fb_block_results *)calloc(1, sizeof(fb_block_results));
     r->n_blocks = n_blocks;
@@ -574,14 +620,14 @@ int fb_phase_blocks_resident(fb_ctx *ctx, const fb_dfrags *df, uint64_t n_blocks
     uint64_t tot = 0;
     for (uint64_t j = 0; j < n_blocks; ++j) {
         r->read_ptr[j] = tot;
-        tot += block_reads[j].size();
+        tot += block_reads(j).size();
     }
     r->read_ptr[n_blocks] = tot;
     r->read_ids = (uint32_t *)calloc(tot + 1, sizeof(uint32_t));
     r->hap = (uint8_t *)calloc(tot + 1, 1);
     for (uint64_t j = 0; j < n_blocks; ++j)
-        if (!block_reads[j].empty())
-            memcpy(r->read_ids + r->read_ptr[j], block_reads[j].data(), block_reads[j].size() * sizeof(uint32_t));
+        if (!block_reads(j).empty())
+            memcpy(r->read_ids + r->read_ptr[j], block_reads(j).data(), block_reads(j).size() * sizeof(uint32_t));
     auto fail = [&](int code) {
         fb_free_block_results(r);
         return code;
@@ -602,7 +648,7 @@ int fb_phase_blocks_resident(fb_ctx *ctx, const fb_dfrags *df, uint64_t n_blocks
     std::vector<std::vector<uint8_t>> hap_prev(n_blocks);  // partition of the last evaluated ploidy (the break may fall back to it)
     uint64_t n_running = 0;
     for (uint64_t j = 0; j < n_blocks; ++j)
-        if (!block_reads[j].empty()) {
+        if (!block_reads(j).empty()) {
             running[j] = 1;
             ++n_running;
         }
@@ -614,10 +660,11 @@ int fb_phase_blocks_resident(fb_ctx *ctx, const fb_dfrags *df, uint64_t n_blocks
         Engine e;
         e.ctx = ctx;
         e.df = df;
+        e.shared = &shared;
         std::vector<int> first_inst(n_blocks, -1), blk_index(n_blocks, -1);
         for (uint64_t j = 0; j < n_blocks; ++j) {
             if (!running[j]) continue;
-            const int b = e.add_block(block_reads[j]);
+            const int b = e.add_shared(planned[j].plan, shared_off[j]);
             blk_index[j] = b;
             for (uint32_t p = p_lo; p <= p_hi; ++p) {
                 const int ii = e.add_instance(b, p);
@@ -712,7 +759,7 @@ int fb_phase_blocks_resident(fb_ctx *ctx, const fb_dfrags *df, uint64_t n_blocks
                 }
                 if (!fall_back) {  // this ploidy's partition is the current candidate
                     const std::vector<uint8_t> &as = s.cur == 0 ? as0 : as1;
-                    hap_prev[j].assign(as.begin() + in.assign_off, as.begin() + in.assign_off + b.reads.size());
+                    hap_prev[j].assign(as.begin() + in.assign_off, as.begin() + in.assign_off + b.n_reads);
                 }
                 if (broke) break;
             }
