@@ -480,10 +480,14 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.set_num_threads(1)  # the hot path is on the GPU; N ranks share the host cores with their planning threads
+    saved_stdout = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if not os.environ.get("FB_KEEP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL_DEBUG=VERSION/INFO prints to stdout: the line printed here must be the only one
+        # NCCL prints its version banner on stdout when the first communicator is created: everything but the JSON line goes
+        # to stderr (file descriptor 1 is pointed at 2 until the line is printed)
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -516,6 +520,8 @@ def run_ours(args):
                         clocks=clocks, e2e=s5["e2e"], cells_per_step=s5["cells_per_step"],
                         note="ONE fixed workload (configs[4], 500 contigs) sharded over the ranks; the 1-GPU value of "
                              "the same workload is shard500.value of the N=1 line")
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
             print(json.dumps(line), flush=True)
         dist.destroy_process_group()
 

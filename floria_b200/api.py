@@ -32,7 +32,7 @@ LIB_PATH = os.environ.get("FB_LIB") or os.path.join(_HERE, "libfloria_b200.so") 
 
 EXPORTS = [
     "fb_init", "fb_destroy", "fb_last_error", "fb_params_default", "fb_last_timings", "fb_stream",
-    "fb_frags_upload", "fb_frags_free", "fb_dfrags_bytes", "fb_get_range_with_lengths",
+    "fb_frags_upload", "fb_frags_upload_parts", "fb_frags_free", "fb_dfrags_bytes", "fb_get_range_with_lengths",
     "fb_find_reads_in_interval", "fb_phase_blocks", "fb_phase_blocks_resident", "fb_free_block_results",
     "fb_phase_block", "fb_phase_block_resident",
     "fb_init_multi", "fb_destroy_multi", "fb_multi_size", "fb_multi_ctx", "fb_multi_last_error", "fb_lpt_assign",

@@ -13,7 +13,8 @@ __global__ void k_pack(uint64_t nnz, uint64_t n_reads, const uint64_t *__restric
                        const uint32_t *__restrict__ gptr, const uint32_t *__restrict__ first,
                        const uint32_t *__restrict__ last, uint8_t *__restrict__ qual_out,
                        uint32_t *__restrict__ allele_out, uint32_t *__restrict__ present_out32,
-                       unsigned long long *__restrict__ err /* first bad cell + 1, 0 = none */) {
+                       unsigned long long *__restrict__ err /* first bad cell + 1, 0 = none */,
+                       const uint32_t *__restrict__ rshift /* per read: added to its positions (batched contigs), or NULL */) {
     uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nnz) return;
     // read of this cell: last r with row_ptr[r] <= c
@@ -25,12 +26,13 @@ __global__ void k_pack(uint64_t nnz, uint64_t n_reads, const uint64_t *__restric
         else
             hi = mid;
     }
-    const uint32_t p = pos[c];
+    const uint32_t sh = rshift ? rshift[lo] : 0u;
+    const uint32_t p = pos[c] + sh;
     const uint32_t a = allele[c];
     // per-cell validation (the per-read checks are done on the host): allele index fits 2 bits, positions strictly
     // ascending inside [first, last] with the end points present
     bool bad = a > 3 || p < first[lo] || p > last[lo];
-    if (c > row_ptr[lo] && pos[c - 1] >= p) bad = true;
+    if (c > row_ptr[lo] && pos[c - 1] + sh >= p) bad = true;
     if (c == row_ptr[lo] && p != first[lo]) bad = true;
     if (c + 1 == row_ptr[lo + 1] && p != last[lo]) bad = true;
     if (bad) {

@@ -124,50 +124,75 @@ void *fb_stream(const fb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr;
 // ======================================================================================================================
 // data movement
 // ======================================================================================================================
-int fb_frags_upload(fb_ctx *ctx, const fb_frags *fr, fb_dfrags **out) {
+// The packed planes of `n_parts` CSR fragment sets concatenated into one contig: the reads of part k follow those of part
+// k - 1 and their SNP positions are shifted by pos_shift[k] (batched contigs, fb_multi.cuh; one part with shift 0 is a plain
+// upload).  The cells go straight from the caller's buffers to the device (one copy per array and part) and are shifted by
+// k_pack: the host only touches per-read metadata.
+int fb_frags_upload_parts(fb_ctx *ctx, uint64_t n_parts, const fb_frags *parts, const uint32_t *pos_shift, fb_dfrags **out) {
     if (!ctx) return FB_ERR_ARG;
-    if (!fr || !out) FB_FAIL(FB_ERR_ARG, "null argument");
+    if (!parts || !out || n_parts == 0) FB_FAIL(FB_ERR_ARG, "null argument");
     *out = nullptr;
     FB_CK(cudaSetDevice(ctx->device));
-    const uint64_t R = fr->n_reads;
+    uint64_t R = 0, NNZ = 0;
+    for (uint64_t k = 0; k < n_parts; ++k) {
+        R += parts[k].n_reads;
+        NNZ += parts[k].nnz;
+    }
     if (R >= (1ull << 31)) FB_FAIL(FB_ERR_LIMIT, "too many reads");
     std::unique_ptr<fb_dfrags> df(new fb_dfrags());
     df->ctx = ctx;
     df->n_reads = R;
-    df->nnz = fr->nnz;
-    df->h_first.assign(fr->first, fr->first + R);
-    df->h_last.assign(fr->last, fr->last + R);
+    df->nnz = NNZ;
+    df->h_first.resize(R);
+    df->h_last.resize(R);
     df->h_nnz.resize(R);
     df->h_gstart.resize(R);
     df->h_gptr.resize(R + 1);
     df->h_gnum.resize(R);
     df->h_prefmax_last.resize(R);
-    uint64_t ng = 0;
-    uint32_t pm = 0;
-    if (R && fr->row_ptr[0] != 0) FB_FAIL(FB_ERR_ARG, "row_ptr[0] must be 0");
-    if (R && fr->row_ptr[R] != fr->nnz) FB_FAIL(FB_ERR_ARG, "row_ptr[n_reads] must equal nnz");
-    for (uint64_t i = 0; i < R; ++i) {
-        uint64_t a = fr->row_ptr[i], b = fr->row_ptr[i + 1];
-        if (b <= a) FB_FAIL(FB_ERR_ARG, "read %llu has no cells", (unsigned long long)i);
-        uint32_t f = fr->first[i], l = fr->last[i];
-        if (f < 1 || l < f) FB_FAIL(FB_ERR_ARG, "read %llu: bad first/last", (unsigned long long)i);
-        // per-cell checks (strictly ascending positions inside [first, last], allele <= 3) run in k_pack on the device
-        if (i > 0) {
-            // Frag::cmp (types_structs.rs:87-93): first asc, last desc, counter_id asc
-            uint32_t pf = fr->first[i - 1], pl = fr->last[i - 1];
-            if (f < pf || (f == pf && l > pl))
-                FB_FAIL(FB_ERR_ARG, "reads must be sorted by Frag::cmp (violated at read %llu)", (unsigned long long)i);
+    std::vector<uint64_t> row(R + 1);
+    std::vector<uint32_t> rshift(n_parts > 1 ? R : 0);
+    uint64_t ng = 0, r0 = 0, c0 = 0;
+    uint32_t pm = 0, pf = 0, pl = 0;
+    row[0] = 0;
+    for (uint64_t k = 0; k < n_parts; ++k) {
+        const fb_frags *fr = &parts[k];
+        const uint32_t sh = pos_shift ? pos_shift[k] : 0u;
+        const uint64_t Rk = fr->n_reads;
+        if (Rk && fr->row_ptr[0] != 0) FB_FAIL(FB_ERR_ARG, "row_ptr[0] must be 0");
+        if (Rk && fr->row_ptr[Rk] != fr->nnz) FB_FAIL(FB_ERR_ARG, "row_ptr[n_reads] must equal nnz");
+        for (uint64_t i = 0; i < Rk; ++i) {
+            const uint64_t a = fr->row_ptr[i], b = fr->row_ptr[i + 1];
+            if (b <= a) FB_FAIL(FB_ERR_ARG, "read %llu has no cells", (unsigned long long)(r0 + i));
+            if (fr->first[i] < 1 || fr->last[i] < fr->first[i] || fr->last[i] > 0xFFFFFFFFu - sh)
+                FB_FAIL(FB_ERR_ARG, "read %llu: bad first/last", (unsigned long long)(r0 + i));
+            const uint32_t f = fr->first[i] + sh, l = fr->last[i] + sh;
+            // per-cell checks (strictly ascending positions inside [first, last], allele <= 3) run in k_pack on the device
+            if (r0 + i > 0) {
+                // Frag::cmp (types_structs.rs:87-93): first asc, last desc, counter_id asc
+                if (f < pf || (f == pf && l > pl))
+                    FB_FAIL(FB_ERR_ARG, "reads must be sorted by Frag::cmp (violated at read %llu)", (unsigned long long)(r0 + i));
+            }
+            pf = f;
+            pl = l;
+            const uint64_t x = r0 + i;
+            df->h_first[x] = f;
+            df->h_last[x] = l;
+            df->h_nnz[x] = (uint32_t)(b - a);
+            row[x + 1] = c0 + b;
+            if (n_parts > 1) rshift[x] = sh;
+            const uint32_t g0 = (f - 1) >> 4, g1 = (l - 1) >> 4;
+            df->h_gstart[x] = g0;
+            ng = (ng + 7) & ~7ULL;  // every read starts on an 8-group boundary (16-byte aligned planes)
+            df->h_gptr[x] = (uint32_t)ng;
+            df->h_gnum[x] = g1 - g0 + 1;
+            ng += (uint64_t)(g1 - g0 + 1);
+            if (ng >= (1ull << 32) - 64) FB_FAIL(FB_ERR_LIMIT, "more than 2^32 groups");
+            pm = std::max(pm, l);
+            df->h_prefmax_last[x] = pm;
         }
-        df->h_nnz[i] = (uint32_t)(b - a);
-        uint32_t g0 = (f - 1) >> 4, g1 = (l - 1) >> 4;
-        df->h_gstart[i] = g0;
-        ng = (ng + 7) & ~7ULL;  // every read starts on an 8-group boundary (16-byte aligned planes)
-        df->h_gptr[i] = (uint32_t)ng;
-        df->h_gnum[i] = g1 - g0 + 1;
-        ng += (uint64_t)(g1 - g0 + 1);
-        if (ng >= (1ull << 32) - 64) FB_FAIL(FB_ERR_LIMIT, "more than 2^32 groups");
-        pm = std::max(pm, l);
-        df->h_prefmax_last[i] = pm;
+        r0 += Rk;
+        c0 += fr->nnz;
     }
     ng = (ng + 7) & ~7ULL;
     df->h_gptr[R] = (uint32_t)ng;
@@ -176,7 +201,7 @@ int fb_frags_upload(fb_ctx *ctx, const fb_frags *fr, fb_dfrags **out) {
     cudaEvent_t e0 = fb_event(ctx);
     // temporary CSR on the device
     uint64_t *d_row = nullptr;
-    uint32_t *d_pos = nullptr;
+    uint32_t *d_pos = nullptr, *d_rshift = nullptr;
     uint8_t *d_al = nullptr, *d_q = nullptr;
     unsigned long long *d_err = nullptr;
     unsigned long long h_err = 0;
@@ -186,9 +211,10 @@ int fb_frags_upload(fb_ctx *ctx, const fb_frags *fr, fb_dfrags **out) {
         fb_cache_free(d_pos);
         fb_cache_free(d_al);
         fb_cache_free(d_q);
+        fb_cache_free(d_rshift);
     };
-    if ((rc = fb_upload(ctx, &d_row, fr->row_ptr, R + 1)) || (rc = fb_upload(ctx, &d_pos, fr->pos, fr->nnz)) ||
-        (rc = fb_upload(ctx, &d_al, fr->allele, fr->nnz)) || (rc = fb_upload(ctx, &d_q, fr->qual, fr->nnz)) ||
+    if ((rc = fb_upload(ctx, &d_row, row)) || (rc = fb_dalloc(ctx, &d_pos, NNZ)) || (rc = fb_dalloc(ctx, &d_al, NNZ)) ||
+        (rc = fb_dalloc(ctx, &d_q, NNZ)) || (n_parts > 1 && (rc = fb_upload(ctx, &d_rshift, rshift))) ||
         (rc = fb_upload(ctx, &df->d_first, df->h_first)) || (rc = fb_upload(ctx, &df->d_last, df->h_last)) ||
         (rc = fb_upload(ctx, &df->d_nnz, df->h_nnz)) || (rc = fb_upload(ctx, &df->d_gstart, df->h_gstart)) ||
         (rc = fb_upload(ctx, &df->d_gptr, df->h_gptr)) || (rc = fb_upload(ctx, &df->d_gnum, df->h_gnum)) ||
@@ -199,16 +225,26 @@ int fb_frags_upload(fb_ctx *ctx, const fb_frags *fr, fb_dfrags **out) {
         fb_frags_free(ctx, df.release());
         return rc;
     }
+    c0 = 0;
+    for (uint64_t k = 0; k < n_parts; ++k) {
+        const fb_frags *fr = &parts[k];
+        if (fr->nnz) {
+            cudaMemcpyAsync(d_pos + c0, fr->pos, fr->nnz * 4, cudaMemcpyHostToDevice, ctx->stream);
+            cudaMemcpyAsync(d_al + c0, fr->allele, fr->nnz, cudaMemcpyHostToDevice, ctx->stream);
+            cudaMemcpyAsync(d_q + c0, fr->qual, fr->nnz, cudaMemcpyHostToDevice, ctx->stream);
+        }
+        c0 += fr->nnz;
+    }
     cudaEvent_t e1 = fb_event(ctx);
     // absent cells carry quality byte 0xFF (never read: masked by `present`), so a zero byte always is a real q = 0 cell
     cudaMemsetAsync(df->d_qual, 0xFF, (ng + 1) * sizeof(uint4), ctx->stream);
     cudaMemsetAsync(df->d_allele, 0, (ng + 1) * sizeof(uint32_t), ctx->stream);
     cudaMemsetAsync(df->d_present, 0, (ng + 2) * sizeof(uint16_t), ctx->stream);
     cudaMemsetAsync(d_err, 0xFF, sizeof(unsigned long long), ctx->stream);
-    if (fr->nnz) {
-        k_pack<<<(unsigned)((fr->nnz + 255) / 256), 256, 0, ctx->stream>>>(
-            fr->nnz, R, d_row, d_pos, d_al, d_q, df->d_gstart, df->d_gptr, df->d_first, df->d_last,
-            reinterpret_cast<uint8_t *>(df->d_qual), df->d_allele, reinterpret_cast<uint32_t *>(df->d_present), d_err);
+    if (NNZ) {
+        k_pack<<<(unsigned)((NNZ + 255) / 256), 256, 0, ctx->stream>>>(
+            NNZ, R, d_row, d_pos, d_al, d_q, df->d_gstart, df->d_gptr, df->d_first, df->d_last,
+            reinterpret_cast<uint8_t *>(df->d_qual), df->d_allele, reinterpret_cast<uint32_t *>(df->d_present), d_err, d_rshift);
         ctx->tim.n_launches++;
     }
     cudaMemcpyAsync(&h_err, d_err, sizeof(h_err), cudaMemcpyDeviceToHost, ctx->stream);
@@ -223,12 +259,14 @@ int fb_frags_upload(fb_ctx *ctx, const fb_frags *fr, fb_dfrags **out) {
     }
     if (h_err != ~0ULL) {
         const uint64_t c = h_err - 1;
-        uint64_t r = std::upper_bound(fr->row_ptr, fr->row_ptr + R + 1, c) - fr->row_ptr - 1;
+        const uint64_t r = std::upper_bound(row.begin(), row.end(), c) - row.begin() - 1;
+        uint64_t k = 0, cc = c;
+        while (k + 1 < n_parts && cc >= parts[k].nnz) cc -= parts[k++].nnz;
         char b_[256];
         snprintf(b_, sizeof(b_),
                  "read %llu: invalid cell (allele %u at position %u): alleles must be 0..3 and positions strictly "
                  "ascending with first/last_position their min/max",
-                 (unsigned long long)r, (unsigned)fr->allele[c], fr->pos[c]);
+                 (unsigned long long)r, (unsigned)parts[k].allele[cc], parts[k].pos[cc]);
         ctx->err = b_;
         fb_frags_free(ctx, df.release());
         return FB_ERR_ARG;
@@ -241,6 +279,12 @@ int fb_frags_upload(fb_ctx *ctx, const fb_frags *fr, fb_dfrags **out) {
     df->bytes = ng * 22;
     *out = df.release();
     return FB_OK;
+}
+
+int fb_frags_upload(fb_ctx *ctx, const fb_frags *fr, fb_dfrags **out) {
+    if (!ctx) return FB_ERR_ARG;
+    if (!fr || !out) FB_FAIL(FB_ERR_ARG, "null argument");
+    return fb_frags_upload_parts(ctx, 1, fr, nullptr, out);
 }
 
 void fb_frags_free(fb_ctx *ctx, fb_dfrags *df) {

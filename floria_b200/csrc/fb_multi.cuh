@@ -123,16 +123,11 @@ int fb_contigs_upload(fb_multi *m, uint64_t n_contigs, const fb_frags *contigs, 
         fb_ctx *ctx = m->ctx[d];
         const std::vector<uint64_t> &mem = dc->members[d];
         if (mem.empty()) return;
-        uint64_t R = 0, NNZ = 0;
-        for (uint64_t k : mem) {
-            R += contigs[k].n_reads;
-            NNZ += contigs[k].nnz;
-        }
-        std::vector<uint64_t> row_ptr(R + 1);
-        std::vector<uint32_t> first(R), last(R), pos(NNZ);
-        std::vector<uint8_t> allele(NNZ), qual(NNZ);
-        uint64_t r0 = 0, c0 = 0, p0 = 0;
-        row_ptr[0] = 0;
+        // positions of contig k are shifted past everything of the contigs before it; the cells themselves go from the
+        // caller's buffers straight to the device and are shifted there (fb_frags_upload_parts)
+        std::vector<fb_frags> parts;
+        std::vector<uint32_t> shift;
+        uint64_t r0 = 0, p0 = 0;
         for (uint64_t k : mem) {
             const fb_frags &f = contigs[k];
             FbContigSlot &sl = dc->slot[k];
@@ -141,25 +136,16 @@ int fb_contigs_upload(fb_multi *m, uint64_t n_contigs, const fb_frags *contigs, 
             sl.blk_off = dc->lo[d].size();
             sl.n_blocks = blk_ptr[k + 1] - blk_ptr[k];
             uint32_t span = 0;
-            for (uint64_t i = 0; i < f.n_reads; ++i) {
-                row_ptr[r0 + i + 1] = c0 + f.row_ptr[i + 1];
-                first[r0 + i] = f.first[i] + (uint32_t)p0;
-                last[r0 + i] = f.last[i] + (uint32_t)p0;
-                span = std::max(span, f.last[i]);
-            }
-            for (uint64_t c = 0; c < f.nnz; ++c) pos[c0 + c] = f.pos[c] + (uint32_t)p0;
-            if (f.nnz) {
-                memcpy(allele.data() + c0, f.allele, f.nnz);
-                memcpy(qual.data() + c0, f.qual, f.nnz);
-            }
+            for (uint64_t i = 0; i < f.n_reads; ++i) span = std::max(span, f.last[i]);
             for (uint64_t j = blk_ptr[k]; j < blk_ptr[k + 1]; ++j) {
                 dc->lo[d].push_back(blk_lo[j] + (uint32_t)p0);
                 dc->hi[d].push_back(blk_hi[j] + (uint32_t)p0);
                 span = std::max(span, blk_hi[j]);
             }
+            parts.push_back(f);
+            shift.push_back((uint32_t)p0);
             // the next contig starts on a fresh 16-position group beyond everything of this one
             p0 = (p0 + span + 64 + 15) & ~15ULL;
-            c0 += f.nnz;
             r0 += f.n_reads;
             if (p0 >= (1ULL << 32) - (1ULL << 20)) {
                 ctx->err = "batched contigs exceed the 32-bit SNP index space";
@@ -167,16 +153,7 @@ int fb_contigs_upload(fb_multi *m, uint64_t n_contigs, const fb_frags *contigs, 
                 return;
             }
         }
-        fb_frags merged;
-        merged.n_reads = R;
-        merged.nnz = NNZ;
-        merged.row_ptr = row_ptr.data();
-        merged.first = first.data();
-        merged.last = last.data();
-        merged.pos = pos.data();
-        merged.allele = allele.data();
-        merged.qual = qual.data();
-        rcs[d] = fb_frags_upload(ctx, &merged, &dc->df[d]);
+        rcs[d] = fb_frags_upload_parts(ctx, parts.size(), parts.data(), shift.data(), &dc->df[d]);
     };
     std::vector<std::thread> th;
     for (uint32_t d = 1; d < D; ++d) th.emplace_back(work, d);

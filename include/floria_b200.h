@@ -150,6 +150,11 @@ int fb_phase_contigs(fb_multi *, uint64_t n_contigs, const fb_frags *contigs, co
 /* Validates (sorted by Frag::cmp, allele <= 3, pos within [first,last]) and packs the CSR reads into
  * the HBM layout of DESIGN.md (2-bit allele planes, 8-bit quals, 1-bit presence, 16-position groups). */
 int fb_frags_upload(fb_ctx *, const fb_frags *, fb_dfrags **out);
+/* Several fragment sets as ONE resident contig: the reads of part k follow those of part k - 1 and their SNP positions
+ * are shifted by pos_shift[k] (the caller chooses shifts that keep the merged reads sorted, e.g. past the last position of
+ * the previous part).  The cells go from the caller's buffers straight to the device; this is how fb_contigs_upload batches
+ * the contigs of a device without a host-side merge. */
+int fb_frags_upload_parts(fb_ctx *, uint64_t n_parts, const fb_frags *parts, const uint32_t *pos_shift, fb_dfrags **out);
 void fb_frags_free(fb_ctx *, fb_dfrags *);
 uint64_t fb_dfrags_bytes(const fb_dfrags *); /* bytes of packed planes resident in HBM */
 
