@@ -75,6 +75,7 @@ struct BeamParams {
     struct BeamWideAcc *wacc;        // [3][maxNS] per-state partial sums of a step (three step slots)
     struct BeamWideStep *wstep;      // [3] per-read sums of a step
     unsigned long long *wbar;        // monotonic arrival counter of the grid barrier
+    const unsigned int *ready;       // pipelined upload: number of leading reads whose planes are packed (NULL: all)
 };
 
 // shared-memory carve-up (same arithmetic on host and device)

@@ -184,6 +184,8 @@ static int fb_run_beam(fb_ctx *ctx, Engine &e, const fb_params *prm, const BeamT
                 cleanup();
                 FB_FAIL(FB_ERR_LIMIT, "k_beam_wide does not fit an SM (%u bytes of shared memory)", L.total);
             }
+            // pipelined upload: leave SMs to the k_pack launches that run beside this kernel
+            if (e.df->pipelined) grid_w = std::max(1, grid_w - 32);
             if (getenv("FB_BEAM_WIDE_GRID")) grid_w = std::max(1, std::min(grid_w, atoi(getenv("FB_BEAM_WIDE_GRID"))));
         }
         uint8_t *d_scratch = nullptr;
@@ -235,13 +237,21 @@ static int fb_run_beam(fb_ctx *ctx, Engine &e, const fb_params *prm, const BeamT
         bp.wacc = d_wacc;
         bp.wstep = d_wstep;
         bp.wbar = d_wbar;
-        if (kind == 0)
+        if (kind == 0) {
+            // k_beam takes its reads in any order: it needs the whole contig
+            if (e.df->pipelined) cudaStreamWaitEvent(ctx->stream, e.df->ev_done, 0);
             launch_err = (cudaError_t)fb_beam_launch(nt, (unsigned)n_slots, L.total, ctx->stream, bp);
-        else
+        } else {
+            if (e.df->pipelined) {
+                bp.ready = e.df->d_ready;  // reads are consumed in order: start as soon as the first chunk is packed
+                cudaStreamWaitEvent(ctx->stream, e.df->ev_first, 0);
+            }
             launch_err = (cudaError_t)fb_beam_wide_launch((unsigned)grid_w, L.total, ctx->stream, bp);
+        }
         ctx->tim.n_launches++;
         ctx->tim.n_beam_launches++;
     }
+    if (e.df->pipelined) cudaStreamWaitEvent(ctx->stream, e.df->ev_done, 0);  // the rest of the call reads the whole contig
     cudaEvent_t e1 = fb_event(ctx);
     cudaError_t ce = launch_err;
     if (ce == cudaSuccess) {

@@ -42,16 +42,34 @@ __device__ __forceinline__ unsigned long long fb_ld_acquire_u64(const unsigned l
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+// Every spin of this kernel is bounded: a wait that outlasts FB_BW_SPIN_LIMIT polls (tens of seconds; a step takes
+// microseconds, an upload chunk milliseconds) can only be a lost producer, and the kernel traps (the launch fails with an
+// error) instead of hanging the device.
+#define FB_BW_SPIN_LIMIT (1ull << 25)
 // all threads of all CTAs; `target` = arrivals expected so far (monotonic counter, never reset during a launch)
 __device__ __forceinline__ void fb_grid_barrier(unsigned long long *ctr, unsigned long long target) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(ctr) : "memory");
-        while (fb_ld_acquire_u64(ctr) < target) {
-        }
+        unsigned long long spins = 0;
+        while (fb_ld_acquire_u64(ctr) < target)
+            if (++spins > FB_BW_SPIN_LIMIT) __trap();
     }
     __syncthreads();
+}
+// reads [0, n) of the contig are packed in HBM once *ready >= n (pipelined upload, fb_lib.cu): thread 0 of the CTA polls, the
+// CTA-wide barrier that follows every call site publishes the result to the other threads
+__device__ __forceinline__ void fb_wait_reads(const unsigned int *ready, unsigned int need, unsigned int &seen) {
+    if (ready == nullptr || seen >= need) return;
+    unsigned int v;
+    unsigned long long spins = 0;
+    for (;;) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ready) : "memory");
+        if (v >= need) break;
+        if (++spins > FB_BW_SPIN_LIMIT) __trap();
+    }
+    seen = v;
 }
 
 // stable_binom_cdf_p_rev (utils_frags.rs:211-248) with its two log terms on the two lanes of a pair (sub = 0 / 1); the
@@ -301,6 +319,13 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
             if (dl) atomicAdd(&bp.wstep[slot_idx].delta, dl);
         }
     };
+    // pipelined upload: the planes of read t are valid once *bp.ready > t.  Thread 0 waits (bounded) before the CTA touches
+    // a read; step t touches read t (phase C) and read t + 1 (prefetch).
+    unsigned int ready_seen = 0;
+    if (bp.ready) {
+        if (tid == 0) fb_wait_reads(bp.ready, min(2u, in.n_reads), ready_seen);
+        __syncthreads();
+    }
     if (warp != 0) {
         FB_BW_PREFETCH_ISSUE(ri_next)
         prefetch_commit(ri_next, 0);
@@ -481,6 +506,11 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
                     ms->full_reads = 1;
                 }
             }
+        }
+        if (bp.ready) {
+            // the next step prefetches read step + 2 at the top of its phase A: make sure it has landed (thread 0 waits, the
+            // named barriers of phase B.2 / C order the other warps behind it: warp 0 arrives on them only afterwards)
+            if (tid == 0) fb_wait_reads(bp.ready, min(step + 3u, in.n_reads), ready_seen);
         }
         PROF(4)
 

@@ -20,6 +20,7 @@
 struct fb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;  // copy / pack stream of the pipelined upload (created on first use)
     std::string err;
     uint32_t *d_lut = nullptr;  // 256 x u32 (units of 2^-26)
     uint32_t h_lut[256];
@@ -45,6 +46,13 @@ struct fb_dfrags {
     uint32_t *d_allele = nullptr;
     uint16_t *d_present = nullptr;
     std::vector<uint32_t> h_first, h_last, h_nnz, h_gstart, h_gptr, h_gnum, h_prefmax_last;
+    // pipelined upload (fb_frags_upload_impl with pipelined = 1): the planes are filled chunk by chunk on ctx->stream2 while
+    // the caller already computes on the leading reads; *d_ready = number of leading reads whose planes are complete
+    bool pipelined = false;
+    unsigned int *d_ready = nullptr;
+    unsigned long long *d_pack_err = nullptr;
+    cudaEvent_t ev_first = nullptr, ev_done = nullptr, ev_begin = nullptr;
+    std::vector<void *> pipe_temps;  // device temporaries of the upload, released by fb_frags_finish
     DFragsDev dev() const {
         DFragsDev d;
         d.n_reads = n_reads;

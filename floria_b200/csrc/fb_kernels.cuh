@@ -7,7 +7,9 @@
 // ---------------------------------------------------------------------------------------------------------------------
 // pack: CSR cells -> banded planes.  One thread per stored cell.
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void k_pack(uint64_t nnz, uint64_t n_reads, const uint64_t *__restrict__ row_ptr,
+// cell_base: index of pos[0] / allele[0] / qual[0] in the contig's cell numbering (chunked uploads hand in one chunk of
+// whole reads at a time; row_ptr always is the contig's full array)
+__global__ void k_pack(uint64_t nnz, uint64_t cell_base, uint64_t n_reads, const uint64_t *__restrict__ row_ptr,
                        const uint32_t *__restrict__ pos, const uint8_t *__restrict__ allele,
                        const uint8_t *__restrict__ qual, const uint32_t *__restrict__ gstart,
                        const uint32_t *__restrict__ gptr, const uint32_t *__restrict__ first,
@@ -15,8 +17,9 @@ __global__ void k_pack(uint64_t nnz, uint64_t n_reads, const uint64_t *__restric
                        uint32_t *__restrict__ allele_out, uint32_t *__restrict__ present_out32,
                        unsigned long long *__restrict__ err /* first bad cell + 1, 0 = none */,
                        const uint32_t *__restrict__ rshift /* per read: added to its positions (batched contigs), or NULL */) {
-    uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nnz) return;
+    const uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // index into this launch's arrays
+    if (x >= nnz) return;
+    const uint64_t c = cell_base + x;
     // read of this cell: last r with row_ptr[r] <= c
     uint64_t lo = 0, hi = n_reads;  // invariant: row_ptr[lo] <= c < row_ptr[hi]
     while (hi - lo > 1) {
@@ -27,12 +30,12 @@ __global__ void k_pack(uint64_t nnz, uint64_t n_reads, const uint64_t *__restric
             hi = mid;
     }
     const uint32_t sh = rshift ? rshift[lo] : 0u;
-    const uint32_t p = pos[c] + sh;
-    const uint32_t a = allele[c];
+    const uint32_t p = pos[x] + sh;
+    const uint32_t a = allele[x];
     // per-cell validation (the per-read checks are done on the host): allele index fits 2 bits, positions strictly
     // ascending inside [first, last] with the end points present
     bool bad = a > 3 || p < first[lo] || p > last[lo];
-    if (c > row_ptr[lo] && pos[c - 1] + sh >= p) bad = true;
+    if (c > row_ptr[lo] && pos[x - 1] + sh >= p) bad = true;  // (chunks start on read boundaries: x >= 1 here)
     if (c == row_ptr[lo] && p != first[lo]) bad = true;
     if (c + 1 == row_ptr[lo + 1] && p != last[lo]) bad = true;
     if (bad) {
@@ -44,7 +47,13 @@ __global__ void k_pack(uint64_t nnz, uint64_t n_reads, const uint64_t *__restric
     uint32_t k = p0 & 15u;
     atomicOr(&allele_out[g], ((a & 1u) << k) | (((a >> 1) & 1u) << (16 + k)));
     atomicOr(&present_out32[g >> 1], 1u << (k + 16u * (g & 1u)));
-    qual_out[(uint64_t)g * 16 + k] = qual[c];
+    qual_out[(uint64_t)g * 16 + k] = qual[x];
+}
+
+// pipelined upload: the planes of reads [0, n) are complete
+__global__ void k_set_ready(unsigned int *ready, unsigned int n) {
+    __threadfence();
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ready), "r"(n) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -90,6 +90,7 @@ void fb_destroy(fb_ctx *ctx) {
     ctx->cache.trim();
     FbCacheRegistry::get().orphan(&ctx->cache);
     if (ctx->h_n_active) cudaFreeHost(ctx->h_n_active);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -128,7 +129,11 @@ void *fb_stream(const fb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr;
 // k - 1 and their SNP positions are shifted by pos_shift[k] (batched contigs, fb_multi.cuh; one part with shift 0 is a plain
 // upload).  The cells go straight from the caller's buffers to the device (one copy per array and part) and are shifted by
 // k_pack: the host only touches per-read metadata.
-int fb_frags_upload_parts(fb_ctx *ctx, uint64_t n_parts, const fb_frags *parts, const uint32_t *pos_shift, fb_dfrags **out) {
+}  // extern "C"
+
+// pipelined = 1: see fb_frags_upload_pipelined below (one part only)
+static int fb_frags_upload_impl(fb_ctx *ctx, uint64_t n_parts, const fb_frags *parts, const uint32_t *pos_shift, int pipelined,
+                                fb_dfrags **out) {
     if (!ctx) return FB_ERR_ARG;
     if (!parts || !out || n_parts == 0) FB_FAIL(FB_ERR_ARG, "null argument");
     *out = nullptr;
@@ -198,6 +203,88 @@ int fb_frags_upload_parts(fb_ctx *ctx, uint64_t n_parts, const fb_frags *parts, 
     df->h_gptr[R] = (uint32_t)ng;
     df->n_groups = ng;
     int rc;
+    if (pipelined) {
+        // ---- chunked, on ctx->stream2: H2D of a chunk of whole reads -> k_pack of that chunk -> *d_ready = reads done.  The caller
+        //      computes on ctx->stream meanwhile (k_beam_wide polls d_ready); fb_frags_finish waits and reports cell errors.
+        if (!ctx->stream2) FB_CK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+        cudaStream_t s2 = ctx->stream2;
+        const fb_frags *fr = &parts[0];
+        const uint64_t chunk_cells = 192ull << 20;  // ~1.2 GB of CSR per chunk (about 20 ms of PCIe)
+        uint64_t max_chunk = 0;
+        std::vector<uint64_t> cuts(1, 0);  // read indices where chunks start
+        for (uint64_t r = 0; r < R;) {
+            uint64_t r1 = r + 1;
+            while (r1 < R && row[r1 + 1] - row[r] <= chunk_cells) ++r1;
+            max_chunk = std::max(max_chunk, row[r1] - row[r]);
+            cuts.push_back(r1);
+            r = r1;
+        }
+        uint64_t *d_row = nullptr;
+        uint32_t *d_pos[2] = {nullptr, nullptr};
+        uint8_t *d_al[2] = {nullptr, nullptr}, *d_q[2] = {nullptr, nullptr};
+        auto track = [&](void *p) { df->pipe_temps.push_back(p); };
+        df->pipelined = true;
+        if ((rc = fb_dalloc(ctx, &d_row, R + 1)) || (track(d_row), 0) || (rc = fb_dalloc(ctx, &df->d_ready, 1)) ||
+            (rc = fb_dalloc(ctx, &df->d_pack_err, 1)) || (rc = fb_dalloc(ctx, &df->d_first, R)) || (rc = fb_dalloc(ctx, &df->d_last, R)) ||
+            (rc = fb_dalloc(ctx, &df->d_nnz, R)) || (rc = fb_dalloc(ctx, &df->d_gstart, R)) || (rc = fb_dalloc(ctx, &df->d_gptr, R + 1)) ||
+            (rc = fb_dalloc(ctx, &df->d_gnum, R)) || (rc = fb_dalloc(ctx, &df->d_qual, ng + 1)) ||
+            (rc = fb_dalloc(ctx, &df->d_allele, ng + 1)) || (rc = fb_dalloc(ctx, &df->d_present, ng + 2))) {
+            fb_frags_free(ctx, df.release());
+            return rc;
+        }
+        for (int b = 0; b < 2; ++b)
+            if ((rc = fb_dalloc(ctx, &d_pos[b], max_chunk)) || (track(d_pos[b]), 0) || (rc = fb_dalloc(ctx, &d_al[b], max_chunk)) ||
+                (track(d_al[b]), 0) || (rc = fb_dalloc(ctx, &d_q[b], max_chunk)) || (track(d_q[b]), 0)) {
+                fb_frags_free(ctx, df.release());
+                return rc;
+            }
+        cudaEventCreateWithFlags(&df->ev_begin, cudaEventDefault);
+        cudaEventCreateWithFlags(&df->ev_first, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&df->ev_done, cudaEventDefault);
+        // everything of this upload is ordered on stream2; the memory comes from this context's cache, whose blocks were last
+        // used on ctx->stream: order stream2 behind what ctx->stream has queued so far
+        cudaEvent_t ev_prev;
+        cudaEventCreateWithFlags(&ev_prev, cudaEventDisableTiming);
+        cudaEventRecord(ev_prev, ctx->stream);
+        cudaStreamWaitEvent(s2, ev_prev, 0);
+        cudaEventDestroy(ev_prev);
+        cudaEventRecord(df->ev_begin, s2);
+        cudaMemcpyAsync(d_row, row.data(), (R + 1) * 8, cudaMemcpyHostToDevice, s2);
+        cudaMemcpyAsync(df->d_first, df->h_first.data(), R * 4, cudaMemcpyHostToDevice, s2);
+        cudaMemcpyAsync(df->d_last, df->h_last.data(), R * 4, cudaMemcpyHostToDevice, s2);
+        cudaMemcpyAsync(df->d_nnz, df->h_nnz.data(), R * 4, cudaMemcpyHostToDevice, s2);
+        cudaMemcpyAsync(df->d_gstart, df->h_gstart.data(), R * 4, cudaMemcpyHostToDevice, s2);
+        cudaMemcpyAsync(df->d_gptr, df->h_gptr.data(), (R + 1) * 4, cudaMemcpyHostToDevice, s2);
+        cudaMemcpyAsync(df->d_gnum, df->h_gnum.data(), R * 4, cudaMemcpyHostToDevice, s2);
+        cudaMemsetAsync(df->d_qual, 0xFF, (ng + 1) * sizeof(uint4), s2);
+        cudaMemsetAsync(df->d_allele, 0, (ng + 1) * sizeof(uint32_t), s2);
+        cudaMemsetAsync(df->d_present, 0, (ng + 2) * sizeof(uint16_t), s2);
+        cudaMemsetAsync(df->d_ready, 0, sizeof(unsigned int), s2);
+        cudaMemsetAsync(df->d_pack_err, 0xFF, sizeof(unsigned long long), s2);
+        // `row` (pageable) must stay alive until its copy has run: the small metadata copies above are synchronous with respect
+        // to the host for pageable sources (staged), so they have been consumed when cudaMemcpyAsync returns
+        cudaEvent_t ev_buf[2] = {nullptr, nullptr};
+        for (size_t k = 0; k + 1 < cuts.size(); ++k) {
+            const int b = (int)(k & 1);
+            const uint64_t ra = cuts[k], rb = cuts[k + 1], ca = row[ra], cb = row[rb], n = cb - ca;
+            if (ev_buf[b]) cudaStreamWaitEvent(s2, ev_buf[b], 0);  // (same stream: already ordered; kept for clarity)
+            cudaMemcpyAsync(d_pos[b], fr->pos + ca, n * 4, cudaMemcpyHostToDevice, s2);
+            cudaMemcpyAsync(d_al[b], fr->allele + ca, n, cudaMemcpyHostToDevice, s2);
+            cudaMemcpyAsync(d_q[b], fr->qual + ca, n, cudaMemcpyHostToDevice, s2);
+            k_pack<<<(unsigned)((n + 255) / 256), 256, 0, s2>>>(n, ca, R, d_row, d_pos[b], d_al[b], d_q[b], df->d_gstart, df->d_gptr,
+                                                              df->d_first, df->d_last, reinterpret_cast<uint8_t *>(df->d_qual),
+                                                              df->d_allele, reinterpret_cast<uint32_t *>(df->d_present),
+                                                              df->d_pack_err, nullptr);
+            k_set_ready<<<1, 1, 0, s2>>>(df->d_ready, (unsigned int)rb);
+            ctx->tim.n_launches += 2;
+            if (k == 0) cudaEventRecord(df->ev_first, s2);
+        }
+        cudaEventRecord(df->ev_done, s2);
+        FB_CK(cudaGetLastError());
+        df->bytes = ng * 22;
+        *out = df.release();
+        return FB_OK;
+    }
     cudaEvent_t e0 = fb_event(ctx);
     // temporary CSR on the device
     uint64_t *d_row = nullptr;
@@ -243,7 +330,7 @@ int fb_frags_upload_parts(fb_ctx *ctx, uint64_t n_parts, const fb_frags *parts, 
     cudaMemsetAsync(d_err, 0xFF, sizeof(unsigned long long), ctx->stream);
     if (NNZ) {
         k_pack<<<(unsigned)((NNZ + 255) / 256), 256, 0, ctx->stream>>>(
-            NNZ, R, d_row, d_pos, d_al, d_q, df->d_gstart, df->d_gptr, df->d_first, df->d_last,
+            NNZ, 0, R, d_row, d_pos, d_al, d_q, df->d_gstart, df->d_gptr, df->d_first, df->d_last,
             reinterpret_cast<uint8_t *>(df->d_qual), df->d_allele, reinterpret_cast<uint32_t *>(df->d_present), d_err, d_rshift);
         ctx->tim.n_launches++;
     }
@@ -281,15 +368,57 @@ int fb_frags_upload_parts(fb_ctx *ctx, uint64_t n_parts, const fb_frags *parts, 
     return FB_OK;
 }
 
+// waits for a pipelined upload, reports invalid cells, releases the upload's temporaries (no-op for a plain upload)
+static int fb_frags_finish(fb_ctx *ctx, fb_dfrags *df, const fb_frags *fr) {
+    if (!df || !df->pipelined) return FB_OK;
+    df->pipelined = false;
+    cudaError_t ce = cudaStreamSynchronize(ctx->stream2);
+    unsigned long long h_err = ~0ULL;
+    if (ce == cudaSuccess) ce = cudaMemcpy(&h_err, df->d_pack_err, sizeof(h_err), cudaMemcpyDeviceToHost);
+    float ms = 0;
+    if (ce == cudaSuccess && cudaEventElapsedTime(&ms, df->ev_begin, df->ev_done) == cudaSuccess) ctx->tim.upload_ms += ms;
+    for (void *p : df->pipe_temps) fb_cache_free(p);
+    df->pipe_temps.clear();
+    if (ce != cudaSuccess) {
+        ctx->err = std::string("pipelined upload: ") + cudaGetErrorString(ce);
+        return FB_ERR_CUDA;
+    }
+    if (h_err != ~0ULL) {
+        const uint64_t c = h_err - 1;
+        const uint64_t r = std::upper_bound(fr->row_ptr, fr->row_ptr + fr->n_reads + 1, c) - fr->row_ptr - 1;
+        char b_[256];
+        snprintf(b_, sizeof(b_),
+                 "read %llu: invalid cell (allele %u at position %u): alleles must be 0..3 and positions strictly "
+                 "ascending with first/last_position their min/max",
+                 (unsigned long long)r, (unsigned)fr->allele[c], fr->pos[c]);
+        ctx->err = b_;
+        return FB_ERR_ARG;
+    }
+    return FB_OK;
+}
+
+extern "C" {
+
+int fb_frags_upload_parts(fb_ctx *ctx, uint64_t n_parts, const fb_frags *parts, const uint32_t *pos_shift, fb_dfrags **out) {
+    return fb_frags_upload_impl(ctx, n_parts, parts, pos_shift, 0, out);
+}
+
 int fb_frags_upload(fb_ctx *ctx, const fb_frags *fr, fb_dfrags **out) {
     if (!ctx) return FB_ERR_ARG;
     if (!fr || !out) FB_FAIL(FB_ERR_ARG, "null argument");
-    return fb_frags_upload_parts(ctx, 1, fr, nullptr, out);
+    return fb_frags_upload_impl(ctx, 1, fr, nullptr, 0, out);
 }
 
 void fb_frags_free(fb_ctx *ctx, fb_dfrags *df) {
     if (!df) return;
     if (ctx) cudaSetDevice(ctx->device);
+    if (df->pipelined && ctx && ctx->stream2) cudaStreamSynchronize(ctx->stream2);  // never free under a running upload
+    for (void *p : df->pipe_temps) fb_cache_free(p);
+    fb_cache_free(df->d_ready);
+    fb_cache_free(df->d_pack_err);
+    if (df->ev_first) cudaEventDestroy(df->ev_first);
+    if (df->ev_done) cudaEventDestroy(df->ev_done);
+    if (df->ev_begin) cudaEventDestroy(df->ev_begin);
     fb_cache_free(df->d_first);
     fb_cache_free(df->d_last);
     fb_cache_free(df->d_nnz);
@@ -883,6 +1012,7 @@ int fb_phase_block_resident(fb_ctx *ctx, const fb_dfrags *df, uint64_t n_sel, co
     if ((rc = e.finalize_and_upload(prm->epsilon))) return rc;
     BeamRun br;
     if ((rc = fb_run_beam(ctx, e, prm, nullptr, br))) return rc;
+    if (df->pipelined) cudaStreamWaitEvent(ctx->stream, df->ev_done, 0);  // everything below reads the whole contig
     if ((rc = e.run_optimize(prm->num_iter_optimize))) return rc;
     // get_mec_stats_epsilon_no_phred on the optimized partition: unweighted histogram into the spare buffer
     if ((rc = e.launch_hist(1, 0, 0, 0, 1))) return rc;
@@ -924,12 +1054,18 @@ int fb_phase_block_resident(fb_ctx *ctx, const fb_dfrags *df, uint64_t n_sel, co
 int fb_phase_block(fb_ctx *ctx, const fb_frags *fr, uint64_t n_sel, const uint32_t *sel, uint32_t ploidy,
                    const fb_params *prm, uint8_t *hap_out, double *mec_bases, double *mec_errors, fb_block_phase *out) {
     if (!ctx) return FB_ERR_ARG;
+    if (!fr) FB_FAIL(FB_ERR_ARG, "null argument");
     fb_dfrags *df = nullptr;
-    int rc = fb_frags_upload(ctx, fr, &df);
+    // Large inputs: the upload is pipelined with the beam search (chunks of reads are copied and packed on a second stream
+    // while k_beam_wide, which consumes the reads in order, already runs on the leading ones).  FB_PIPELINE_UPLOAD=0/1 forces it.
+    const char *env = getenv("FB_PIPELINE_UPLOAD");
+    const bool pipelined = ploidy >= 2 && (env ? atoi(env) != 0 : fr->nnz >= (256ull << 20));
+    int rc = fb_frags_upload_impl(ctx, 1, fr, nullptr, pipelined ? 1 : 0, &df);
     if (rc) return rc;
     rc = fb_phase_block_resident(ctx, df, n_sel, sel, ploidy, prm, hap_out, mec_bases, mec_errors, out);
+    const int rc2 = fb_frags_finish(ctx, df, fr);
     fb_frags_free(ctx, df);
-    return rc;
+    return rc ? rc : rc2;
 }
 
 void fb_free_block_results(fb_block_results *r) {

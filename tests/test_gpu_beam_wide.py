@@ -172,3 +172,38 @@ def test_config3_shape_golden(ctx, monkeypatch):
     gb, ge = ctx.get_mec_stats_epsilon(fr, sel, oh, p, 0, prm)
     assert_f64_identical(gb, z["mec_bases"], "no-phred bases")
     assert_f64_identical(ge, z["mec_errors"], "no-phred errors (the MEC of the ploidy loop)")
+
+
+@pytest.mark.parametrize("wide", ["1", "0"])
+def test_phase_block_with_pipelined_upload(ctx, monkeypatch, wide):
+    """fb_phase_block from host buffers with the upload pipelined under the beam search (chunks of reads copied and packed on
+    a second stream while k_beam_wide already consumes the leading reads; k_beam waits for the whole contig): same result as
+    the plain upload and as the oracle"""
+    monkeypatch.setenv("FB_BEAM_WIDE", wide)
+    for seed, n, S, p, kw in ((81, 300, 400, 3, dict(span_mean=120)), (82, 90, 6000, 4, dict(full_span=True))):
+        c = synth.make_contig(seed, n, S, p, **kw)
+        prm = default_params(epsilon=0.04, max_ploidy=p)
+        sel = np.arange(0, c.frags.n_reads, dtype=np.uint32)
+        oh, ob, oe, oi = oracle.phase_block(c.frags, sel, p, prm)
+        monkeypatch.setenv("FB_PIPELINE_UPLOAD", "1")
+        gh, gb, ge, gi = ctx.phase_block(c.frags, sel, p, prm)
+        monkeypatch.setenv("FB_PIPELINE_UPLOAD", "0")
+        hh, hb, he, hi = ctx.phase_block(c.frags, sel, p, prm)
+        for h, e, i in ((gh, ge, gi), (hh, he, hi)):
+            assert np.array_equal(h, oh)
+            assert_f64_identical(e, oe, "no-phred errors")
+            assert (i["cells_sweep"], i["cells_hist"], i["cells_beam"]) == (oi["cells_sweep"], oi["cells_hist"], oi["cells_beam"])
+            assert_f64_identical([i["beam_score"], i["opt_score"]], [oi["beam_score"], oi["opt_score"]], "scores")
+
+
+def test_pipelined_upload_reports_bad_cells(ctx, monkeypatch):
+    monkeypatch.setenv("FB_PIPELINE_UPLOAD", "1")
+    c = synth.make_contig(83, 60, 300, 2, span_mean=100)
+    bad = c.frags.allele.copy()
+    bad[len(bad) // 2] = 7
+    fr = type(c.frags)(c.frags.row_ptr, c.frags.pos, bad, c.frags.qual, c.frags.first, c.frags.last)
+    with pytest.raises(api.FloriaB200Error, match="invalid cell"):
+        ctx.phase_block(fr, None, 2, default_params())
+    # the context stays usable
+    h, b, e, i = ctx.phase_block(c.frags, None, 2, default_params())
+    assert len(h) == c.frags.n_reads
