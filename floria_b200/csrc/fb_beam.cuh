@@ -136,6 +136,12 @@ struct BeamJob {
     uint32_t _pad;
 };
 
+// cycle counter of the FB_BEAM_PROF probes: the memory clobber keeps it on its side of barriers and named barriers
+__device__ __forceinline__ long long fb_clock() {
+    long long c;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(c)::"memory");
+    return c;
+}
 __device__ __forceinline__ void fb_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int P, int NT>
@@ -222,10 +228,10 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
             }
         }
         long long pt[24] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-        long long tc = clock64();
+        long long tc = fb_clock();
 #define PROF(i)                         \
     if (bp.prof && tid == 0) {          \
-        long long n_ = clock64();       \
+        long long n_ = fb_clock();       \
         pt[i] += n_ - tc;               \
         tc = n_;                        \
     }
@@ -282,6 +288,7 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
                 rx_next = rextra[step + 1];
             }
             const uint32_t cur_start = rx.first0;
+            if (bp.prof && tid == 0) pt[22] += fb_clock() - tc;  // step top reached
             const uint32_t g0 = ri.gbase + ri.lg0, g1 = ri.gbase + ri.lg1;  // global groups of the read
             const int par = (int)(step & 1u);
             const bool staged = (ri.lg1 - ri.lg0) <= FB_BEAM_RG;
@@ -316,7 +323,7 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
                     continue;
                 }
                 long long q0 = 0;
-                if (bp.prof && tid == 0) q0 = clock64();
+                if (bp.prof && tid == 0) q0 = fb_clock();
                 const uint2 *mk = ST_MASK(s);
                 unsigned long long total = 0, same = 0, emptyw = 0;
                 uint32_t ne_cnt = 0;
@@ -353,13 +360,13 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
                     const uint32_t db = pr & ne & ~sb & 0xFFFFu;
                     if (db) last_diff = max(last_diff, (int)(lg * 16u) + 31 - __clz(db));
                 }
-                if (bp.prof && tid == 0) { long long n_ = clock64(); pt[16] += n_ - q0; q0 = n_; }
+                if (bp.prof && tid == 0) { long long n_ = fb_clock(); pt[16] += n_ - q0; q0 = n_; }
                 total = fb_warp_sum_u64(total);
                 same = fb_warp_sum_u64(same);
                 emptyw = fb_warp_sum_u64(emptyw);
                 ne_cnt = fb_warp_sum_u32(ne_cnt);
                 const long long diff_q = (long long)(total - same - emptyw);
-                if (bp.prof && tid == 0) { long long n_ = clock64(); pt[17] += n_ - q0; q0 = n_; }
+                if (bp.prof && tid == 0) { long long n_ = fb_clock(); pt[17] += n_ - q0; q0 = n_; }
                 double diff_f;
                 if (ne_cnt == 0)
                     diff_f = fb_q26_to_f64(diff_q);
@@ -372,7 +379,7 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
                     diff_f = fb_add_eps_n(fb_q26_to_f64(diff_q), bp.eps, ne_cnt);
                 else
                     diff_f = fb_replay_diff(bp.fr, g0, g1, mk, ri.lg0, hi, lut_s, bp.eps, wscr);
-                if (bp.prof && tid == 0) { long long n_ = clock64(); pt[18] += n_ - q0 + (long long)(diff_f * 0.0); q0 = n_; }
+                if (bp.prof && tid == 0) { long long n_ = fb_clock(); pt[18] += n_ - q0 + (long long)(diff_f * 0.0); q0 = n_; }
                 {
                     // stable_binom_cdf_p_rev (utils_frags.rs:211-248) with its two log terms evaluated on two lanes; the
                     // operations and their order are those of fb_stable_binom_cdf_p_rev (global_clustering.rs:81-88).
@@ -399,9 +406,10 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
                         sc_diff[s] = diff_f;
                         sc_pv[s] = 1.0 * pvs;
                     }
-                    if (bp.prof && tid == 0) { long long n_ = clock64(); pt[19] += n_ - q0 + (long long)(pvs * 0.0); q0 = n_; }
+                    if (bp.prof && tid == 0) { long long n_ = fb_clock(); pt[19] += n_ - q0 + (long long)(pvs * 0.0); q0 = n_; }
                 }
             }
+            if (bp.prof && tid == 0) pt[3] += fb_clock() - tc;  // warp 0 done with its own tasks
             __syncthreads();
             PROF(0)
 

@@ -277,6 +277,8 @@ static int fb_run_beam(fb_ctx *ctx, Engine &e, const fb_params *prm, const BeamT
             const double steps = (double)std::max<unsigned long long>(h[12], 1);
             fprintf(stderr, "[k_beam prof] scoring warp 0, cycles/step: loop %.0f | reductions %.0f | diff_f %.0f | p-value %.0f\n",
                     h[16] / steps, h[17] / steps, h[18] / steps, h[19] / steps);
+            fprintf(stderr, "[k_beam prof] warp 0: step top reached %.0f cycles after the end-of-step barrier, own phase-1 task done at %.0f\n",
+                    h[22] / steps, h[3] / steps);
             fprintf(stderr,
                     "[k_beam prof] %.3f ms (both kernels), %d instances on %llu CTAs, %.0f steps; cycles/step: phase1(score) %.0f | warp0: lse %.0f "
                     "compact+fold+dups+classes %.0f heap %.0f nextgen %.0f | phase3(copy) %.0f | children/step %.1f survivors/step %.1f "

@@ -212,10 +212,10 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
     __shared__ long long pt[24];
     if (tid < 24) pt[tid] = 0;
     __syncthreads();
-    long long tc = clock64();
+    long long tc = fb_clock();
 #define PROF(i)                                \
     if (bp.prof && writer && tid == 0) {       \
-        long long n_ = clock64();              \
+        long long n_ = fb_clock();              \
         pt[i] += n_ - tc;                      \
         tc = n_;                               \
     }
@@ -352,7 +352,7 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
         //      read against every live state ------------------------------------------------------------------------------
         if (warp != 0) {
             long long q0 = 0;
-            if (prof1) q0 = clock64();
+            if (prof1) q0 = fb_clock();
             const int n_live = ms->n_live;
             if (step + 1 < in.n_reads) FB_BW_PREFETCH_ISSUE(ri_next)  // consumed in this step's phase B.2
             if (writer) zero_slot((step + 1) % 3u, 32, NT - 32);  // last read two steps ago, first written after this step's barrier
@@ -441,7 +441,7 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
                     }
                 }
             }
-            if (prof1) pa += clock64() - q0;
+            if (prof1) pa += fb_clock() - q0;
         }
         PROF(1)  // warp 0: the bookkeeping that follows the previous step's live list (overlaps phase A)
         fb_grid_barrier(bp.wbar, bar_target += G);
@@ -522,17 +522,17 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
         // overlap another CTA's in-place update of the same step: all CTAs meet at a second grid barrier first.
         if (warp != 0) {
             long long q0 = 0;
-            if (prof1) q0 = clock64();
+            if (prof1) q0 = fb_clock();
             if (step + 1 < in.n_reads) prefetch_commit(ri_next, (step + 1) % 3u);
             if (prof1) {
-                const long long n_ = clock64();
+                const long long n_ = fb_clock();
                 pc += n_ - q0;
                 q0 = n_;
             }
             asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
             if (ms->full_reads) fb_grid_barrier(bp.wbar, bar_target += G);
             if (prof1) {
-                const long long n_ = clock64();
+                const long long n_ = fb_clock();
                 pw += n_ - q0;
                 q0 = n_;
             }
@@ -626,12 +626,12 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
                 }
             }
             if (prof1) {
-                const long long n_ = clock64();
+                const long long n_ = fb_clock();
                 pc += n_ - q0;
                 q0 = n_;
             }
             asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory");  // the next step's live list
-            if (prof1) pw += clock64() - q0;
+            if (prof1) pw += fb_clock() - q0;
         } else {
 #define FB_BEAM_POOL_LD(p) __ldcg(p)
 #define FB_BEAM_WRITER writer
