@@ -83,7 +83,7 @@ struct BeamSmem {
     uint32_t off_nd_score, off_nd_err, off_nd_ref, off_st_hash, off_sc_same, off_sc_diff, off_st_hi, off_st_mark,
         off_free, off_live, off_ch_score, off_ch_parent, off_ch_part, off_ch_class, off_ch_diff, off_hp_score,
         off_hp_item, off_lut, off_wscr, off_misc, off_job, off_addnew, off_plain, off_sc_pv, off_ch_fold, off_ch_m, off_rq,
-        off_ral, off_rpr, off_replay, total;
+        off_ral, off_rpr, off_replay, off_adone, off_inpl, total;
     __host__ __device__ void layout(uint32_t P, uint32_t W, uint32_t NS) {
         uint32_t o = 0;
         auto take = [&](uint32_t bytes) {
@@ -121,6 +121,8 @@ struct BeamSmem {
         off_ral = take(2 * FB_BEAM_RG * 4);
         off_rpr = take(2 * FB_BEAM_RG * 2);
         off_replay = take(NS * 4);  // k_beam_wide: states whose epsilon sum needs the ordered replay
+        off_adone = take(NS * 4);   // k_beam_wide: read index up to which a state has been scored (early scoring)
+        off_inpl = take(NS * 4);    // k_beam_wide: step whose p-values see the state as updated in place one step before
         total = o;
     }
 };
@@ -140,6 +142,12 @@ struct BeamJob {
 __device__ __forceinline__ long long fb_clock() {
     long long c;
     asm volatile("mov.u64 %0, %%clock64;" : "=l"(c)::"memory");
+    return c;
+}
+// the same, read only once `dep` has been produced (an operand of the instruction)
+__device__ __forceinline__ long long fb_clock_after(unsigned long long dep) {
+    long long c;
+    asm volatile("{ .reg .u64 t; mov.u64 t, %1; mov.u64 %0, %%clock64; }" : "=l"(c) : "l"(dep) : "memory");
     return c;
 }
 __device__ __forceinline__ void fb_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }

@@ -199,8 +199,8 @@ static int fb_run_beam(fb_ctx *ctx, Engine &e, const fb_params *prm, const BeamT
             return rc;
         }
         if (kind == 1) {
-            if ((rc = fb_dalloc(ctx, &d_wacc, (size_t)3 * maxNS)) || (temps.push_back(d_wacc), 0) ||
-                (rc = fb_dalloc(ctx, &d_wstep, 3)) || (temps.push_back(d_wstep), 0) ||
+            if ((rc = fb_dalloc(ctx, &d_wacc, (size_t)FB_BW_SLOTS * maxNS)) || (temps.push_back(d_wacc), 0) ||
+                (rc = fb_dalloc(ctx, &d_wstep, FB_BW_SLOTS)) || (temps.push_back(d_wstep), 0) ||
                 (rc = fb_dalloc(ctx, &d_wbar, 1)) || (temps.push_back(d_wbar), 0)) {
                 cleanup();
                 return rc;
@@ -290,6 +290,8 @@ static int fb_run_beam(fb_ctx *ctx, Engine &e, const fb_params *prm, const BeamT
         if (!order_w.empty()) {
             const unsigned long long *h = hh + 24;
             const double steps = (double)std::max<unsigned long long>(h[12], 1);
+            fprintf(stderr, "[k_beam_wide prof] p-value step of CTA 0 (cycles after the grid barrier): sums loaded %.0f, p-values formed %.0f\n",
+                    h[16] / steps, h[17] / steps);
             fprintf(stderr,
                     "[k_beam_wide prof] %.3f ms (both kernels), %d instances on a grid of %d CTAs, %.0f steps; CTA 0 cycles/step: "
                     "warp 0: bookkeeping after the live list %.0f | grid barrier %.0f | p-values %.0f | lse %.0f "

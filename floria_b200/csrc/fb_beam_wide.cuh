@@ -13,6 +13,11 @@
 //            identical inputs, so all CTAs hold the same node tables / job list without a broadcast
 //   phase C  every CTA materialises its slice of the surviving generation's new states (copy or in place) and the is-max
 //            planes; the next step's phase A reads only the CTA's own slices, so no barrier is needed here
+// Optional (FB_BW_EARLY, off: measured slower): while warp 0 forms the p-values and runs the decision section of step t,
+// the other warps score read t + 1 against every state that is live NOW (early scoring, into the slot of step t + 1).  A
+// state that survives unchanged is then done; the state that step t updates in place gets the difference between its
+// updated and its old planes added by the materialisation itself (phase C holds both in registers); only states created
+// by a copy in step t are scored by the regular phase A at the top of step t + 1.
 // Full-state reads (the ordered epsilon replay of a non-dyadic epsilon, the word-by-word equality check behind a hash
 // match) touch slices that other CTAs update in place in phase C of the same step: steps that execute one add a second
 // grid barrier before phase C.  Both are rare (first reads of a haplotype; states that became equal after the window
@@ -23,11 +28,28 @@
 #define FB_BW_THREADS 256
 #define FB_BW_WARPS (FB_BW_THREADS / 32)
 #define FB_BW_CH 2  // groups per ownership chunk: 32 positions = 1 KB of counts = one warp pass of the materialisation
+#define FB_BW_SLOTS 4  // step slots of the grid reduction: read t uses slot t mod 4 (written in steps t - 1 and t, read in step t,
+                       // zeroed in step t - 2 after that step's grid barrier)
+#ifndef FB_BW_EARLY
+// 1: score the next read one step ahead, while warp 0 runs the p-values and the decision section, and let the
+// materialisation add the difference for the state it updates in place.  Bit-identical results (tests/test_gpu_beam_wide.py
+// passes either way), but measured SLOWER on the 100k x 50k block (964 ms against 917 ms per search): the early pass and the
+// deltas cost the other warps more than the regular scoring pass they remove.  Kept for A/B runs (profiles/README.md).
+#define FB_BW_EARLY 0
+#endif
 
 struct __align__(8) BeamWideAcc {  // one per (step slot, state)
     unsigned long long same, emptyw, sub;
     unsigned int ne_cnt;
+    // Last diff / first empty position of the read on the state.  A read is scored one step EARLY, against the planes as
+    // they are before that step's in-place update; sums are corrected by the update (signed deltas), extremes cannot be,
+    // so they are kept apart: groups outside the updating read's range (`last_diff`, `first_empty`: never touched by the
+    // update; also everything the regular scoring adds), groups inside it under the old planes (`_in`) and under the
+    // updated planes (`_new`, written by the materialisation).  The p-value step takes outside + new for a state that
+    // was updated in place, outside + in otherwise.
     int last_diff, first_empty;
+    int last_diff_in, first_empty_in;
+    int last_diff_new, first_empty_new;
     unsigned int _pad;
 };
 struct __align__(8) BeamWideStep {  // one per step slot
@@ -129,6 +151,8 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
     int *addnew = reinterpret_cast<int *>(smem + L.off_addnew);
     int *plain = reinterpret_cast<int *>(smem + L.off_plain);
     int *replay = reinterpret_cast<int *>(smem + L.off_replay);
+    uint32_t *a_done = reinterpret_cast<uint32_t *>(smem + L.off_adone);  // read index whose sums are complete for the state
+    uint32_t *inpl = reinterpret_cast<uint32_t *>(smem + L.off_inpl);     // step that must read the `_new` extremes
     struct Misc {
         unsigned long long delta[2];  // delta(read) of the current step (index = step parity, as in k_beam)
         int n_nodes[2];
@@ -172,13 +196,15 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
         st_mark[s] = 0;
         plain[s] = 0;
         addnew[s] = -1;
+        a_done[s] = ~0u;
+        inpl[s] = ~0u;
     }
     auto zero_slot = [&](uint32_t sl, int t0, int nt) {  // CTA 0, threads [t0, t0 + nt)
         BeamWideAcc z;
         z.same = z.emptyw = z.sub = 0;
         z.ne_cnt = 0;
-        z.last_diff = -1;
-        z.first_empty = INT_MAX;
+        z.last_diff = z.last_diff_in = z.last_diff_new = -1;
+        z.first_empty = z.first_empty_in = z.first_empty_new = INT_MAX;
         z._pad = 0;
         for (int s = tid - t0; s >= 0 && s < (int)NS; s += nt) bp.wacc[(uint64_t)sl * bp.maxNS + s] = z;
         if (tid == t0) {
@@ -186,11 +212,8 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
             bp.wstep[sl].delta = 0;
         }
     };
-    if (writer) {
-        zero_slot(0, 0, NT);
-        zero_slot(1, 0, NT);
-        zero_slot(2, 0, NT);
-    }
+    if (writer)
+        for (uint32_t sl = 0; sl < FB_BW_SLOTS; ++sl) zero_slot(sl, 0, NT);
     __syncthreads();
     if (tid == 0) {
         ms->n_free = 0;  // explicit free stack (ids below hw); state 0 is the root's empty state
@@ -228,8 +251,17 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
     uint32_t prev_start = 0;  // block-local position0 from which the hashes are valid
     int gmax = -1;            // last block-local group touched so far
     unsigned long long cells = 0, tapn = 0;
-    RInfo ri_next = rinfo[0];
-    RExtra rx_next = rextra[0];
+    // The reads' descriptors go through a shared-memory ring filled 32 steps ahead (a descriptor fetched from global
+    // memory in the step that needs it costs a DRAM round trip on the critical path).
+    __shared__ RInfo rd_i[64];
+    __shared__ RExtra rd_x[64];
+    if (tid < 64 && (uint32_t)tid < in.n_reads) {
+        rd_i[tid] = rinfo[tid];
+        rd_x[tid] = rextra[tid];
+    }
+    __syncthreads();
+    RInfo ri_next = rd_i[0];
+    RExtra rx_next = rd_x[0];
 
     // This CTA's groups of a read, staged in shared memory one step ahead (by the warps that idle while warp 0 runs the
     // decision section) together with the read-only sums of the step: total weight and delta(read) = sum of
@@ -240,13 +272,8 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
         c0 = my_first_chunk(cA);
         return c0 <= cB ? ((cB - c0) / G + 1) * CH : 0u;  // group slots of my chunks (the ends may fall outside the read)
     };
-    // The loads of a read's planes are ISSUED one step ahead, at the top of phase A (prefetch_issue: registers), so that
-    // their DRAM latency hides behind phase A, the grid barrier and the p-values; they are COMMITTED to the shared-memory
-    // staging buffer while warp 0 runs the decision section (prefetch_commit), where the per-read sums are formed too.
-    // (scalars and a macro rather than arrays captured by a lambda: the prefetched values must stay in registers, a trip
-    // through local memory would wait for the loads right where they are issued)
-    uint4 pf_q0 = make_uint4(~0u, ~0u, ~0u, ~0u), pf_q1 = pf_q0;
-    uint32_t pf_al0 = 0, pf_al1 = 0, pf_pr0 = 0, pf_pr1 = 0;
+    // The planes of read t + 1 are fetched while warp 0 runs the p-values and the decision section of step t (the DRAM
+    // latency falls into the time the other warps would wait for the job list anyway), two groups per thread in flight.
 #define FB_BW_PREFETCH_ONE(r_, gi_, q_, al_, pr_, c0_, nmg_)                          \
     {                                                                                \
         q_ = make_uint4(~0u, ~0u, ~0u, ~0u);                                         \
@@ -262,18 +289,15 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
             }                                                                        \
         }                                                                            \
     }
-#define FB_BW_PREFETCH_ISSUE(r_)                                                                        \
-    {                                                                                                   \
-        uint32_t c0_;                                                                                   \
-        const uint32_t nmg_ = min(my_groups(r_, c0_), STG);                                             \
-        FB_BW_PREFETCH_ONE(r_, (uint32_t)tid - 32u, pf_q0, pf_al0, pf_pr0, c0_, nmg_)                   \
-        FB_BW_PREFETCH_ONE(r_, (uint32_t)tid - 32u + (uint32_t)(NT - 32), pf_q1, pf_al1, pf_pr1, c0_, nmg_) \
-    }
     auto prefetch_commit = [&](const RInfo &r, uint32_t slot_idx) {  // warps 1..NW-1
         uint32_t c0;
         const uint32_t nmg = my_groups(r, c0), nst = min(nmg, STG);
         {
             const uint32_t gi0 = (uint32_t)tid - 32, gi1 = gi0 + (uint32_t)(NT - 32);
+            uint4 pf_q0, pf_q1;
+            uint32_t pf_al0, pf_al1, pf_pr0, pf_pr1;
+            FB_BW_PREFETCH_ONE(r, gi0, pf_q0, pf_al0, pf_pr0, c0, nst)
+            FB_BW_PREFETCH_ONE(r, gi1, pf_q1, pf_al1, pf_pr1, c0, nst)
             if (gi0 < nst) {
                 rq[gi0] = pf_q0;
                 ral[gi0] = pf_al0;
@@ -319,6 +343,87 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
             if (dl) atomicAdd(&bp.wstep[slot_idx].delta, dl);
         }
     };
+    // One warp pass per (live state, tile of 32 of this CTA's groups of read `r`): the slice of the read against the state's
+    // is-max planes, partial sums RED-added into the slot `accp` of step `stepno`.  The read's planes are the staged ones.
+    //   early = false  regular scoring at the top of step `stepno`: states not yet scored for it (created by a copy)
+    //   early = true   read `stepno` one step ahead, every state that is live now; [in_lo, in_hi) = groups of the read of
+    //                  the running step, whose planes that step may still update in place (extremes kept apart)
+    auto score_states = [&](const RInfo &r, BeamWideAcc *accp, uint32_t stepno, bool early, uint32_t in_lo, uint32_t in_hi) {
+        const int n_live = ms->n_live;
+        uint32_t c0;
+        const uint32_t nmg = my_groups(r, c0);
+        const int tiles_g = (int)((nmg + 31) / 32);
+        const int n_tiles = n_live * tiles_g;
+        for (int t = (int)warp - 1; t < n_tiles; t += NW - 1) {
+            const int si = t % n_live, gt = t / n_live;
+            const int s = live[si];
+            if (!early && a_done[s] == stepno) continue;  // scored one step ahead (warp-uniform)
+            const int hi = st_hi[s];
+            const uint32_t gi = (uint32_t)gt * 32 + lane;
+            const uint32_t lg = (c0 + (gi / CH) * G) * CH + gi % CH;
+            const bool valid = gi < nmg && lg >= r.lg0 && lg < r.lg1;
+            const bool in_rng = early && lg >= in_lo && lg < in_hi;
+            uint32_t same = 0, emptyw = 0, ne_cnt = 0;  // per lane: at most 16 weights of 2^26
+            int last_diff = -1, first_empty = INT_MAX;
+            if (valid) {
+                const uint2 m = ((int)lg <= hi) ? __ldcg(ST_MASK(s) + lg) : make_uint2(0u, 0u);
+                uint4 q;
+                uint32_t al, pr;
+                if (gi < STG) {
+                    q = rq[gi];
+                    al = ral[gi];
+                    pr = rpr[gi];
+                } else {
+                    const uint32_t g = r.gbase + lg;
+                    q = bp.fr.qual[g];
+                    al = bp.fr.allele[g];
+                    pr = bp.fr.present[g];
+                }
+                uint32_t w[16];
+                fb_group_weights(q, pr, lut_s, w);
+                uint32_t sb, ne;
+                fb_group_masks(al, m, sb, ne);
+                same = fb_masked_sum(w, sb);
+                const uint32_t eb = pr & ~ne & 0xFFFFu;
+                if (eb) {
+                    emptyw = fb_masked_sum(w, eb);
+                    ne_cnt = __popc(eb);
+                    first_empty = (int)(lg * 16u) + __ffs(eb) - 1;
+                }
+                const uint32_t db = pr & ne & ~sb & 0xFFFFu;
+                if (db) last_diff = (int)(lg * 16u) + 31 - __clz(db);
+            }
+            // warp sums of values below 2^30 as two 16-bit halves (each REDUX result fits 32 bits)
+            const unsigned long long same_w = (unsigned long long)__reduce_add_sync(0xFFFFFFFFu, same & 0xFFFFu) +
+                                              ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, same >> 16) << 16);
+            ne_cnt = __reduce_add_sync(0xFFFFFFFFu, ne_cnt);
+            unsigned long long emptyw_w = 0;
+            int fe_out = INT_MAX, fe_in = INT_MAX, ld_out = -1, ld_in = -1;
+            if (ne_cnt) {
+                emptyw_w = (unsigned long long)__reduce_add_sync(0xFFFFFFFFu, emptyw & 0xFFFFu) +
+                           ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, emptyw >> 16) << 16);
+                fe_out = __reduce_min_sync(0xFFFFFFFFu, in_rng ? INT_MAX : first_empty);
+                if (early) fe_in = __reduce_min_sync(0xFFFFFFFFu, in_rng ? first_empty : INT_MAX);
+            }
+            if (!bp.eps_safe) {  // only the epsilon order needs it
+                ld_out = __reduce_max_sync(0xFFFFFFFFu, in_rng ? -1 : last_diff);
+                if (early) ld_in = __reduce_max_sync(0xFFFFFFFFu, in_rng ? last_diff : -1);
+            }
+            if (lane == 0) {
+                if (same_w) atomicAdd(&accp[s].same, same_w);
+                if (ne_cnt) {
+                    atomicAdd(&accp[s].ne_cnt, ne_cnt);
+                    if (emptyw_w) atomicAdd(&accp[s].emptyw, emptyw_w);
+                    if (fe_out != INT_MAX) atomicMin(&accp[s].first_empty, fe_out);
+                    if (fe_in != INT_MAX) atomicMin(&accp[s].first_empty_in, fe_in);
+                }
+                if (ld_out >= 0) atomicMax(&accp[s].last_diff, ld_out);
+                if (ld_in >= 0) atomicMax(&accp[s].last_diff_in, ld_in);
+            }
+        }
+        if (early)
+            for (int i = tid - 32; i < n_live; i += NT - 32) a_done[live[i]] = stepno;
+    };
     // pipelined upload: the planes of read t are valid once *bp.ready > t.  Thread 0 waits (bounded) before the CTA touches
     // a read; step t touches read t (phase C) and read t + 1 (prefetch).
     unsigned int ready_seen = 0;
@@ -326,25 +431,29 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
         if (tid == 0) fb_wait_reads(bp.ready, min(2u, in.n_reads), ready_seen);
         __syncthreads();
     }
-    if (warp != 0) {
-        FB_BW_PREFETCH_ISSUE(ri_next)
-        prefetch_commit(ri_next, 0);
-    }
+    if (warp != 0) prefetch_commit(ri_next, 0);
     __syncthreads();
 
     for (uint32_t step = 0; step < in.n_reads; ++step) {
         const uint32_t width = step < 25 ? Wmax : bp.B;  // global_clustering.rs:50-53
         const RInfo ri = ri_next;
         const RExtra rx = rx_next;
-        if (step + 1 < in.n_reads) {  // prefetch the next read's descriptor (consumed next iteration)
-            ri_next = rinfo[step + 1];
-            rx_next = rextra[step + 1];
+        if (step + 1 < in.n_reads) {
+            ri_next = rd_i[(step + 1) & 63u];
+            rx_next = rd_x[(step + 1) & 63u];
+        }
+        if ((step & 31u) == 0 && step >= 32 && warp == NW - 1) {  // ring slots of steps [step - 32, step) are dead: refill
+            const uint32_t t = step + 32 + lane;
+            if (t < in.n_reads) {
+                rd_i[t & 63u] = rinfo[t];
+                rd_x[t & 63u] = rextra[t];
+            }
         }
         const uint32_t cur_start = rx.first0;
         const int par = (int)(step & 1u);
         const int gmax_new = max(gmax, (int)ri.lg1 - 1);
         const uint32_t wend = (uint32_t)(gmax_new + 1) * 16u;  // one past the last live window position
-        const uint32_t sl = step % 3u;
+        const uint32_t sl = step % FB_BW_SLOTS;
         BeamWideAcc *acc = bp.wacc + (uint64_t)sl * bp.maxNS;
         BeamWideStep *sacc = bp.wstep + sl;
 
@@ -354,70 +463,7 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
             long long q0 = 0;
             if (prof1) q0 = fb_clock();
             const int n_live = ms->n_live;
-            if (step + 1 < in.n_reads) FB_BW_PREFETCH_ISSUE(ri_next)  // consumed in this step's phase B.2
-            if (writer) zero_slot((step + 1) % 3u, 32, NT - 32);  // last read two steps ago, first written after this step's barrier
-            uint32_t c0;
-            const uint32_t nmg = my_groups(ri, c0);
-            const int tiles_g = (int)((nmg + 31) / 32);
-            const int n_tiles = n_live * tiles_g;
-            for (int t = (int)warp - 1; t < n_tiles; t += NW - 1) {
-                const int si = t % n_live, gt = t / n_live;
-                const int s = live[si];
-                const int hi = st_hi[s];
-                const uint32_t gi = (uint32_t)gt * 32 + lane;
-                const uint32_t lg = (c0 + (gi / CH) * G) * CH + gi % CH;
-                const bool valid = gi < nmg && lg >= ri.lg0 && lg < ri.lg1;
-                uint32_t same = 0, emptyw = 0, ne_cnt = 0;  // per lane: at most 16 weights of 2^26
-                int last_diff = -1, first_empty = INT_MAX;
-                if (valid) {
-                    const uint2 m = ((int)lg <= hi) ? __ldcg(ST_MASK(s) + lg) : make_uint2(0u, 0u);
-                    uint4 q;
-                    uint32_t al, pr;
-                    if (gi < STG) {
-                        q = rq[gi];
-                        al = ral[gi];
-                        pr = rpr[gi];
-                    } else {
-                        const uint32_t g = ri.gbase + lg;
-                        q = bp.fr.qual[g];
-                        al = bp.fr.allele[g];
-                        pr = bp.fr.present[g];
-                    }
-                    uint32_t w[16];
-                    fb_group_weights(q, pr, lut_s, w);
-                    uint32_t sb, ne;
-                    fb_group_masks(al, m, sb, ne);
-                    same = fb_masked_sum(w, sb);
-                    const uint32_t eb = pr & ~ne & 0xFFFFu;
-                    if (eb) {
-                        emptyw = fb_masked_sum(w, eb);
-                        ne_cnt = __popc(eb);
-                        first_empty = (int)(lg * 16u) + __ffs(eb) - 1;
-                    }
-                    const uint32_t db = pr & ne & ~sb & 0xFFFFu;
-                    if (db) last_diff = (int)(lg * 16u) + 31 - __clz(db);
-                }
-                // warp sums of values below 2^30 as two 16-bit halves (each REDUX result fits 32 bits)
-                const unsigned long long same_w = (unsigned long long)__reduce_add_sync(0xFFFFFFFFu, same & 0xFFFFu) +
-                                                  ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, same >> 16) << 16);
-                ne_cnt = __reduce_add_sync(0xFFFFFFFFu, ne_cnt);
-                unsigned long long emptyw_w = 0;
-                if (ne_cnt) {
-                    emptyw_w = (unsigned long long)__reduce_add_sync(0xFFFFFFFFu, emptyw & 0xFFFFu) +
-                               ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, emptyw >> 16) << 16);
-                    first_empty = __reduce_min_sync(0xFFFFFFFFu, first_empty);
-                }
-                if (!bp.eps_safe) last_diff = __reduce_max_sync(0xFFFFFFFFu, last_diff);  // only the epsilon order needs it
-                if (lane == 0) {
-                    if (same_w) atomicAdd(&acc[s].same, same_w);
-                    if (ne_cnt) {
-                        atomicAdd(&acc[s].ne_cnt, ne_cnt);
-                        if (emptyw_w) atomicAdd(&acc[s].emptyw, emptyw_w);
-                        atomicMin(&acc[s].first_empty, first_empty);
-                    }
-                    if (!bp.eps_safe && last_diff >= 0) atomicMax(&acc[s].last_diff, last_diff);
-                }
-            }
+            score_states(ri, acc, step, false, 0u, 0u);  // states created by a copy in the previous step (all of them at step 0)
             // hash terms of the positions [prev_start, cur_start) that leave the window, my slice of every live state
             if (cur_start > prev_start) {
                 const uint32_t dA = (prev_start >> 4) / CH, dB = ((cur_start - 1) >> 4) / CH;
@@ -449,33 +495,42 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
         const int n_nodes = ms->n_nodes[gen];
         const int n_live = ms->n_live;
 
-        // ---- phase B.1 (every CTA, redundantly): scores and p-values of all live states ------------------------------------
-        {
+        // ---- phase B.1 (warp 0 of every CTA, redundantly): scores and p-values of all live states, a pair of lanes per state;
+        //      the other warps are already staging / scoring the next read --------------------------------------------------
+        if (warp == 0) {
             const unsigned long long tot_q = __ldcg(&sacc->total);
-            if (tid == 0) ms->delta[par] = __ldcg(&sacc->delta);
-            for (int base = 0; base < n_live; base += NT / 2) {
-                const int si = base + (tid >> 1);
-                const uint32_t sub = tid & 1u;
+            if (lane == 0) ms->delta[par] = __ldcg(&sacc->delta);
+            for (int base = 0; base < n_live; base += 16) {
+                const int si = base + (int)(lane >> 1);
+                const uint32_t sub = lane & 1u;
                 const bool v = si < n_live;
                 const int s = v ? live[si] : 0;
                 const unsigned long long same_q = v ? __ldcg(&acc[s].same) : 0, emptyw = v ? __ldcg(&acc[s].emptyw) : 0;
                 const unsigned long long hsub = v ? __ldcg(&acc[s].sub) : 0;
                 const uint32_t ne_cnt = v ? __ldcg(&acc[s].ne_cnt) : 0;
                 const long long diff_q = v ? (long long)(tot_q - same_q - emptyw) : 0;
+                if (bp.prof && writer && tid == 0) pt[16] += fb_clock_after((unsigned long long)diff_q + hsub + ne_cnt) - tc;  // sums arrived from L2
                 double diff_f = 0.0;
                 bool need_replay = false;
                 if (ne_cnt == 0)
                     diff_f = fb_q26_to_f64(diff_q);
                 else if (bp.eps_safe)
                     diff_f = fb_q26_to_f64(diff_q + (long long)ne_cnt * (long long)(bp.eps * FB_Q26));
-                else if (__ldcg(&acc[s].last_diff) < __ldcg(&acc[s].first_empty))
-                    // every empty position lies right of every diff position: the exact dyadic part followed by ne_cnt
-                    // consecutive `+= epsilon`, evaluated in closed form per binade (fb_add_eps_n)
-                    diff_f = fb_add_eps_n(fb_q26_to_f64(diff_q), bp.eps, ne_cnt);
-                else
-                    need_replay = true;
+                else {
+                    // extremes: groups the previous step's read does not cover + those it covers, under the planes that apply
+                    const bool upd = inpl[s] == step;  // updated in place by the previous step
+                    const int ld = max(__ldcg(&acc[s].last_diff), upd ? __ldcg(&acc[s].last_diff_new) : __ldcg(&acc[s].last_diff_in));
+                    const int fe = min(__ldcg(&acc[s].first_empty), upd ? __ldcg(&acc[s].first_empty_new) : __ldcg(&acc[s].first_empty_in));
+                    if (ld < fe)
+                        // every empty position lies right of every diff position: the exact dyadic part followed by ne_cnt
+                        // consecutive `+= epsilon`, evaluated in closed form per binade (fb_add_eps_n)
+                        diff_f = fb_add_eps_n(fb_q26_to_f64(diff_q), bp.eps, ne_cnt);
+                    else
+                        need_replay = true;
+                }
                 const double same_f = fb_q26_to_f64((long long)same_q);
                 const double pv = fb_pvalue_pair(same_f, diff_f, sub, bp.eps, bp.div_factor, div_pow2, inv_div);
+                if (bp.prof && writer && tid == 0) pt[17] += fb_clock_after((unsigned long long)__double_as_longlong(pv)) - tc;  // p-value formed
                 if (v && sub == 0) {
                     sc_same[s] = same_f;
                     sc_diff[s] = diff_f;
@@ -484,13 +539,13 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
                     if (need_replay) replay[atomicAdd(&ms->n_replay, 1)] = s;
                 }
             }
-            __syncthreads();
+            __syncwarp();
             const int n_replay = ms->n_replay;
             if (n_replay) {
                 // ordered replay over the whole read (utils_frags.rs:33-72 in canonical order); reads planes that other
                 // CTAs own, hence the second grid barrier of this step before phase C
                 const uint32_t g0 = ri.gbase + ri.lg0, g1 = ri.gbase + ri.lg1;
-                for (int x = warp; x < n_replay; x += NW) {
+                for (int x = 0; x < n_replay; ++x) {
                     const int s = replay[x];
                     const double diff_f =
                         fb_replay_diff_t<32, true>(bp.fr, g0, g1, ST_MASK(s), ri.lg0, st_hi[s], lut_s, bp.eps, wscr);
@@ -500,11 +555,12 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
                         sc_pv[s] = pv;
                     }
                 }
-                __syncthreads();
-                if (tid == 0) {
+                __syncwarp();
+                if (lane == 0) {
                     ms->n_replay = 0;
                     ms->full_reads = 1;
                 }
+                __syncwarp();
             }
         }
         if (bp.ready) {
@@ -523,14 +579,22 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
         if (warp != 0) {
             long long q0 = 0;
             if (prof1) q0 = fb_clock();
-            if (step + 1 < in.n_reads) prefetch_commit(ri_next, (step + 1) % 3u);
+            const bool fuse = FB_BW_EARLY && step + 1 < in.n_reads;  // there is a next read: it is scored now, one step ahead
+            if (writer) zero_slot((step + 2) % FB_BW_SLOTS, 32, NT - 32);  // last read two steps ago, first written after the next barrier
+            if (step + 1 < in.n_reads) prefetch_commit(ri_next, (step + 1) % FB_BW_SLOTS);
+            if (fuse) {
+                score_states(ri_next, bp.wacc + (uint64_t)((step + 1) % FB_BW_SLOTS) * bp.maxNS, step + 1, true, ri.lg0, ri.lg1);
+            }
             if (prof1) {
                 const long long n_ = fb_clock();
                 pc += n_ - q0;
                 q0 = n_;
             }
+            // warp 0 joins this barrier with the job list (it must not touch the live list / extents the early scoring reads)
             asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
             if (ms->full_reads) fb_grid_barrier(bp.wbar, bar_target += G);
+            if (fuse)  // states updated in place: the next step's p-values take the extremes written by phase C
+                for (int j = tid - 32; j < ms->n_jobs_inplace; j += NT - 32) inpl[jobs[(int)Wm + 1 - j].dst] = step + 1;
             if (prof1) {
                 const long long n_ = fb_clock();
                 pw += n_ - q0;
@@ -555,8 +619,12 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
                     bool act, in_read;
                     ulonglong2 v0, v1;
                     uint32_t pr, al, qb;
+                    uint2 om;  // in place: the group's is-max planes before the update
                 };
                 const uint32_t k = lane & 15u;
+                const bool fuse_c = fuse && pass == 1;
+                BeamWideAcc *accn = bp.wacc + (uint64_t)((step + 1) % FB_BW_SLOTS) * bp.maxNS;
+                const uint32_t c0n = my_first_chunk(ri_next.lg0 / CH);  // this CTA's first chunk of the next read
                 auto c_load = [&](int x, CItem &it) {
                     const int jn = x / nmc, kc = x - jn * nmc;
                     const BeamJob jb = pass == 0 ? jobs[jn] : jobs[(int)Wm + 1 - jn];
@@ -569,11 +637,13 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
                     it.v0 = make_ulonglong2(0ULL, 0ULL);
                     it.v1 = it.v0;
                     it.pr = it.al = it.qb = 0;
+                    it.om = make_uint2(0u, 0u);
                     if (it.act && it.lg <= it.src_hi) {
                         const ulonglong2 *src =
                             reinterpret_cast<const ulonglong2 *>(ST_CNT(it.src) + ((uint64_t)it.lg * 16 + k) * 4);
                         it.v0 = __ldcg(src);
                         it.v1 = __ldcg(src + 1);
+                        if (fuse_c) it.om = __ldcg(ST_MASK(it.src) + it.lg);
                     }
                     if (it.in_read) {
                         const uint32_t g = ri.gbase + (uint32_t)it.lg;
@@ -614,7 +684,65 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
                     const uint32_t b1 = (__ballot_sync(0xFFFFFFFFu, im1) >> sh) & 0xFFFFu;
                     const uint32_t b2 = (__ballot_sync(0xFFFFFFFFu, im2) >> sh) & 0xFFFFu;
                     const uint32_t b3 = (__ballot_sync(0xFFFFFFFFu, im3) >> sh) & 0xFFFFu;
-                    if (it.act && k == 0) ST_MASK(it.dst)[it.lg] = make_uint2(b0 | (b1 << 16), b2 | (b3 << 16));
+                    const uint32_t nmx = b0 | (b1 << 16), nmy = b2 | (b3 << 16);
+                    if (it.act && k == 0) ST_MASK(it.dst)[it.lg] = make_uint2(nmx, nmy);
+                    if (fuse_c) {
+                        // The next read was scored against the OLD planes of this state (early scoring): add what the update
+                        // changes, one lane per cell of the next read in this item's two groups.  same / empty weight /
+                        // empty count take signed deltas (wrapping adds); the extremes under the new planes go to `_new`.
+                        uint32_t w = 0;
+                        int ds = 0, de = 0;  // change of "same" (+1 / -1) and of "empty" (-1: a position can only fill up)
+                        int pe = INT_MAX, pd = -1;  // position if the cell is empty / a diff under the new planes
+                        if (it.act && it.lg >= (int)ri_next.lg0 && it.lg < (int)ri_next.lg1) {
+                            const uint32_t gi = (((uint32_t)it.lg / CH - c0n) / G) * CH + (uint32_t)it.lg % CH;  // staging slot
+                            uint32_t pr, al, qb;
+                            if (gi < STG) {
+                                pr = rpr[gi];
+                                al = ral[gi];
+                                qb = reinterpret_cast<const uint8_t *>(rq)[gi * 16 + k];
+                            } else {
+                                const uint32_t g = ri_next.gbase + (uint32_t)it.lg;
+                                pr = bp.fr.present[g];
+                                al = bp.fr.allele[g];
+                                qb = qual8[(uint64_t)g * 16 + k];
+                            }
+                            if ((pr >> k) & 1u) {
+                                const uint32_t av = ((al >> k) & 1u) | (((al >> (16 + k)) & 1u) << 1);
+                                const uint32_t sh_a = k + 16u * (av & 1u);
+                                const uint32_t sb_o = ((av < 2 ? it.om.x : it.om.y) >> sh_a) & 1u;
+                                const uint32_t sb_n = ((av < 2 ? nmx : nmy) >> sh_a) & 1u;
+                                const uint32_t ao = it.om.x | it.om.y, an = nmx | nmy;
+                                const uint32_t ne_o = ((ao | (ao >> 16)) >> k) & 1u, ne_n = ((an | (an >> 16)) >> k) & 1u;
+                                w = lut_s[qb];
+                                ds = (int)sb_n - (int)sb_o;
+                                de = (int)ne_o - (int)ne_n;
+                                const int pos = it.lg * 16 + (int)k;
+                                if (!ne_n) pe = pos;
+                                if (ne_n && !sb_n) pd = pos;
+                            }
+                        }
+                        if (__any_sync(0xFFFFFFFFu, ds != 0 || de != 0)) {  // weights are at most 2^26: 32 of them fit 32 bits
+                            const uint32_t ps = __reduce_add_sync(0xFFFFFFFFu, ds > 0 ? w : 0u);
+                            const uint32_t ns = __reduce_add_sync(0xFFFFFFFFu, ds < 0 ? w : 0u);
+                            const uint32_t nE = __reduce_add_sync(0xFFFFFFFFu, de < 0 ? w : 0u);
+                            const uint32_t nC = __reduce_add_sync(0xFFFFFFFFu, de < 0 ? 1u : 0u);
+                            if (lane == 0) {
+                                if (ps != ns) atomicAdd(&accn[it.dst].same, (unsigned long long)ps - (unsigned long long)ns);
+                                if (nC) {
+                                    if (nE) atomicAdd(&accn[it.dst].emptyw, 0ULL - (unsigned long long)nE);
+                                    atomicSub(&accn[it.dst].ne_cnt, nC);
+                                }
+                            }
+                        }
+                        if (!bp.eps_safe) {
+                            pe = __reduce_min_sync(0xFFFFFFFFu, pe);
+                            pd = __reduce_max_sync(0xFFFFFFFFu, pd);
+                            if (lane == 0) {
+                                if (pe != INT_MAX) atomicMin(&accn[it.dst].first_empty_new, pe);
+                                if (pd >= 0) atomicMax(&accn[it.dst].last_diff_new, pd);
+                            }
+                        }
+                    }
                 };
                 for (int x = (int)warp - 1; x < total; x += 2 * (NW - 1)) {
                     CItem ia, ib;
@@ -638,7 +766,7 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
 #define FB_BEAM_VERIFIED(x) \
     if (lane == 0) ms->full_reads = 1
 #define FB_BEAM_ARRIVE()                                              \
-    asm volatile("bar.arrive 1, %0;" ::"n"(NT) : "memory");           \
+    asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");             \
     if (ms->full_reads) {                                             \
         fb_grid_barrier(bp.wbar, bar_target += G);                    \
         if (lane == 0) ms->full_reads = 0;                            \
@@ -710,7 +838,6 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
     }
 #undef PROF
 #undef FB_BW_PREFETCH_ONE
-#undef FB_BW_PREFETCH_ISSUE
 #undef ST_CNT
 #undef ST_MASK
 #undef ND_SCORE
