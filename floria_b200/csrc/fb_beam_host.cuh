@@ -185,7 +185,10 @@ static int fb_run_beam(fb_ctx *ctx, Engine &e, const fb_params *prm, const BeamT
                 FB_FAIL(FB_ERR_LIMIT, "k_beam_wide does not fit an SM (%u bytes of shared memory)", L.total);
             }
             // pipelined upload: leave SMs to the k_pack launches that run beside this kernel
-            if (e.df->pipelined) grid_w = std::max(1, grid_w - 32);
+            if (e.df->pipelined) {
+                const char *ps = getenv("FB_PIPE_SMS");
+                grid_w = std::max(1, grid_w - (ps ? std::max(1, atoi(ps)) : 32));
+            }
             if (getenv("FB_BEAM_WIDE_GRID")) grid_w = std::max(1, std::min(grid_w, atoi(getenv("FB_BEAM_WIDE_GRID"))));
         }
         uint8_t *d_scratch = nullptr;

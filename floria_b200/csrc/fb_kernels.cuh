@@ -18,36 +18,64 @@ __global__ void k_pack(uint64_t nnz, uint64_t cell_base, uint64_t n_reads, const
                        unsigned long long *__restrict__ err /* first bad cell + 1, 0 = none */,
                        const uint32_t *__restrict__ rshift /* per read: added to its positions (batched contigs), or NULL */) {
     const uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // index into this launch's arrays
-    if (x >= nnz) return;
-    const uint64_t c = cell_base + x;
-    // read of this cell: last r with row_ptr[r] <= c
-    uint64_t lo = 0, hi = n_reads;  // invariant: row_ptr[lo] <= c < row_ptr[hi]
-    while (hi - lo > 1) {
-        uint64_t mid = (lo + hi) >> 1;
-        if (row_ptr[mid] <= c)
-            lo = mid;
-        else
-            hi = mid;
+    const bool in = x < nnz;
+    const uint32_t lane = threadIdx.x & 31u;
+    // read of a cell: last r with row_ptr[r] <= c.  The CTA's cells are consecutive: two threads search the reads of its
+    // first and last cell over the whole array, everybody else searches between those two (no search at all inside a long read).
+    __shared__ uint64_t r_ends[2];
+    auto find_read = [&](uint64_t c, uint64_t lo, uint64_t hi) {  // invariant: row_ptr[lo] <= c < row_ptr[hi]
+        while (hi - lo > 1) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (row_ptr[mid] <= c)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        return lo;
+    };
+    if (threadIdx.x == 0 || threadIdx.x == 32) {
+        const uint64_t x0 = (uint64_t)blockIdx.x * blockDim.x;
+        const uint64_t xe = threadIdx.x == 0 ? x0 : min(x0 + blockDim.x, nnz) - 1;
+        r_ends[threadIdx.x >> 5] = find_read(cell_base + xe, 0, n_reads);
     }
-    const uint32_t sh = rshift ? rshift[lo] : 0u;
-    const uint32_t p = pos[x] + sh;
-    const uint32_t a = allele[x];
-    // per-cell validation (the per-read checks are done on the host): allele index fits 2 bits, positions strictly
-    // ascending inside [first, last] with the end points present
-    bool bad = a > 3 || p < first[lo] || p > last[lo];
-    if (c > row_ptr[lo] && pos[x - 1] + sh >= p) bad = true;  // (chunks start on read boundaries: x >= 1 here)
-    if (c == row_ptr[lo] && p != first[lo]) bad = true;
-    if (c + 1 == row_ptr[lo + 1] && p != last[lo]) bad = true;
-    if (bad) {
-        atomicMin(err, c + 1);
-        return;
+    __syncthreads();
+    const uint64_t c = cell_base + (in ? x : 0);
+    uint64_t lo = r_ends[0];
+    if (in && r_ends[1] != lo) lo = find_read(c, lo, r_ends[1] + 1);
+    bool ok = in;
+    uint32_t g = 0xFFFFFFFFu - lane, k = 0, abits = 0, q = 0;  // a key of its own for the threads that store nothing
+    if (in) {
+        const uint32_t sh = rshift ? rshift[lo] : 0u;
+        const uint32_t p = pos[x] + sh;
+        const uint32_t a = allele[x];
+        // per-cell validation (the per-read checks are done on the host): allele index fits 2 bits, positions strictly
+        // ascending inside [first, last] with the end points present
+        bool bad = a > 3 || p < first[lo] || p > last[lo];
+        if (c > row_ptr[lo] && pos[x - 1] + sh >= p) bad = true;  // (chunks start on read boundaries: x >= 1 here)
+        if (c == row_ptr[lo] && p != first[lo]) bad = true;
+        if (c + 1 == row_ptr[lo + 1] && p != last[lo]) bad = true;
+        if (bad) {
+            atomicMin(err, c + 1);
+            ok = false;
+        } else {
+            const uint32_t p0 = p - 1u;
+            g = gptr[lo] + ((p0 >> 4) - gstart[lo]);
+            k = p0 & 15u;
+            abits = ((a & 1u) << k) | (((a >> 1) & 1u) << (16 + k));
+            q = qual[x];
+        }
     }
-    uint32_t p0 = p - 1u;
-    uint32_t g = gptr[lo] + ((p0 >> 4) - gstart[lo]);
-    uint32_t k = p0 & 15u;
-    atomicOr(&allele_out[g], ((a & 1u) << k) | (((a >> 1) & 1u) << (16 + k)));
-    atomicOr(&present_out32[g >> 1], 1u << (k + 16u * (g & 1u)));
-    qual_out[(uint64_t)g * 16 + k] = qual[x];
+    // the cells of a group sit on neighbouring lanes (positions ascend inside a read): one atomic per group and warp
+    const unsigned peers = __match_any_sync(0xFFFFFFFFu, g);
+    const uint32_t al_or = __reduce_or_sync(peers, abits);
+    const uint32_t pr_or = __reduce_or_sync(peers, ok ? (1u << k) : 0u);
+    if (ok) {
+        if (lane == (uint32_t)__ffs(peers) - 1u) {
+            atomicOr(&allele_out[g], al_or);
+            atomicOr(&present_out32[g >> 1], pr_or << (16u * (g & 1u)));
+        }
+        qual_out[(uint64_t)g * 16 + k] = (uint8_t)q;
+    }
 }
 
 // pipelined upload: the planes of reads [0, n) are complete
