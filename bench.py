@@ -16,6 +16,8 @@ N > 1 (torchrun, one rank per GPU): BASELINE.json configs[4], the 500-contig met
   library's static LPT queue (fb_lpt_assign), every rank phases its share in one batched call (fb_phase_contigs), rank 0
   gathers the partition records over NCCL inside the timed region.  No data-path collective.  The same workload on one
   GPU is the `shard500` object of the N = 1 line, so value(N) / shard500.value(1) is the strong-scaling speed-up.
+  `shard_blocks` (every N): BASELINE.json configs[3] (2M short reads x 100k SNPs, ploidy 3, one contig) with its BLOCKS
+  dealt to the ranks as contiguous ranges, the reference's other parallel axis; same strong-scaling reading.
 --impl reference : the CPU restatement of the reference path (oracle/, all host threads) on a bounded sample of the
   same workload (the reference itself is Rust and cannot be built in this image; nothing of this repo's CUDA library is
   loaded by this arm).
@@ -440,7 +442,9 @@ def run_shard500(args, torch, dist, rank, world, local_rank, sampler):
     e2e_fn = lambda: m.phase_contigs(pin, blocks, prm)
     timed_steps(resident, args.warmup, torch, flush, after=gather)
     barrier()
+    l0 = int(m.timings(0)["n_launches"])
     ev, out = timed_steps(resident, args.steps, torch, flush, sampler=sampler, after=gather)
+    launches = int(m.timings(0)["n_launches"]) - l0  # this rank's kernels inside the timed region
     barrier()
     timed_steps(e2e_fn, 1, torch, flush, after=gather)
     barrier()
@@ -467,7 +471,65 @@ def run_shard500(args, torch, dist, rank, world, local_rank, sampler):
             "value": cells / (ms / 1e3), "ms_per_step": ms, "cells_per_step": cells, "n_gpus": world,
             "e2e": {"value": cells / (ms2 / 1e3), "unit": "cells/s", "h2d_bytes_per_step": int(io[0].item()),
                     "d2h_bytes_per_step": int(io[1].item()), "ms_per_step": ms2},
-            "contigs_on_rank0": len(mine)}
+            "contigs_on_rank0": len(mine), "gpu_launches": launches}
+
+
+C4 = dict(n_reads=2000000, n_snps=100000, ploidy=3, epsilon=0.01, block_length=500)
+
+
+def run_shard_blocks(args, torch, dist, rank, world, local_rank):
+    """configs[3] (2M paired short reads x 100k SNPs, ploidy 3) as ONE contig whose BLOCKS are sharded over the ranks
+    (the reference's other parallel axis, graph_processing.rs:345-362): every rank holds the contig resident, phases a
+    contiguous range of blocks of equal estimated cost (reads x block incidence) through fb_phase_blocks_resident, and
+    the partition records are gathered on rank 0 inside the timed region."""
+    from floria_b200 import api, default_params, shard, synth
+
+    dev = torch.device("cuda", local_rank)
+    c = synth.config4(1.0)
+    prm = default_params(epsilon=C4["epsilon"], max_ploidy=C4["ploidy"], block_length=C4["block_length"])
+    lo, hi = api.get_range_with_lengths(c.snp_to_genome_pos, C4["block_length"], C4["block_length"] // 3, 0.0005)
+    lo, hi = np.asarray(lo), np.asarray(hi)
+    fr = c.frags
+    # reads per block from the sorted end points (cost estimate), then `world` contiguous ranges of equal cost
+    fs, ls = np.sort(fr.first), np.sort(fr.last)
+    per_block = np.searchsorted(fs, hi, side="right") - np.searchsorted(ls, lo, side="left")
+    cum = np.concatenate([[0], np.cumsum(per_block.astype(np.float64))])
+    cuts = [int(np.searchsorted(cum, cum[-1] * r / world)) for r in range(world + 1)]
+    cuts[0], cuts[-1] = 0, len(lo)
+    a, b = cuts[rank], cuts[rank + 1]
+    ctx = api.Context(local_rank)
+    d = ctx.upload(fr)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def gather(res):
+        if world == 1:
+            return
+        uids = np.arange(a, b, dtype=np.int64)
+        shard.gather_records(uids, res.read_ptr.astype(np.int64), res.read_ids, res.hap, res.best_ploidy, dev, dst=0,
+                             lazy=True)
+
+    fn = lambda: ctx.phase_blocks_resident(d, lo[a:b], hi[a:b], prm)
+    timed_steps(fn, args.warmup, torch, flush, after=gather)
+    if world > 1:
+        dist.barrier()
+    ev, res = timed_steps(fn, args.steps, torch, flush, after=gather)
+    tot = torch.tensor([sum(ev)], device=dev, dtype=torch.float64)
+    cl = torch.tensor([float(res.cells)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cl, op=dist.ReduceOp.SUM)
+    ctx.close()
+    if rank != 0:
+        return None
+    ms = float(tot[0].item()) / args.steps
+    cells = float(cl[0].item())
+    return {"config": {"workload": "configs[3]: synthetic short-read, 2M paired frags x 100k SNPs, ploidy 3, one contig; "
+                                   "its %d blocks (-l 500) dealt to the ranks as contiguous ranges of equal estimated cost"
+                                   % len(lo), "n_reads": int(fr.n_reads), "n_snps": C4["n_snps"],
+                       "max_ploidy": C4["ploidy"], "epsilon": C4["epsilon"], "n_blocks": int(len(lo)),
+                       "parallelism": "block ranges x %d" % world},
+            "value": cells / (ms / 1e3), "unit": "cells/s", "ms_per_step": ms, "cells_per_step": cells, "n_gpus": world,
+            "scaling": "strong", "blocks_on_rank0": int(b - a)}
 
 
 def run_ours(args):
@@ -508,16 +570,19 @@ def run_ours(args):
         if not args.no_secondary:
             s5 = run_shard500(args, torch, dist, rank, world, local_rank, None)
             line["shard500"] = s5
+            line["shard_blocks"] = run_shard_blocks(args, torch, dist, rank, world, local_rank)
             line["note"] = ("N=1 headline is configs[2] (one block: does not shard).  The multi-GPU workload is "
                             "configs[4] (`shard500`, strong scaling): compare value of the N>1 lines with "
                             "shard500.value of this line.")
         print(json.dumps(line), flush=True)
     else:
         s5 = run_shard500(args, torch, dist, rank, world, local_rank, sampler)
+        sb = None if args.no_secondary else run_shard_blocks(args, torch, dist, rank, world, local_rank)
         if rank == 0:
             clocks = sampler.result() if sampler else None
             line = dict(base, value=s5["value"], ms_per_step=s5["ms_per_step"], scaling="strong", config=s5["config"],
-                        clocks=clocks, e2e=s5["e2e"], cells_per_step=s5["cells_per_step"],
+                        clocks=clocks, e2e=s5["e2e"], cells_per_step=s5["cells_per_step"], shard_blocks=sb,
+                        gpu_launches=s5["gpu_launches"],
                         note="ONE fixed workload (configs[4], 500 contigs) sharded over the ranks; the 1-GPU value of "
                              "the same workload is shard500.value of the N=1 line")
             sys.stdout.flush()

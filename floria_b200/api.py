@@ -222,6 +222,12 @@ class MultiContext:
         except Exception:
             pass
 
+    def timings(self, i=0):
+        """fb_last_timings of device i's context (launch counters, per-kernel times of the last call)"""
+        t = FbTimings()
+        self.L.fb_last_timings(C.c_void_p(self.L.fb_multi_ctx(self.h, i)), C.byref(t))
+        return {k: getattr(t, k) for k, _ in FbTimings._fields_}
+
     def _chk(self, rc):
         if rc != 0:
             raise FloriaB200Error(f"floria_b200 error {rc}: " + self.L.fb_multi_last_error(self.h).decode())

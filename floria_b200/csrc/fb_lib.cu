@@ -829,7 +829,11 @@ int fb_phase_blocks_resident(fb_ctx *ctx, const fb_dfrags *df, uint64_t n_blocks
     float download_ms = 0.f;
     uint64_t sweep_cells_all = 0, hist_cells_all = 0;
     for (uint32_t p_lo = 1; p_lo <= mp && n_running; ) {
-        const uint32_t p_hi = p_lo == 1 ? wave0 : p_lo;  // inclusive
+        // later waves: ONE more ploidy (FB_PLOIDY_STEP = 2 / 3 measured slower at every share size of configs[4]:
+        // profiles/README.md)
+        uint32_t wstep = 1u;
+        if (const char *se = getenv("FB_PLOIDY_STEP")) wstep = (uint32_t)std::max(1, atoi(se));
+        const uint32_t p_hi = p_lo == 1 ? wave0 : std::min(mp, p_lo + wstep - 1);  // inclusive
         Engine e;
         e.ctx = ctx;
         e.df = df;

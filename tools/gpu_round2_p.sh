@@ -1,20 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-export FB_REQUIRE_GPU=1
-rm -f gpurun_out/pipe_sms.log
-timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -5 > gpurun_out/all_tests.log
-for n in 8 16 32; do
-  FB_PIPE_SMS=$n timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu --no-secondary > gpurun_out/bp.json 2> gpurun_out/bp.err
-  python - <<PY >> gpurun_out/pipe_sms.log
+timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e > gpurun_out/bq.json 2> gpurun_out/bq.err
+tail -3 gpurun_out/bq.err
+python - <<'PY'
 import json
-d = json.load(open("gpurun_out/bp.json"))
-print("FB_PIPE_SMS=$n resident", round(d["ms_per_step"],1), "e2e", round(d["e2e"]["ms_per_step"],1), d["e2e"]["same_result"])
+d = json.load(open("gpurun_out/bq.json"))
+print("c3", d["ms_per_step"], "| c1", d["configs1"]["ms_per_step"], "| shard500", d["shard500"]["ms_per_step"], d["shard500"]["e2e"]["ms_per_step"], d["shard500"].get("gpu_launches"), "| shard_blocks", d["shard_blocks"])
 PY
-done
-FB_PIPELINE_UPLOAD=0 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu --no-secondary > gpurun_out/bp.json 2> gpurun_out/bp.err
-python - <<PY >> gpurun_out/pipe_sms.log
-import json
-d = json.load(open("gpurun_out/bp.json"))
-print("no pipeline: resident", round(d["ms_per_step"],1), "e2e", round(d["e2e"]["ms_per_step"],1), d["e2e"]["same_result"])
-PY
-cat gpurun_out/all_tests.log gpurun_out/pipe_sms.log
+for t in 0 1; do echo "FB_SWEEP_TMA=$t"; FB_SWEEP_TMA=$t timeout 300 python tools/c3_once.py 100000 50000 4 5 2>&1 | tail -1; done
