@@ -236,10 +236,10 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
             }
         }
         long long pt[24] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-        long long tc = fb_clock();
+        long long tc = clock64();
 #define PROF(i)                         \
     if (bp.prof && tid == 0) {          \
-        long long n_ = fb_clock();       \
+        long long n_ = clock64();       \
         pt[i] += n_ - tc;               \
         tc = n_;                        \
     }
@@ -296,7 +296,6 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
                 rx_next = rextra[step + 1];
             }
             const uint32_t cur_start = rx.first0;
-            if (bp.prof && tid == 0) pt[22] += fb_clock() - tc;  // step top reached
             const uint32_t g0 = ri.gbase + ri.lg0, g1 = ri.gbase + ri.lg1;  // global groups of the read
             const int par = (int)(step & 1u);
             const bool staged = (ri.lg1 - ri.lg0) <= FB_BEAM_RG;
@@ -331,7 +330,7 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
                     continue;
                 }
                 long long q0 = 0;
-                if (bp.prof && tid == 0) q0 = fb_clock();
+                if (bp.prof && tid == 0) q0 = clock64();
                 const uint2 *mk = ST_MASK(s);
                 unsigned long long total = 0, same = 0, emptyw = 0;
                 uint32_t ne_cnt = 0;
@@ -368,13 +367,13 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
                     const uint32_t db = pr & ne & ~sb & 0xFFFFu;
                     if (db) last_diff = max(last_diff, (int)(lg * 16u) + 31 - __clz(db));
                 }
-                if (bp.prof && tid == 0) { long long n_ = fb_clock(); pt[16] += n_ - q0; q0 = n_; }
+                if (bp.prof && tid == 0) { long long n_ = clock64(); pt[16] += n_ - q0; q0 = n_; }
                 total = fb_warp_sum_u64(total);
                 same = fb_warp_sum_u64(same);
                 emptyw = fb_warp_sum_u64(emptyw);
                 ne_cnt = fb_warp_sum_u32(ne_cnt);
                 const long long diff_q = (long long)(total - same - emptyw);
-                if (bp.prof && tid == 0) { long long n_ = fb_clock(); pt[17] += n_ - q0; q0 = n_; }
+                if (bp.prof && tid == 0) { long long n_ = clock64(); pt[17] += n_ - q0; q0 = n_; }
                 double diff_f;
                 if (ne_cnt == 0)
                     diff_f = fb_q26_to_f64(diff_q);
@@ -387,7 +386,7 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
                     diff_f = fb_add_eps_n(fb_q26_to_f64(diff_q), bp.eps, ne_cnt);
                 else
                     diff_f = fb_replay_diff(bp.fr, g0, g1, mk, ri.lg0, hi, lut_s, bp.eps, wscr);
-                if (bp.prof && tid == 0) { long long n_ = fb_clock(); pt[18] += n_ - q0 + (long long)(diff_f * 0.0); q0 = n_; }
+                if (bp.prof && tid == 0) { long long n_ = clock64(); pt[18] += n_ - q0 + (long long)(diff_f * 0.0); q0 = n_; }
                 {
                     // stable_binom_cdf_p_rev (utils_frags.rs:211-248) with its two log terms evaluated on two lanes; the
                     // operations and their order are those of fb_stable_binom_cdf_p_rev (global_clustering.rs:81-88).
@@ -414,10 +413,9 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
                         sc_diff[s] = diff_f;
                         sc_pv[s] = 1.0 * pvs;
                     }
-                    if (bp.prof && tid == 0) { long long n_ = fb_clock(); pt[19] += n_ - q0 + (long long)(pvs * 0.0); q0 = n_; }
+                    if (bp.prof && tid == 0) { long long n_ = clock64(); pt[19] += n_ - q0 + (long long)(pvs * 0.0); q0 = n_; }
                 }
             }
-            if (bp.prof && tid == 0) pt[3] += fb_clock() - tc;  // warp 0 done with its own tasks
             __syncthreads();
             PROF(0)
 

@@ -27,10 +27,7 @@ static void fb_beam_split(const fb_ctx *ctx, const Engine &e, std::vector<int> &
     for (int i = 0; i < e.n_inst(); ++i) {
         const InstDev &in = e.inst[i];
         if (in.ploidy < 2 || in.n_reads == 0) continue;  // ploidy 1: every read lands in haplotype 0
-        uint64_t g = 0;
-        const std::vector<RInfo> &hr = e.host_rinfo();
-        for (uint32_t r = 0; r < in.n_reads; ++r) g += hr[in.read_off + r].lg1 - hr[in.read_off + r].lg0;
-        const double g_mean = (double)g / in.n_reads;
+        const double g_mean = (double)e.blocks[in.block].groups / in.n_reads;
         if (forced == 1 || (forced != 0 && g_mean >= 192.0)) {
             cand.push_back(i);
             g_sum += g_mean;
@@ -280,8 +277,6 @@ static int fb_run_beam(fb_ctx *ctx, Engine &e, const fb_params *prm, const BeamT
             const double steps = (double)std::max<unsigned long long>(h[12], 1);
             fprintf(stderr, "[k_beam prof] scoring warp 0, cycles/step: loop %.0f | reductions %.0f | diff_f %.0f | p-value %.0f\n",
                     h[16] / steps, h[17] / steps, h[18] / steps, h[19] / steps);
-            fprintf(stderr, "[k_beam prof] warp 0: step top reached %.0f cycles after the end-of-step barrier, own phase-1 task done at %.0f\n",
-                    h[22] / steps, h[3] / steps);
             fprintf(stderr,
                     "[k_beam prof] %.3f ms (both kernels), %d instances on %llu CTAs, %.0f steps; cycles/step: phase1(score) %.0f | warp0: lse %.0f "
                     "compact+fold+dups+classes %.0f heap %.0f nextgen %.0f | phase3(copy) %.0f | children/step %.1f survivors/step %.1f "

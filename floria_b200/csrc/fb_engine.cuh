@@ -143,6 +143,7 @@ struct BlockPlan {
     uint32_t n_reads = 0;
     uint32_t ag0 = 0, ng = 0;
     uint64_t nnz = 0;
+    uint64_t groups = 0;  // sum over the reads of their 16-SNP groups (the beam kernels are chosen by the mean per read)
     uint32_t read_off = 0;
 };
 
@@ -157,6 +158,7 @@ static void fb_plan_block(const fb_dfrags *df, std::vector<uint32_t> &&reads, Pl
     b.reads = std::move(reads);
     b.n_reads = (uint32_t)b.reads.size();
     b.nnz = 0;
+    b.groups = 0;
     uint32_t gmin = 0xFFFFFFFFu, gmax = 0;
     for (uint32_t r : b.reads) {
         uint32_t g0 = df->h_gstart[r];
@@ -164,6 +166,7 @@ static void fb_plan_block(const fb_dfrags *df, std::vector<uint32_t> &&reads, Pl
         gmin = std::min(gmin, g0);
         gmax = std::max(gmax, g1);
         b.nnz += df->h_nnz[r];
+        b.groups += df->h_gnum[r];
     }
     if (b.reads.empty()) {
         gmin = 0;
@@ -294,6 +297,7 @@ struct Engine {
         b.ag0 = plan.ag0;
         b.ng = plan.ng;
         b.nnz = plan.nnz;
+        b.groups = plan.groups;
         b.read_off = read_off;
         blocks.push_back(std::move(b));
         return (int)blocks.size() - 1;

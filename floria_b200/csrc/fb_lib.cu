@@ -740,7 +740,7 @@ int fb_phase_blocks_resident(fb_ctx *ctx, const fb_dfrags *df, uint64_t n_blocks
     std::vector<PlannedBlock> planned(n_blocks);
     {
         const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-        const uint64_t nt = std::max<uint64_t>(1, std::min<uint64_t>(std::min<unsigned>(4u, hw), n_blocks / 256));
+        const uint64_t nt = std::max<uint64_t>(1, std::min<uint64_t>(std::min<unsigned>(8u, hw), n_blocks / 256));
         auto work = [&](uint64_t t) {
             std::vector<uint32_t> reads;
             for (uint64_t j = n_blocks * t / nt; j < n_blocks * (t + 1) / nt; ++j) {

@@ -1,10 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e > gpurun_out/bq.json 2> gpurun_out/bq.err
-tail -3 gpurun_out/bq.err
-python - <<'PY'
-import json
-d = json.load(open("gpurun_out/bq.json"))
-print("c3", d["ms_per_step"], "| c1", d["configs1"]["ms_per_step"], "| shard500", d["shard500"]["ms_per_step"], d["shard500"]["e2e"]["ms_per_step"], d["shard500"].get("gpu_launches"), "| shard_blocks", d["shard_blocks"])
-PY
-for t in 0 1; do echo "FB_SWEEP_TMA=$t"; FB_SWEEP_TMA=$t timeout 300 python tools/c3_once.py 100000 50000 4 5 2>&1 | tail -1; done
+export FB_REQUIRE_GPU=1
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_multi.py tests/test_gpu_baseline_sizes.py -x -q -m gpu 2>&1 | tail -3 > gpurun_out/ab3.log
+FB_HOST_PROF=1 timeout 600 python tools/share_one.py 1 0 2 2>&1 | tail -7 >> gpurun_out/ab3.log
+timeout 600 python tools/share_one.py 8 3 3 2>&1 | tail -1 >> gpurun_out/ab3.log
+cat gpurun_out/ab3.log
