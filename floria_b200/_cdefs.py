@@ -169,3 +169,21 @@ class Parts:
         self.read_ids = np.ctypeslib.as_array(r.read_ids, (max(tot, 1),))[:tot].copy()
         self.range_lo = np.ctypeslib.as_array(r.range_lo, (max(n, 1),))[:n].copy()
         self.range_hi = np.ctypeslib.as_array(r.range_hi, (max(n, 1),))[:n].copy()
+
+
+class FbReaderOptions(C.Structure):
+    _fields_ = [("mapq_cutoff", C.c_uint32), ("use_supp_aln", C.c_uint32), ("supp_aln_dist_cutoff", C.c_int64)]
+
+
+class FbFragSet(C.Structure):
+    _fields_ = [
+        ("frags", FbFrags),
+        ("n_snps", C.c_uint64),
+        ("snp_to_genome_pos", u64p),
+        ("n_records", C.c_uint64),
+        ("n_passed", C.c_uint64),
+        ("n_without_snps", C.c_uint64),
+        ("read_len_p66", C.c_uint32),
+        ("_pad", C.c_uint32),
+        ("contig", C.c_char * 256),
+    ]

@@ -9,7 +9,7 @@ import os
 
 import numpy as np
 
-from ._cdefs import (
+from ._cdefs import (FbReaderOptions, FbFragSet, 
     BlockResults,
     FbBlockPhase,
     FbBlockResults,
@@ -42,6 +42,7 @@ EXPORTS = [
     "fb_update_hap_graph", "fb_process_reads_for_final_parts_resident", "fb_get_hapq_resident",
     "fb_update_hap_graph_resident",
 ]
+READER_EXPORTS = ["fb_reader_options_default", "fb_read_frags", "fb_free_frag_set", "fb_reader_last_error"]  # floria_b200_reader.h
 
 _lib = None
 
@@ -68,6 +69,11 @@ def load_library():
     L.fb_stream.restype = C.c_void_p
     L.fb_stream.argtypes = [C.c_void_p]
     L.fb_last_timings.argtypes = [C.c_void_p, C.POINTER(FbTimings)]
+    L.fb_reader_options_default.argtypes = [C.POINTER(FbReaderOptions)]
+    L.fb_read_frags.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(FbReaderOptions),
+                                C.POINTER(C.POINTER(FbFragSet))]
+    L.fb_free_frag_set.argtypes = [C.POINTER(FbFragSet)]
+    L.fb_reader_last_error.restype = C.c_char_p
     L.fb_frags_upload.argtypes = [C.c_void_p, C.POINTER(FbFrags), C.POINTER(C.c_void_p)]
     L.fb_frags_free.argtypes = [C.c_void_p, C.c_void_p]
     L.fb_dfrags_bytes.restype = C.c_uint64
@@ -164,6 +170,35 @@ def find_reads_in_interval(start, end, frags):
     n = L.fb_find_reads_in_interval(start, end, frags.n_reads, ptr(frags.first, u32p), ptr(frags.last, u32p),
                                     ptr(out, u32p), len(out))
     return out[:n].copy()
+
+
+def read_frags(bam_path, vcf_path, contig=None, mapq_cutoff=15, use_supp_aln=True, supp_aln_dist_cutoff=40000):
+    """fb_read_frags (include/floria_b200_reader.h): BAM + VCF -> (Frags in Frag::cmp order, snp_to_genome_pos, info).
+    Host-only; restates get_vcf_profile / alignment_passed_check / frag_from_record / combine_frags of file_reader.rs."""
+    from .frags import Frags
+
+    L = load_library()
+    o = FbReaderOptions()
+    L.fb_reader_options_default(C.byref(o))
+    o.mapq_cutoff, o.use_supp_aln, o.supp_aln_dist_cutoff = int(mapq_cutoff), int(bool(use_supp_aln)), int(supp_aln_dist_cutoff)
+    out = C.POINTER(FbFragSet)()
+    rc = L.fb_read_frags(os.fsencode(bam_path), os.fsencode(vcf_path), contig.encode() if contig else None, C.byref(o),
+                         C.byref(out))
+    if rc != 0:
+        raise FloriaB200Error(f"fb_read_frags rc={rc}: {L.fb_reader_last_error().decode()}")
+    try:
+        s = out.contents
+        f = s.frags
+        n, nnz = int(f.n_reads), int(f.nnz)
+        take = lambda p, cnt, dt: np.ctypeslib.as_array(p, shape=(max(cnt, 1),))[:cnt].astype(dt, copy=True)
+        fr = Frags(take(f.row_ptr, n + 1, np.uint64), take(f.pos, nnz, np.uint32), take(f.allele, nnz, np.uint8),
+                   take(f.qual, nnz, np.uint8), take(f.first, n, np.uint32), take(f.last, n, np.uint32))
+        g2p = take(s.snp_to_genome_pos, int(s.n_snps), np.uint64)
+        info = {"contig": s.contig.decode(), "n_records": int(s.n_records), "n_passed": int(s.n_passed),
+                "n_without_snps": int(s.n_without_snps), "read_len_p66": int(s.read_len_p66)}
+    finally:
+        L.fb_free_frag_set(out)
+    return fr, g2p, info
 
 
 def contig_cost(frags, n_blocks):

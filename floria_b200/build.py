@@ -15,14 +15,15 @@ FLAGS = [
 
 def sources():
     """the translation units: compiled to objects in parallel, then linked into one shared library"""
-    return [os.path.join(CSRC, f) for f in ("fb_lib.cu", "fb_beam_tu.cu", "fb_beam_wide_tu.cu")]
+    return [os.path.join(CSRC, f) for f in ("fb_lib.cu", "fb_beam_tu.cu", "fb_beam_wide_tu.cu", "fb_reader.cpp")]
 
 
 def stale():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "floria_b200.h")]
+    inc = os.path.join(HERE, "..", "include")
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(inc, f) for f in os.listdir(inc)]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -31,7 +32,7 @@ def build(force=False, verbose=False):
         return OUT
     objs, procs = [], []
     for src in sources():
-        obj = os.path.join(HERE, os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(HERE, os.path.splitext(os.path.basename(src))[0] + ".o")
         objs.append(obj)
         procs.append(subprocess.Popen([NVCC] + FLAGS + ["-c", "-o", obj, src], stdout=subprocess.PIPE,
                                       stderr=subprocess.PIPE, text=True))
@@ -41,7 +42,7 @@ def build(force=False, verbose=False):
         log += out + err
         failed |= p.returncode != 0
     if not failed:
-        res = subprocess.run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-pthread", "-o", OUT] + objs,
+        res = subprocess.run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-pthread", "-o", OUT] + objs + ["-lz"],
                              capture_output=True, text=True)
         log += res.stdout + res.stderr
         failed = res.returncode != 0
