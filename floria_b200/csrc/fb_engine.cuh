@@ -626,6 +626,11 @@ struct Engine {
         if ((rc = launch_hist(0, 1, 0))) return rc;
         if ((rc = launch_mec(0, 0))) return rc;
         if ((rc = launch_accept(1, 0, max_iters))) return rc;
+        // The host learns one round LATE whether any instance is still iterating: round `it` is queued before the count of
+        // round it - 1 is read, so the device never idles between rounds (local_clustering.rs:85-129 runs up to
+        // NUM_ITER_OPTIMIZE rounds per instance; an instance that has stopped is skipped by every kernel, so the one
+        // surplus round after the last instance stops changes nothing).
+        cudaEvent_t ev_prev = nullptr;
         for (uint32_t it = 0; it < max_iters; ++it) {
             if ((rc = launch_sweep(sweep_args(FB_SWEEP_MOVES)))) return rc;
             if ((rc = launch_select())) return rc;
@@ -633,9 +638,13 @@ struct Engine {
             if ((rc = launch_mec(1, 1))) return rc;
             FB_CK(cudaMemsetAsync(ctx->d_n_active, 0, sizeof(int), ctx->stream));
             if ((rc = launch_accept(0, it, max_iters))) return rc;
-            FB_CK(cudaMemcpyAsync(ctx->h_n_active, ctx->d_n_active, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-            FB_CK(cudaStreamSynchronize(ctx->stream));
-            if (*ctx->h_n_active == 0) break;
+            FB_CK(cudaMemcpyAsync(ctx->h_n_active + (it & 1u), ctx->d_n_active, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            cudaEvent_t ev = fb_event(ctx);
+            if (ev_prev) {
+                FB_CK(cudaEventSynchronize(ev_prev));
+                if (ctx->h_n_active[(it - 1) & 1u] == 0) break;
+            }
+            ev_prev = ev;
         }
         return FB_OK;
     }

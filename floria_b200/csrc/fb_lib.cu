@@ -66,7 +66,7 @@ int fb_init(int device, fb_ctx **out) {
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreate(&ctx->stream)) != cudaSuccess ||
         (e = cudaMalloc((void **)&ctx->d_lut, 256 * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMalloc((void **)&ctx->d_n_active, sizeof(int))) != cudaSuccess ||
-        (e = cudaMallocHost((void **)&ctx->h_n_active, sizeof(int))) != cudaSuccess) {
+        (e = cudaMallocHost((void **)&ctx->h_n_active, 2 * sizeof(int))) != cudaSuccess) {
         g_init_err = std::string("fb_init: ") + cudaGetErrorString(e);
         delete ctx;
         return FB_ERR_CUDA;
@@ -740,7 +740,7 @@ int fb_phase_blocks_resident(fb_ctx *ctx, const fb_dfrags *df, uint64_t n_blocks
     std::vector<PlannedBlock> planned(n_blocks);
     {
         const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-        const uint64_t nt = std::max<uint64_t>(1, std::min<uint64_t>(std::min<unsigned>(8u, hw), n_blocks / 256));
+        const uint64_t nt = std::max<uint64_t>(1, std::min<uint64_t>(std::min<unsigned>(8u, hw), n_blocks / 8));
         auto work = [&](uint64_t t) {
             std::vector<uint32_t> reads;
             for (uint64_t j = n_blocks * t / nt; j < n_blocks * (t + 1) / nt; ++j) {
