@@ -413,7 +413,10 @@ __device__ __forceinline__ void fb_tab_add(uint32_t *lo, uint32_t *hi, uint32_t 
     }
 }
 
-__global__ void __launch_bounds__(FB_HIST_THREADS, 2) k_hist(HistArgs a) {
+#ifndef FB_HIST_MIN_CTAS
+#define FB_HIST_MIN_CTAS 2  // three resident CTAs (85 registers) were measured: profiles/README.md
+#endif
+__global__ void __launch_bounds__(FB_HIST_THREADS, FB_HIST_MIN_CTAS) k_hist(HistArgs a) {
     __shared__ uint32_t lut_s[256];
     __shared__ uint4 s_list[FB_HIST_LIST];
     extern __shared__ __align__(128) uint8_t hist_dyn[];
