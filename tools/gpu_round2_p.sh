@@ -1,10 +1,12 @@
 #!/bin/bash
 mkdir -p gpurun_out
-rm -f gpurun_out/wave.log
-for cfg in "3 1" "4 2" "4 1" "2 2" "5 1"; do
-  set -- $cfg
-  echo "== FB_PLOIDY_WAVE=$1 FB_PLOIDY_STEP=$2" >> gpurun_out/wave.log
-  FB_PLOIDY_WAVE=$1 FB_PLOIDY_STEP=$2 timeout 600 python tools/share_one.py 8 3 2 2>&1 | tail -1 | cut -c1-120 >> gpurun_out/wave.log
-  FB_PLOIDY_WAVE=$1 FB_PLOIDY_STEP=$2 timeout 600 python tools/share_one.py 1 0 2 2>&1 | tail -1 | cut -c1-120 >> gpurun_out/wave.log
+export FB_REQUIRE_GPU=1
+rm -f gpurun_out/tiny.log
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "cta or staging" 2>&1 | tail -4 >> gpurun_out/tiny.log
+FB_BEAM_CTA=64 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_multi.py tests/test_gpu_baseline_sizes.py -x -q -m gpu 2>&1 | tail -4 >> gpurun_out/tiny.log
+for cta in 128 64; do
+  echo "== FB_BEAM_CTA=$cta" >> gpurun_out/tiny.log
+  FB_BEAM_CTA=$cta FB_HOST_PROF=1 timeout 600 python tools/share_one.py 8 3 2 2>&1 | grep "run_beam\|world" | tail -5 | cut -c1-150 >> gpurun_out/tiny.log
+  FB_BEAM_CTA=$cta timeout 600 python tools/share_one.py 1 0 2 2>&1 | tail -1 | cut -c1-150 >> gpurun_out/tiny.log
 done
-cat gpurun_out/wave.log
+cat gpurun_out/tiny.log
