@@ -133,12 +133,19 @@ static int fb_run_beam(fb_ctx *ctx, Engine &e, const fb_params *prm, const BeamT
             cleanup();
             FB_FAIL(FB_ERR_LIMIT, "too many haplotype states (%u)", maxNS);
         }
-        if (kind == 0)  // largest first: the queue drains evenly
+        if (kind == 0) {
+            // Largest first, so that the queue drains evenly; and one ploidy after the other (highest first): every ploidy is
+            // its own instantiation of the kernel body, a step's instructions (~30 KB) just fit the SM's 32 KB instruction
+            // cache, and CTAs of different ploidies sharing an SM evict each other's code (ncu: 1.4 no_instruction stalls per
+            // issue in a mixed launch against 0.45 in a single-ploidy one).  FB_BEAM_MIXED=1 restores the pure cost order.
+            const bool mixed = getenv("FB_BEAM_MIXED") && atoi(getenv("FB_BEAM_MIXED")) != 0;
             std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+                if (!mixed && e.inst[a].ploidy != e.inst[b].ploidy) return e.inst[a].ploidy > e.inst[b].ploidy;
                 const uint64_t ca = e.blocks[e.inst[a].block].nnz * e.inst[a].ploidy;
                 const uint64_t cb = e.blocks[e.inst[b].block].nnz * e.inst[b].ploidy;
                 return ca > cb;
             });
+        }
         BeamSmem L;
         L.layout(maxP, maxW, maxNS);
         if (L.total > 200 * 1024) {
