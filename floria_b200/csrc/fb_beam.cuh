@@ -49,35 +49,6 @@ struct BeamTapDev {
     unsigned long long cap;
 };
 
-struct BeamParams {
-    DFragsDev fr;
-    const InstDev *inst;
-    const RInfo *rinfo;
-    const RExtra *rextra;
-    const uint32_t *lut;
-    const int *order;  // instance indices to run, largest first
-    int n_work;
-    int *work_counter;
-    uint8_t *assign_out;  // engine assign buffer 0
-    double eps, div_factor, cutoff;
-    int eps_safe;
-    uint32_t B;           // max_number_solns
-    uint32_t maxP, maxW, maxNS;
-    uint8_t *scratch;     // per-CTA slots
-    uint64_t slot_bytes;  // pool + history
-    uint64_t hist_off;    // offset of the history array inside a slot
-    unsigned long long *cells_out;  // [n_inst]
-    double *best_out;               // [n_inst]
-    unsigned long long *tapn_out;   // [n_inst]
-    BeamTapDev tap;                 // only meaningful for single-instance calls
-    unsigned long long *prof;       // optional [8] cycle counters per phase (FB_BEAM_PROF=1), else NULL
-    // k_beam_wide only (fb_beam_wide.cuh): global workspace of the grid-wide reductions and the grid barrier
-    struct BeamWideAcc *wacc;        // [3][maxNS] per-state partial sums of a step (three step slots)
-    struct BeamWideStep *wstep;      // [3] per-read sums of a step
-    unsigned long long *wbar;        // monotonic arrival counter of the grid barrier
-    const unsigned int *ready;       // pipelined upload: number of leading reads whose planes are packed (NULL: all)
-};
-
 // shared-memory carve-up (same arithmetic on host and device)
 struct BeamSmem {
     uint32_t off_nd_score, off_nd_err, off_nd_ref, off_st_hash, off_sc_same, off_sc_diff, off_st_hi, off_st_mark,
@@ -127,6 +98,37 @@ struct BeamSmem {
     }
 };
 
+struct BeamParams {
+    DFragsDev fr;
+    const InstDev *inst;
+    const RInfo *rinfo;
+    const RExtra *rextra;
+    const uint32_t *lut;
+    const int *order;  // instance indices to run, largest first
+    int n_work;
+    int *work_counter;
+    uint8_t *assign_out;  // engine assign buffer 0
+    double eps, div_factor, cutoff;
+    int eps_safe;
+    uint32_t B;           // max_number_solns
+    uint32_t maxP, maxW, maxNS;
+    BeamSmem L;                      // the shared-memory carve-up for (maxP, maxW, maxNS), computed once on the host
+    uint8_t *scratch;     // per-CTA slots
+    uint64_t slot_bytes;  // pool + history
+    uint64_t hist_off;    // offset of the history array inside a slot
+    unsigned long long *cells_out;  // [n_inst]
+    double *best_out;               // [n_inst]
+    unsigned long long *tapn_out;   // [n_inst]
+    BeamTapDev tap;                 // only meaningful for single-instance calls
+    unsigned long long *prof;       // optional [8] cycle counters per phase (FB_BEAM_PROF=1), else NULL
+    // k_beam_wide only (fb_beam_wide.cuh): global workspace of the grid-wide reductions and the grid barrier
+    struct BeamWideAcc *wacc;        // [3][maxNS] per-state partial sums of a step (three step slots)
+    struct BeamWideStep *wstep;      // [3] per-read sums of a step
+    unsigned long long *wbar;        // monotonic arrival counter of the grid barrier
+    const unsigned int *ready;       // pipelined upload: number of leading reads whose planes are packed (NULL: all)
+};
+
+
 // host entry points of the beam translation unit (fb_beam_tu.cu): the kernel is compiled on its own, in parallel with
 // the rest of the library
 int fb_beam_occupancy(int threads, size_t smem_bytes, int *blocks_per_sm);
@@ -157,8 +159,7 @@ __device__ __noinline__ void fb_beam_instance(const BeamParams &bp, const int ii
     constexpr int NW = NT / 32;  // warps of the CTA
     const int tid = threadIdx.x;
     const uint32_t lane = tid & 31, warp = tid >> 5;
-    BeamSmem L;
-    L.layout(bp.maxP, bp.maxW, bp.maxNS);
+    const BeamSmem &L = bp.L;
     double *nd_score = reinterpret_cast<double *>(smem + L.off_nd_score);     // [2][W]
     double *nd_err = reinterpret_cast<double *>(smem + L.off_nd_err);         // [2][W][P]
     uint16_t *nd_ref = reinterpret_cast<uint16_t *>(smem + L.off_nd_ref);     // [2][W][P]
@@ -579,8 +580,7 @@ __global__ void __launch_bounds__(NT, NT == FB_BEAM_THREADS ? 1 : 3) k_beam(Beam
     __shared__ int s_work;
     const int tid = threadIdx.x;
     {
-        BeamSmem L;
-        L.layout(bp.maxP, bp.maxW, bp.maxNS);
+        const BeamSmem &L = bp.L;
         uint32_t *lut_s = reinterpret_cast<uint32_t *>(smem + L.off_lut);
         for (int i = tid; i < 256; i += NT) lut_s[i] = bp.lut[i];
     }

@@ -233,6 +233,7 @@ static int fb_run_beam(fb_ctx *ctx, Engine &e, const fb_params *prm, const BeamT
         bp.maxP = maxP;
         bp.maxW = maxW;
         bp.maxNS = maxNS;
+        bp.L = L;
         bp.scratch = d_scratch;
         bp.slot_bytes = slot_bytes;
         bp.hist_off = pool_bytes;

@@ -124,8 +124,7 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
     const uint32_t lane = tid & 31, warp = tid >> 5;
     const uint32_t G = gridDim.x, cta = blockIdx.x;
     const bool writer = cta == 0;
-    BeamSmem L;
-    L.layout(bp.maxP, bp.maxW, bp.maxNS);
+    const BeamSmem &L = bp.L;
     double *nd_score = reinterpret_cast<double *>(smem + L.off_nd_score);     // [2][W]
     double *nd_err = reinterpret_cast<double *>(smem + L.off_nd_err);         // [2][W][P]
     uint16_t *nd_ref = reinterpret_cast<uint16_t *>(smem + L.off_nd_ref);     // [2][W][P]
@@ -186,7 +185,15 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
     const RExtra *__restrict__ rextra = bp.rextra + in.read_off;
 
     // chunks of CH groups are dealt round-robin to the CTAs: the first chunk >= cA that this CTA owns
-    auto my_first_chunk = [&](uint32_t cA) { return cA + ((cta + G - cA % G) % G); };
+    // (divisions by the grid size are on every warp's path several times per step: multiply by a 42-bit reciprocal instead,
+    //  exact for numerators below 2^28 and grids of up to 1024 CTAs)
+    const unsigned long long g_recip = ((1ULL << 42) + G - 1) / G;
+    auto div_g = [&](uint32_t n) { return (uint32_t)(((unsigned long long)n * g_recip) >> 42); };
+    auto my_first_chunk = [&](uint32_t cA) {
+        uint32_t t = cta + G - (cA - div_g(cA) * G);  // in [1, 2 G)
+        if (t >= G) t -= G;
+        return cA + t;
+    };
 
     // ---- init: one root node over the empty state (global_clustering.rs:29-47) ---------------------------------------
     fb_grid_barrier(bp.wbar, bar_target += G);  // the previous instance's readers of the step slots are done
@@ -270,7 +277,7 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
     auto my_groups = [&](const RInfo &r, uint32_t &c0) {
         const uint32_t cA = r.lg0 / CH, cB = (r.lg1 - 1) / CH;
         c0 = my_first_chunk(cA);
-        return c0 <= cB ? ((cB - c0) / G + 1) * CH : 0u;  // group slots of my chunks (the ends may fall outside the read)
+        return c0 <= cB ? (div_g(cB - c0) + 1) * CH : 0u;  // group slots of my chunks (the ends may fall outside the read)
     };
     // The planes of read t + 1 are fetched while warp 0 runs the p-values and the decision section of step t (the DRAM
     // latency falls into the time the other warps would wait for the job list anyway), two groups per thread in flight.
@@ -610,7 +617,7 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
                 const int ghi = pass == 0 ? gmax_new : (int)ri.lg1 - 1;
                 const uint32_t cA = (uint32_t)glo / CH, cB = (uint32_t)ghi / CH;
                 const uint32_t c0 = my_first_chunk(cA);
-                const int nmc = c0 <= cB ? (int)((cB - c0) / G + 1) : 0;
+                const int nmc = c0 <= cB ? (int)(div_g(cB - c0) + 1) : 0;
                 const int total = nj * nmc;  // one warp pass per (job, chunk)
                 // two passes in flight per warp: the loads of both are issued before either is finished
                 struct CItem {
@@ -626,7 +633,7 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
                 BeamWideAcc *accn = bp.wacc + (uint64_t)((step + 1) % FB_BW_SLOTS) * bp.maxNS;
                 const uint32_t c0n = my_first_chunk(ri_next.lg0 / CH);  // this CTA's first chunk of the next read
                 auto c_load = [&](int x, CItem &it) {
-                    const int jn = x / nmc, kc = x - jn * nmc;
+                    const int jn = nj == 1 ? 0 : x / nmc, kc = x - jn * nmc;  // (one job per step is the steady state)
                     const BeamJob jb = pass == 0 ? jobs[jn] : jobs[(int)Wm + 1 - jn];
                     it.src = jb.src;
                     it.dst = jb.dst;
@@ -694,7 +701,7 @@ __device__ __noinline__ void fb_beam_wide_instance(const BeamParams &bp, const i
                         int ds = 0, de = 0;  // change of "same" (+1 / -1) and of "empty" (-1: a position can only fill up)
                         int pe = INT_MAX, pd = -1;  // position if the cell is empty / a diff under the new planes
                         if (it.act && it.lg >= (int)ri_next.lg0 && it.lg < (int)ri_next.lg1) {
-                            const uint32_t gi = (((uint32_t)it.lg / CH - c0n) / G) * CH + (uint32_t)it.lg % CH;  // staging slot
+                            const uint32_t gi = div_g((uint32_t)it.lg / CH - c0n) * CH + (uint32_t)it.lg % CH;  // staging slot
                             uint32_t pr, al, qb;
                             if (gi < STG) {
                                 pr = rpr[gi];
@@ -852,8 +859,7 @@ __global__ void __launch_bounds__(FB_BW_THREADS, 1) k_beam_wide(BeamParams bp) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int tid = threadIdx.x;
     {
-        BeamSmem L;
-        L.layout(bp.maxP, bp.maxW, bp.maxNS);
+        const BeamSmem &L = bp.L;
         uint32_t *lut_s = reinterpret_cast<uint32_t *>(smem + L.off_lut);
         for (int i = tid; i < 256; i += FB_BW_THREADS) lut_s[i] = bp.lut[i];
     }
