@@ -44,7 +44,7 @@ C3_DESC = ("configs[2]: synthetic 1 contig, 100k full-span frags x 50k SNPs, plo
 C5 = dict(n_contigs=500, n_reads=2000, n_snps=1000, max_ploidy=6, epsilon=0.04)
 C5_DESC = ("configs[4]: synthetic metagenome, 500 contigs / 1M frags / 500k SNPs, mixed ploidy 2-6 (max ploidy 6), "
            "contig-sharded by a static LPT queue, one batched fb_phase_contigs call per GPU")
-CPU_SAMPLE_READS = 8  # reads per CPU thread of the configs[2] sample (~10-15 s of oracle time per thread and step)
+CPU_SAMPLE_READS = int(os.environ.get("FB_BENCH_CPU_READS", "8"))  # reads per CPU thread of the configs[2] sample (~10-15 s of oracle time per thread and step; the override is for the contract test)
 
 
 def hbm_peak():
@@ -183,7 +183,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = int(os.environ.get("FB_BENCH_CPU_THREADS", "0")) or os.cpu_count() or 1
     if args.gpus <= 1:
         prm = c3_params()
         frags, slices, sample = c3_cpu_sample(threads)
