@@ -33,3 +33,11 @@ def test_reference_arm_line_at_n1():
 
 def test_reference_arm_prints_on_rank_0_only():
     assert run_reference({"RANK": "1", "WORLD_SIZE": "2"}, ["--gpus", "2"]) == []
+
+
+def test_reference_arm_line_at_n2_is_the_sharded_workload():
+    lines = run_reference({"RANK": "0", "WORLD_SIZE": "2"}, ["--gpus", "2"])
+    d = json.loads(lines[-1])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["scaling"] == "strong"
+    assert d["config"]["workload"].startswith("configs[4]") and d["config"]["n_contigs"] == 500
+    assert d["cpu_baseline"]["cores"] == 2 and "contigs" in d["cpu_baseline"]["sample"] and d["value"] > 0
