@@ -25,6 +25,7 @@ N > 1 (torchrun, one rank per GPU): BASELINE.json configs[4], the 500-contig met
 import argparse
 import json
 import os
+import shutil
 import statistics
 import sys
 import threading
@@ -222,7 +223,11 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f64 (reference arithmetic)", "data": "synthetic", "config": config,
-            "cpu_baseline": {"value": value, "unit": "cells/s", "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "cells/s", "cores": threads, "kind": "port", "sample": sample,
+                             # BASELINE.md "Baseline B": the real floria needs cargo + 236 crates (no network here); probed at run time
+                             "rust_toolchain": {"cargo": shutil.which("cargo") is not None, "rustc": shutil.which("rustc") is not None},
+                             "why_port": "the reference is Rust and cannot be built on this box (tools/pin_with_floria.sh builds and "
+                                         "diffs it wherever a toolchain and the crates exist); the arm times the C++ restatement"},
             "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 

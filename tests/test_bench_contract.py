@@ -27,6 +27,7 @@ def test_reference_arm_line_at_n1():
     assert d["config"]["workload"].startswith("configs[2]") and d["config"]["n_reads"] == 100000 and d["config"]["ploidy"] == 4
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] == 2 and cb["value"] == d["value"] and "slices of 2 consecutive" in cb["sample"]
+    assert set(cb["rust_toolchain"]) == {"cargo", "rustc"} and "restatement" in cb["why_port"]
     e = d["e2e"]
     assert e["value"] == d["value"] and e["unit"] == d["unit"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
 
